@@ -1,0 +1,413 @@
+// 753-bit prime-field arithmetic (Fq / Fr of MNT4753 and MNT6753) and the Fq2 / Fq3 towers used by G2.
+//
+// One field element = 24 little-endian u32 limbs = 96 bytes, Montgomery form x*2^768 mod p, always fully reduced,
+// i.e. bit-compatible with the reference's on-disk / in-memory encoding (libsnark/serialization.hpp:22-32,
+// depends/libff/libff/algebra/fields/fp.tcc:161-186).
+//
+// The same formulas compile for host and device:
+//   * device: one thread owns one element; the multiply is the generated IMAD.WIDE chain in fp_ptx_gen.cuh, kept
+//     out-of-line (one copy of the ~1.3k-instruction body per modulus) and fed from memory-resident operands.
+//   * host  : portable 12 x u64 CIOS with unsigned __int128 - used for the O(1) serial tails of the prover
+//     (window combine, r*Bt1, to-affine inversion) and by the CPU-side unit tests of the shared formulas.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "constants_gen.h"
+
+#if defined(__CUDACC__)
+#include "fp_ptx_gen.cuh"
+#define B200_DEV __device__
+#define B200_INLINE __forceinline__
+#else
+#define B200_DEV
+#define B200_INLINE inline
+#endif
+
+namespace b200 {
+
+constexpr int kLimbs = 24;
+
+// ------------------------------------------------------------------------------------------------ base field
+template <class P>
+struct alignas(16) Fp {
+  uint32_t l[kLimbs];
+  typedef P Prime;
+  static constexpr int kDegree = 1;
+
+  B200_HD static void set_zero(Fp &r) {
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) r.l[i] = 0;
+  }
+  B200_HD static void set_one(Fp &r) {
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) r.l[i] = P::one(i);
+  }
+  B200_HD static bool is_zero(const Fp &a) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) acc |= a.l[i];
+    return acc == 0;
+  }
+  B200_HD static bool eq(const Fp &a, const Fp &b) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) acc |= (a.l[i] ^ b.l[i]);
+    return acc == 0;
+  }
+
+  // ---------------------------------------------------------------- host implementations (u64 limbs)
+#if !defined(__CUDA_ARCH__)
+  static inline uint64_t p64(int i) { return (uint64_t)P::p(2 * i) | ((uint64_t)P::p(2 * i + 1) << 32); }
+  static inline uint64_t ld64(const Fp &a, int i) { return (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32); }
+  static inline void st64(Fp &r, int i, uint64_t v) {
+    r.l[2 * i] = (uint32_t)v;
+    r.l[2 * i + 1] = (uint32_t)(v >> 32);
+  }
+  static inline void host_cond_sub_p(uint64_t *t) {  // t in [0, 2p) -> [0, p)
+    uint64_t u[12];
+    unsigned __int128 brw = 0;
+    for (int i = 0; i < 12; i++) {
+      unsigned __int128 d = (unsigned __int128)t[i] - p64(i) - (uint64_t)brw;
+      u[i] = (uint64_t)d;
+      brw = (d >> 64) & 1;
+    }
+    if (!brw)
+      for (int i = 0; i < 12; i++) t[i] = u[i];
+  }
+  static inline void host_add(Fp &r, const Fp &a, const Fp &b) {
+    uint64_t t[12];
+    unsigned __int128 c = 0;
+    for (int i = 0; i < 12; i++) {
+      c += (unsigned __int128)ld64(a, i) + ld64(b, i);
+      t[i] = (uint64_t)c;
+      c >>= 64;
+    }
+    host_cond_sub_p(t);
+    for (int i = 0; i < 12; i++) st64(r, i, t[i]);
+  }
+  static inline void host_sub(Fp &r, const Fp &a, const Fp &b) {
+    uint64_t t[12];
+    unsigned __int128 brw = 0;
+    for (int i = 0; i < 12; i++) {
+      unsigned __int128 d = (unsigned __int128)ld64(a, i) - ld64(b, i) - (uint64_t)brw;
+      t[i] = (uint64_t)d;
+      brw = (d >> 64) & 1;
+    }
+    if (brw) {
+      unsigned __int128 c = 0;
+      for (int i = 0; i < 12; i++) {
+        c += (unsigned __int128)t[i] + p64(i);
+        t[i] = (uint64_t)c;
+        c >>= 64;
+      }
+    }
+    for (int i = 0; i < 12; i++) st64(r, i, t[i]);
+  }
+  static inline void host_mul(Fp &r, const Fp &a, const Fp &b) {
+    // CIOS Montgomery, 12 x u64, inv64 derived from the 32-bit constant by one Newton step.
+    static const uint64_t inv64 = []() {
+      uint64_t p0 = p64(0), x = 1;  // x = p0^-1 mod 2^64
+      for (int i = 0; i < 6; i++) x *= 2 - p0 * x;
+      return (uint64_t)(0 - x);
+    }();
+    uint64_t t[14];
+    for (int i = 0; i < 14; i++) t[i] = 0;
+    uint64_t av[12], bv[12], pv[12];
+    for (int i = 0; i < 12; i++) {
+      av[i] = ld64(a, i);
+      bv[i] = ld64(b, i);
+      pv[i] = p64(i);
+    }
+    for (int i = 0; i < 12; i++) {
+      unsigned __int128 c = 0;
+      for (int j = 0; j < 12; j++) {
+        c += (unsigned __int128)av[j] * bv[i] + t[j];
+        t[j] = (uint64_t)c;
+        c >>= 64;
+      }
+      c += t[12];
+      t[12] = (uint64_t)c;
+      t[13] = (uint64_t)(c >> 64);
+      uint64_t m = t[0] * inv64;
+      c = (unsigned __int128)m * pv[0] + t[0];
+      c >>= 64;
+      for (int j = 1; j < 12; j++) {
+        c += (unsigned __int128)m * pv[j] + t[j];
+        t[j - 1] = (uint64_t)c;
+        c >>= 64;
+      }
+      c += t[12];
+      t[11] = (uint64_t)c;
+      t[12] = t[13] + (uint64_t)(c >> 64);
+    }
+    host_cond_sub_p(t);
+    for (int i = 0; i < 12; i++) st64(r, i, t[i]);
+  }
+#endif
+
+  // ---------------------------------------------------------------- dispatch
+  B200_HD static B200_INLINE void add(Fp &r, const Fp &a, const Fp &b) {
+#if defined(__CUDA_ARCH__)
+    if (P::kTag == 'A')
+      fp_add_ptx_A(r.l, a.l, b.l);
+    else
+      fp_add_ptx_B(r.l, a.l, b.l);
+#else
+    host_add(r, a, b);
+#endif
+  }
+  B200_HD static B200_INLINE void sub(Fp &r, const Fp &a, const Fp &b) {
+#if defined(__CUDA_ARCH__)
+    if (P::kTag == 'A')
+      fp_sub_ptx_A(r.l, a.l, b.l);
+    else
+      fp_sub_ptx_B(r.l, a.l, b.l);
+#else
+    host_sub(r, a, b);
+#endif
+  }
+  B200_HD static B200_INLINE void dbl(Fp &r, const Fp &a) { add(r, a, a); }
+  B200_HD static B200_INLINE void neg(Fp &r, const Fp &a) {
+    Fp z;
+    set_zero(z);
+    sub(r, z, a);
+  }
+#if defined(__CUDACC__)
+  // out-of-line device multiply: operands come from (local/shared/global) memory, limbs live in registers only
+  // inside the body. One copy per modulus per module keeps the instruction footprint inside the 32 KB L1.5 I-cache.
+  static __device__ __noinline__ void mul_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) {
+      x[i] = a[i];
+      y[i] = b[i];
+    }
+    if (P::kTag == 'A')
+      fp_mul_ptx_A(z, x, y);
+    else
+      fp_mul_ptx_B(z, x, y);
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) r[i] = z[i];
+  }
+#endif
+  B200_HD static B200_INLINE void mul(Fp &r, const Fp &a, const Fp &b) {
+#if defined(__CUDA_ARCH__)
+    mul_dev(r.l, a.l, b.l);
+#else
+    host_mul(r, a, b);
+#endif
+  }
+  B200_HD static B200_INLINE void sqr(Fp &r, const Fp &a) { mul(r, a, a); }
+
+  // r = k*a for a small compile-time constant k (double-and-add; used for curve a, non-residues 13 / 11)
+  template <unsigned K>
+  B200_HD static B200_INLINE void mul_small(Fp &r, const Fp &a) {
+    static_assert(K >= 1 && K < 256, "small constant");
+    Fp acc = a, base = a;
+    int top = 7;
+    while (!((K >> top) & 1)) top--;
+    for (int bit = top - 1; bit >= 0; bit--) {
+      dbl(acc, acc);
+      if ((K >> bit) & 1) add(acc, acc, base);
+    }
+    r = acc;
+  }
+
+  // Montgomery <-> integer
+  B200_HD static void from_mont(Fp &r, const Fp &a) {
+    Fp one_int;
+    set_zero(one_int);
+    one_int.l[0] = 1;
+    mul(r, a, one_int);
+  }
+  B200_HD static void to_mont(Fp &r, const Fp &a) {
+    Fp r2;
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) r2.l[i] = P::r2(i);
+    mul(r, a, r2);
+  }
+  // r = a^e, e given as little-endian u32 words (plain integer)
+  B200_HD static void pow_words(Fp &r, const Fp &a, const uint32_t *e, int nwords) {
+    Fp acc;
+    set_one(acc);
+    bool started = false;
+    for (int w = nwords - 1; w >= 0; w--) {
+      for (int bit = 31; bit >= 0; bit--) {
+        if (started) sqr(acc, acc);
+        if ((e[w] >> bit) & 1) {
+          if (started)
+            mul(acc, acc, a);
+          else {
+            acc = a;
+            started = true;
+          }
+        }
+      }
+    }
+    r = acc;
+  }
+  // r = a^-1 (Fermat, a^(p-2)); a != 0. The reference uses an extended gcd (fp.tcc:641-685); the inverse is unique.
+  B200_HD static void inv(Fp &r, const Fp &a) {
+    uint32_t e[kLimbs];
+    for (int i = 0; i < kLimbs; i++) e[i] = P::p(i);
+    e[0] -= 2;  // p is odd and p mod 2^32 >= 3, no borrow
+    pow_words(r, a, e, kLimbs);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ Fq2 = Fq[u]/(u^2 - 13)
+// (depends/libff/libff/algebra/fields/fp2.tcc:78-126; non-residue 13: mnt4753_init.cpp:105)
+template <class P, unsigned NR>
+struct alignas(16) Fp2 {
+  typedef Fp<P> B;
+  typedef P Prime;
+  static constexpr int kDegree = 2;
+  B c0, c1;
+
+  B200_HD static void set_zero(Fp2 &r) { B::set_zero(r.c0); B::set_zero(r.c1); }
+  B200_HD static void set_one(Fp2 &r) { B::set_one(r.c0); B::set_zero(r.c1); }
+  B200_HD static bool is_zero(const Fp2 &a) { return B::is_zero(a.c0) && B::is_zero(a.c1); }
+  B200_HD static bool eq(const Fp2 &a, const Fp2 &b) { return B::eq(a.c0, b.c0) && B::eq(a.c1, b.c1); }
+  B200_HD static void add(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::add(r.c0, a.c0, b.c0); B::add(r.c1, a.c1, b.c1); }
+  B200_HD static void sub(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::sub(r.c0, a.c0, b.c0); B::sub(r.c1, a.c1, b.c1); }
+  B200_HD static void dbl(Fp2 &r, const Fp2 &a) { B::dbl(r.c0, a.c0); B::dbl(r.c1, a.c1); }
+  B200_HD static void neg(Fp2 &r, const Fp2 &a) { B::neg(r.c0, a.c0); B::neg(r.c1, a.c1); }
+  B200_HD static void mul(Fp2 &r, const Fp2 &a, const Fp2 &b) {  // Karatsuba, 3 base multiplications
+    B aA, bB, s, t;
+    B::mul(aA, a.c0, b.c0);
+    B::mul(bB, a.c1, b.c1);
+    B::add(s, a.c0, a.c1);
+    B::add(t, b.c0, b.c1);
+    B::mul(s, s, t);
+    B::sub(s, s, aA);
+    B::sub(r.c1, s, bB);
+    B::template mul_small<NR>(t, bB);
+    B::add(r.c0, aA, t);
+  }
+  B200_HD static void sqr(Fp2 &r, const Fp2 &a) {  // complex squaring, 2 base multiplications
+    B ab, s, t;
+    B::mul(ab, a.c0, a.c1);
+    B::add(s, a.c0, a.c1);
+    B::template mul_small<NR>(t, a.c1);
+    B::add(t, t, a.c0);
+    B::mul(s, s, t);
+    B::sub(s, s, ab);
+    B::template mul_small<NR>(t, ab);
+    B::sub(r.c0, s, t);
+    B::dbl(r.c1, ab);
+  }
+  B200_HD static void inv(Fp2 &r, const Fp2 &a) {  // fp2.tcc:128-142
+    B t0, t1, t2;
+    B::sqr(t0, a.c0);
+    B::sqr(t1, a.c1);
+    B::template mul_small<NR>(t1, t1);
+    B::sub(t2, t0, t1);
+    B::inv(t2, t2);
+    B::mul(r.c0, a.c0, t2);
+    B::mul(t0, a.c1, t2);
+    B::neg(r.c1, t0);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ Fq3 = Fq[u]/(u^3 - 11)
+// (depends/libff/libff/algebra/fields/fp3.tcc:82-123; non-residue 11: mnt6753_init.cpp:109)
+template <class P, unsigned NR>
+struct alignas(16) Fp3 {
+  typedef Fp<P> B;
+  typedef P Prime;
+  static constexpr int kDegree = 3;
+  B c0, c1, c2;
+
+  B200_HD static void set_zero(Fp3 &r) { B::set_zero(r.c0); B::set_zero(r.c1); B::set_zero(r.c2); }
+  B200_HD static void set_one(Fp3 &r) { B::set_one(r.c0); B::set_zero(r.c1); B::set_zero(r.c2); }
+  B200_HD static bool is_zero(const Fp3 &a) { return B::is_zero(a.c0) && B::is_zero(a.c1) && B::is_zero(a.c2); }
+  B200_HD static bool eq(const Fp3 &a, const Fp3 &b) {
+    return B::eq(a.c0, b.c0) && B::eq(a.c1, b.c1) && B::eq(a.c2, b.c2);
+  }
+  B200_HD static void add(Fp3 &r, const Fp3 &a, const Fp3 &b) {
+    B::add(r.c0, a.c0, b.c0); B::add(r.c1, a.c1, b.c1); B::add(r.c2, a.c2, b.c2);
+  }
+  B200_HD static void sub(Fp3 &r, const Fp3 &a, const Fp3 &b) {
+    B::sub(r.c0, a.c0, b.c0); B::sub(r.c1, a.c1, b.c1); B::sub(r.c2, a.c2, b.c2);
+  }
+  B200_HD static void dbl(Fp3 &r, const Fp3 &a) { B::dbl(r.c0, a.c0); B::dbl(r.c1, a.c1); B::dbl(r.c2, a.c2); }
+  B200_HD static void neg(Fp3 &r, const Fp3 &a) { B::neg(r.c0, a.c0); B::neg(r.c1, a.c1); B::neg(r.c2, a.c2); }
+  B200_HD static void mul(Fp3 &r, const Fp3 &a, const Fp3 &b) {  // Karatsuba, 6 base multiplications
+    B aA, bB, cC, s, t, u;
+    B::mul(aA, a.c0, b.c0);
+    B::mul(bB, a.c1, b.c1);
+    B::mul(cC, a.c2, b.c2);
+    // c0 = aA + nr*((b+c)(B+C) - bB - cC)
+    B::add(s, a.c1, a.c2);
+    B::add(t, b.c1, b.c2);
+    B::mul(s, s, t);
+    B::sub(s, s, bB);
+    B::sub(s, s, cC);
+    B::template mul_small<NR>(s, s);
+    // c1 = (a+b)(A+B) - aA - bB + nr*cC
+    B::add(t, a.c0, a.c1);
+    B::add(u, b.c0, b.c1);
+    B::mul(t, t, u);
+    B::sub(t, t, aA);
+    B::sub(t, t, bB);
+    B::template mul_small<NR>(u, cC);
+    B::add(t, t, u);
+    // c2 = (a+c)(A+C) - aA + bB - cC
+    B u2, v2;
+    B::add(u2, a.c0, a.c2);
+    B::add(v2, b.c0, b.c2);
+    B::mul(u2, u2, v2);
+    B::sub(u2, u2, aA);
+    B::add(u2, u2, bB);
+    B::sub(r.c2, u2, cC);
+    B::add(r.c0, aA, s);
+    r.c1 = t;
+  }
+  B200_HD static void sqr(Fp3 &r, const Fp3 &a) {  // CH-SQR2: 3 squarings + 2 multiplications
+    B s0, s1, s2, s3, s4, t;
+    B::sqr(s0, a.c0);
+    B::mul(s1, a.c0, a.c1);
+    B::dbl(s1, s1);
+    B::sub(t, a.c0, a.c1);
+    B::add(t, t, a.c2);
+    B::sqr(s2, t);
+    B::mul(s3, a.c1, a.c2);
+    B::dbl(s3, s3);
+    B::sqr(s4, a.c2);
+    // c0 = s0 + nr*s3 ; c1 = s1 + nr*s4 ; c2 = s1 + s2 + s3 - s0 - s4
+    B::template mul_small<NR>(t, s3);
+    B::add(r.c0, s0, t);
+    B::template mul_small<NR>(t, s4);
+    B::add(r.c1, s1, t);
+    B::add(t, s1, s2);
+    B::add(t, t, s3);
+    B::sub(t, t, s0);
+    B::sub(r.c2, t, s4);
+  }
+  B200_HD static void inv(Fp3 &r, const Fp3 &a) {  // fp3.tcc:125-143
+    B t0, t1, t2, t3, t4, t5, c0, c1, c2, t6, u;
+    B::sqr(t0, a.c0);
+    B::sqr(t1, a.c1);
+    B::sqr(t2, a.c2);
+    B::mul(t3, a.c0, a.c1);
+    B::mul(t4, a.c0, a.c2);
+    B::mul(t5, a.c1, a.c2);
+    B::template mul_small<NR>(u, t5);
+    B::sub(c0, t0, u);
+    B::template mul_small<NR>(u, t2);
+    B::sub(c1, u, t3);
+    B::sub(c2, t1, t4);
+    B::mul(t6, a.c0, c0);
+    B::mul(t0, a.c2, c1);
+    B::mul(t1, a.c1, c2);
+    B::add(t0, t0, t1);
+    B::template mul_small<NR>(t0, t0);
+    B::add(t6, t6, t0);
+    B::inv(t6, t6);
+    B::mul(r.c0, t6, c0);
+    B::mul(r.c1, t6, c1);
+    B::mul(r.c2, t6, c2);
+  }
+};
+
+}  // namespace b200
