@@ -1,0 +1,136 @@
+/*
+ * b200_groth16.h - C-ABI of the B200-native Groth16 prover hot path for MNT4753 / MNT6753.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. It is what the reference's
+ * `B::` wrapper layer (libsnark/prover_reference_include/prover_reference_functions.hpp:5-162, implemented on the
+ * CPU by libsnark/prover_reference_functions.cpp) binds to in this repo; each entry point cites the reference
+ * interface it replaces. INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - field element: 96 bytes = 12 LE u64 limbs, Montgomery form x*2^768 mod p, canonical
+ *     (libsnark/serialization.hpp:22-32).
+ *   - G1 affine point: 192 B (x, y); G2 affine: 384 B (MNT4753, Fq2) / 576 B (MNT6753, Fq3); y == 0 encodes the
+ *     point at infinity (serialization.hpp:43-67, 83-111).
+ *   - projective point (X:Y:Z), O = (0:1:0): 3 coordinates of the same field, i.e. 288 B (G1), 576 B / 864 B (G2).
+ *   - `d_` pointers are device memory of the current device, `h_` pointers are host memory.
+ *   - every function returns 0 on success; on failure a negative code, and b200_last_error() describes it.
+ *     There is no CPU fallback: without a usable CUDA device every compute entry point fails.
+ */
+#ifndef B200_GROTH16_H
+#define B200_GROTH16_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_MNT4753 0
+#define B200_MNT6753 1
+#define B200_FE_BYTES 96
+
+/* ---- runtime ------------------------------------------------------------------------------------------------ */
+const char *b200_version(void);
+const char *b200_last_error(void);
+int b200_device_count(void);
+int b200_set_device(int ordinal);
+int b200_sync(void);
+int b200_malloc(void **d_ptr, size_t bytes);
+int b200_free(void *d_ptr);
+int b200_host_alloc(void **h_ptr, size_t bytes); /* pinned */
+int b200_host_free(void *h_ptr);
+int b200_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes);
+int b200_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes);
+int b200_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes);
+int b200_memset_zero(void *d_ptr, size_t bytes);
+
+/* ---- Fr vectors (elements of the scalar field of `curve`) -------------------------------------------------- */
+/* a[i] *= b[i]          replaces B::vector_Fr_muleq  (prover_reference_functions.cpp:170-180 / 485-495) */
+int b200_fr_muleq(int curve, void *d_a, const void *d_b, size_t n);
+/* a[i] -= b[i]          replaces B::vector_Fr_subeq  (prover_reference_functions.cpp:182-192 / 497-507) */
+int b200_fr_subeq(int curve, void *d_a, const void *d_b, size_t n);
+
+/* ---- evaluation domain (basic radix-2, libfqfft basic_radix2_domain.tcc:25-134) ------------------------------ */
+typedef struct b200_domain b200_domain;
+/* replaces B::get_evaluation_domain (prover_reference_functions.cpp:157-161); m must be a power of two <= 2^s */
+int b200_domain_create(int curve, size_t m, b200_domain **out);
+int b200_domain_destroy(b200_domain *dom);
+size_t b200_domain_size(const b200_domain *dom); /* B::domain_get_m */
+int b200_domain_fft(b200_domain *dom, void *d_a);       /* basic_radix2_domain::FFT       (:62-68)  */
+int b200_domain_ifft(b200_domain *dom, void *d_a);      /* B::domain_iFFT                  (:70-82)  */
+int b200_domain_coset_fft(b200_domain *dom, void *d_a); /* B::domain_cosetFFT, g = 17      (:84-89)  */
+int b200_domain_icoset_fft(b200_domain *dom, void *d_a);/* B::domain_icosetFFT             (:91-96)  */
+int b200_domain_divide_by_z_on_coset(b200_domain *dom, void *d_a); /* B::domain_divide_by_Z_on_coset (:125-134) */
+/* whole witness map, libsnark/main.cpp:104-163 == cuda_prover_piecewise.cu:18-53. ca/cb/cc (m elements each) are
+ * clobbered; d_out receives m+1 elements with out[m] = 0. */
+int b200_compute_h(b200_domain *dom, void *d_ca, void *d_cb, void *d_cc, void *d_out);
+
+/* ---- multi-scalar multiplication ---------------------------------------------------------------------------- */
+/* sum_i scalars[i] * points[i]. scalars: n Fr elements (Montgomery, as on disk); points: n affine points (wire
+ * format, infinity = y==0). Result: projective point written to HOST memory (288 / 576 / 864 B).
+ * replaces B::multiexp_G1 / B::multiexp_G2 (prover_reference_functions.cpp:247-265 / 553-571), i.e.
+ * libff::multi_exp_with_mixed_addition (multiexp.tcc:443-496). */
+int b200_msm_g1(int curve, const void *d_scalars, const void *d_points, size_t n, void *h_out_proj);
+int b200_msm_g2(int curve, const void *d_scalars, const void *d_points, size_t n, void *h_out_proj);
+/* tuning hook: force the Pippenger window width (0 = automatic) */
+int b200_msm_set_window(int c);
+
+/* ---- O(1) group / field helpers on HOST buffers (serial tail of the prover) --------------------------------- */
+int b200_g1_add(int curve, const void *h_p, const void *h_q, void *h_out);          /* B::G1_add   (:163-168) */
+int b200_g2_add(int curve, const void *h_p, const void *h_q, void *h_out);
+int b200_g1_scale(int curve, const void *h_fr, const void *h_p, void *h_out);       /* B::G1_scale (:150-155) */
+int b200_g2_scale(int curve, const void *h_fr, const void *h_p, void *h_out);
+int b200_g1_to_affine(int curve, const void *h_p, void *h_out_xy);                  /* write_g1 (serialization.hpp:43-54) */
+int b200_g2_to_affine(int curve, const void *h_p, void *h_out_xy);                  /* write_g2 (serialization.hpp:56-67) */
+int b200_g1_from_affine(int curve, const void *h_xy, void *h_out_proj);             /* read_g1  (serialization.hpp:83-91) */
+int b200_g2_from_affine(int curve, const void *h_xy, void *h_out_proj);
+/* host field ops (tag 0 = modulus A, 1 = modulus B); op: 0 add 1 sub 2 mul 3 inv 4 from_mont 5 to_mont */
+int b200_host_fp_op(int tag, int op, const void *h_a, const void *h_b, void *h_r);
+
+/* ---- proving key resident on the device + whole-proof entry point ------------------------------------------ */
+typedef struct b200_params b200_params;
+/* h_image = byte image of a parameter file (libsnark/main.cpp:42-61): d, m, A[m+1], B1[m+1], B2[m+1], L[m-1], H[d].
+ * replaces B::read_params (prover_reference_functions.cpp:291-345) */
+int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_params **out);
+/* adopt caller-owned device arrays (synthetic keys built on the device) */
+int b200_params_from_device(int curve, size_t d, size_t m, const void *d_A, const void *d_B1, const void *d_B2,
+                            const void *d_L, const void *d_H, b200_params **out);
+int b200_params_destroy(b200_params *p);
+size_t b200_params_d(const b200_params *p);
+size_t b200_params_m(const b200_params *p);
+const void *b200_params_query(const b200_params *p, int which); /* 0 A, 1 B1, 2 B2, 3 L, 4 H (device pointers) */
+
+typedef struct {
+  double h2d_ms, compute_h_ms, msm_a_ms, msm_b1_ms, msm_b2_ms, msm_h_ms, msm_l_ms, tail_ms, total_ms;
+} b200_prove_timings;
+/* One proof: h_input = byte image of an input file (libsnark/main.cpp:63-83): w[m+1], ca, cb, cc [d+1 each], r.
+ * h_out receives A (G1) | B (G2) | C (G1) in wire format (768 B MNT4753 / 960 B MNT6753), main.cpp:85-101,187-272.
+ * The input is copied host->device inside the call; timings (optional) are wall-clock per phase.
+ * range_lo/range_hi (in [0,1]) select the fraction of every MSM's point range this call sums - (0,1) for a whole
+ * proof; for multi-GPU sharding each rank passes its slice and gets PARTIAL projective sums in h_partials
+ * (5 points: A, B1, B2(G2), H, L) instead of a finished proof when h_out == NULL. */
+int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_out, size_t *out_bytes,
+               b200_prove_timings *timings);
+int b200_prove_partial(b200_params *p, const void *h_input, size_t input_bytes, int rank, int world,
+                       void *h_partials, size_t *partial_bytes, b200_prove_timings *timings);
+/* combine `world` partial results (rank-major, as produced by b200_prove_partial) into the final proof */
+int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
+                       size_t *out_bytes);
+
+/* ---- test / bench hooks: element-wise application of the device primitives the kernels are built from ------- */
+/* op: 0 add 1 sub 2 mul 3 sqr 4 from_mont 5 to_mont 6 inv ; tag: 0 = modulus A, 1 = modulus B */
+int b200_dev_fp_op(int tag, int op, const void *d_a, const void *d_b, void *d_r, size_t n);
+/* G2 coordinate-field op (Fq2 for MNT4753, Fq3 for MNT6753). op: 0 add 1 sub 2 mul 3 sqr */
+int b200_dev_fqe_op(int curve, int op, const void *d_a, const void *d_b, void *d_r, size_t n);
+/* group: 1 = G1, 2 = G2. op: 0 add(proj,proj) 1 dbl(proj) 2 mixed_add(proj, affine) 3 to_affine(proj)->affine */
+int b200_dev_group_op(int curve, int group, int op, const void *d_p, const void *d_q, void *d_r, size_t n);
+/* synthetic bases: out[i] = (first + i) * G  in affine wire format, G = the curve's G1/G2 generator */
+int b200_gen_points(int curve, int group, void *d_out_affine, size_t n, uint64_t first);
+/* IMAD roofline microbenchmark: independent IMAD.WIDE chains on every SM; returns MAC32/s */
+int b200_imad_peak(double *mac32_per_s, double *ms);
+/* time of the last MSM phases (ms): 0 digits, 1 sort, 2 accumulate, 3 reduce, 4 host tail */
+int b200_msm_last_phase_ms(double *out5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,314 @@
+"""B200-native Groth16 prover hot path for MNT4753 / MNT6753 (sm_100a CUDA kernels behind a C ABI).
+
+Python here is plumbing only: it loads ``libb200groth16.so`` (built in-tree by ``build.py``) with ctypes and exposes
+the C entry points of ``include/b200_groth16.h`` one-to-one, plus a few helpers that use torch for device memory.
+There is no CPU fallback: importing works anywhere, but every compute call fails loudly without the CUDA library
+or without a GPU.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200groth16.so")
+
+MNT4753, MNT6753 = 0, 1
+CURVE_NAMES = {MNT4753: "MNT4753", MNT6753: "MNT6753"}
+FE = 96  # bytes per field element (12 LE u64 limbs, Montgomery form)
+
+
+def g2_degree(curve):
+    return 2 if curve == MNT4753 else 3
+
+
+def affine_bytes(curve, group):
+    return 2 * FE * (1 if group == 1 else g2_degree(curve))
+
+
+def proj_bytes(curve, group):
+    return 3 * FE * (1 if group == 1 else g2_degree(curve))
+
+
+def proof_bytes(curve):
+    return 2 * affine_bytes(curve, 1) + affine_bytes(curve, 2)
+
+
+def partial_bytes(curve):
+    return 4 * proj_bytes(curve, 1) + proj_bytes(curve, 2)
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class ProveTimings(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in ("h2d_ms", "compute_h_ms", "msm_a_ms", "msm_b1_ms", "msm_b2_ms",
+                                               "msm_h_ms", "msm_l_ms", "tail_ms", "total_ms")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+_vp, _sz, _i, _u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
+_SIGNATURES = {
+    "b200_version": (ctypes.c_char_p, []),
+    "b200_last_error": (ctypes.c_char_p, []),
+    "b200_device_count": (_i, []),
+    "b200_set_device": (_i, [_i]),
+    "b200_sync": (_i, []),
+    "b200_malloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "b200_free": (_i, [_vp]),
+    "b200_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "b200_host_free": (_i, [_vp]),
+    "b200_memcpy_h2d": (_i, [_vp, _vp, _sz]),
+    "b200_memcpy_d2h": (_i, [_vp, _vp, _sz]),
+    "b200_memcpy_d2d": (_i, [_vp, _vp, _sz]),
+    "b200_memset_zero": (_i, [_vp, _sz]),
+    "b200_fr_muleq": (_i, [_i, _vp, _vp, _sz]),
+    "b200_fr_subeq": (_i, [_i, _vp, _vp, _sz]),
+    "b200_domain_create": (_i, [_i, _sz, ctypes.POINTER(_vp)]),
+    "b200_domain_destroy": (_i, [_vp]),
+    "b200_domain_size": (_sz, [_vp]),
+    "b200_domain_fft": (_i, [_vp, _vp]),
+    "b200_domain_ifft": (_i, [_vp, _vp]),
+    "b200_domain_coset_fft": (_i, [_vp, _vp]),
+    "b200_domain_icoset_fft": (_i, [_vp, _vp]),
+    "b200_domain_divide_by_z_on_coset": (_i, [_vp, _vp]),
+    "b200_compute_h": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b200_msm_g1": (_i, [_i, _vp, _vp, _sz, _vp]),
+    "b200_msm_g2": (_i, [_i, _vp, _vp, _sz, _vp]),
+    "b200_msm_set_window": (_i, [_i]),
+    "b200_msm_last_phase_ms": (_i, [ctypes.POINTER(ctypes.c_double)]),
+    "b200_g1_add": (_i, [_i, _vp, _vp, _vp]),
+    "b200_g2_add": (_i, [_i, _vp, _vp, _vp]),
+    "b200_g1_scale": (_i, [_i, _vp, _vp, _vp]),
+    "b200_g2_scale": (_i, [_i, _vp, _vp, _vp]),
+    "b200_g1_to_affine": (_i, [_i, _vp, _vp]),
+    "b200_g2_to_affine": (_i, [_i, _vp, _vp]),
+    "b200_g1_from_affine": (_i, [_i, _vp, _vp]),
+    "b200_g2_from_affine": (_i, [_i, _vp, _vp]),
+    "b200_host_fp_op": (_i, [_i, _i, _vp, _vp, _vp]),
+    "b200_params_from_host": (_i, [_i, _vp, _sz, ctypes.POINTER(_vp)]),
+    "b200_params_from_device": (_i, [_i, _sz, _sz, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "b200_params_destroy": (_i, [_vp]),
+    "b200_params_d": (_sz, [_vp]),
+    "b200_params_m": (_sz, [_vp]),
+    "b200_params_query": (_vp, [_vp, _i]),
+    "b200_prove": (_i, [_vp, _vp, _sz, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
+    "b200_prove_partial": (_i, [_vp, _vp, _sz, _i, _i, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
+    "b200_prove_combine": (_i, [_i, _vp, _i, _vp, _vp, ctypes.POINTER(_sz)]),
+    "b200_dev_fp_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
+    "b200_dev_fqe_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
+    "b200_dev_group_op": (_i, [_i, _i, _i, _vp, _vp, _vp, _sz]),
+    "b200_gen_points": (_i, [_i, _i, _vp, _sz, _u64]),
+    "b200_imad_peak": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Load the CUDA library (once). Raises B200Error if it has not been built - there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error("%s is missing: run `python -m snark_challenge_prover_reference_b200.build` "
+                            "(the CUDA library is the product; there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B200Error("b200 call failed (%d): %s" % (rc, lib().b200_last_error().decode()))
+
+
+def _ptr(x):
+    """Address of a bytes-like / ctypes buffer / torch tensor / int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(x)) if isinstance(x, bytes) else (ctypes.c_char * len(x)).from_buffer(x),
+                           ctypes.c_void_p).value
+    return ctypes.addressof(x)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host helpers (no GPU needed): the serial tail of the prover
+def host_fp_op(tag, op, a, b=None):
+    out = ctypes.create_string_buffer(FE)
+    ab = ctypes.create_string_buffer(bytes(a), FE)
+    bb = ctypes.create_string_buffer(bytes(b), FE) if b is not None else None
+    check(lib().b200_host_fp_op(tag, op, ctypes.addressof(ab), ctypes.addressof(bb) if bb else None,
+                                ctypes.addressof(out)))
+    return out.raw
+
+
+def _host_group(fname, curve, group, *bufs, out_len):
+    out = ctypes.create_string_buffer(out_len)
+    keep = [ctypes.create_string_buffer(bytes(b), len(b)) for b in bufs]
+    fn = getattr(lib(), fname % ("g1" if group == 1 else "g2"))
+    check(fn(curve, *[ctypes.addressof(k) for k in keep], ctypes.addressof(out)))
+    return out.raw
+
+
+def g_add(curve, group, p, q):
+    return _host_group("b200_%s_add", curve, group, p, q, out_len=proj_bytes(curve, group))
+
+
+def g_scale(curve, group, fr, p):
+    return _host_group("b200_%s_scale", curve, group, fr, p, out_len=proj_bytes(curve, group))
+
+
+def g_to_affine(curve, group, p):
+    return _host_group("b200_%s_to_affine", curve, group, p, out_len=affine_bytes(curve, group))
+
+
+def g_from_affine(curve, group, xy):
+    return _host_group("b200_%s_from_affine", curve, group, xy, out_len=proj_bytes(curve, group))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device helpers (torch uint8 tensors as device memory)
+def to_device(data, device="cuda:0"):
+    import torch
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8) if len(data) else torch.zeros(0, dtype=torch.uint8)
+    return t.to(device)
+
+
+def from_device(t):
+    return t.cpu().numpy().tobytes()
+
+
+def msm(curve, group, d_scalars, d_points, n):
+    """sum_i scalars[i]*points[i] -> projective point bytes (host). d_* are torch CUDA tensors or raw addresses."""
+    out = ctypes.create_string_buffer(proj_bytes(curve, group))
+    fn = lib().b200_msm_g1 if group == 1 else lib().b200_msm_g2
+    check(fn(curve, _ptr(d_scalars), _ptr(d_points), n, ctypes.addressof(out)))
+    return out.raw
+
+
+def msm_phase_ms():
+    arr = (ctypes.c_double * 5)()
+    check(lib().b200_msm_last_phase_ms(arr))
+    return dict(zip(("digits", "sort", "accumulate", "reduce", "host_tail"), list(arr)))
+
+
+class Domain:
+    """basic radix-2 evaluation domain over Fr of `curve` (B::get_evaluation_domain)."""
+
+    h = None
+
+    def __init__(self, curve, m):
+        h = ctypes.c_void_p()
+        check(lib().b200_domain_create(curve, m, ctypes.byref(h)))
+        self.h, self.curve, self.m = h, curve, m
+
+    def close(self):
+        if self.h:
+            lib().b200_domain_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def fft(self, a):
+        check(lib().b200_domain_fft(self.h, _ptr(a)))
+
+    def ifft(self, a):
+        check(lib().b200_domain_ifft(self.h, _ptr(a)))
+
+    def coset_fft(self, a):
+        check(lib().b200_domain_coset_fft(self.h, _ptr(a)))
+
+    def icoset_fft(self, a):
+        check(lib().b200_domain_icoset_fft(self.h, _ptr(a)))
+
+    def divide_by_z_on_coset(self, a):
+        check(lib().b200_domain_divide_by_z_on_coset(self.h, _ptr(a)))
+
+    def compute_h(self, ca, cb, cc, out):
+        check(lib().b200_compute_h(self.h, _ptr(ca), _ptr(cb), _ptr(cc), _ptr(out)))
+
+
+class Params:
+    """Proving key resident on the current device (B::read_params)."""
+
+    def __init__(self, curve, handle, keep=None):
+        self.curve, self.h, self._keep = curve, handle, keep
+
+    @classmethod
+    def from_bytes(cls, curve, image):
+        h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(bytes(image), len(image))
+        check(lib().b200_params_from_host(curve, ctypes.addressof(buf), len(image), ctypes.byref(h)))
+        return cls(curve, h)
+
+    @classmethod
+    def from_device(cls, curve, d, m, A, B1, B2, L, H):
+        h = ctypes.c_void_p()
+        check(lib().b200_params_from_device(curve, d, m, _ptr(A), _ptr(B1), _ptr(B2), _ptr(L), _ptr(H), ctypes.byref(h)))
+        return cls(curve, h, keep=(A, B1, B2, L, H))
+
+    @property
+    def d(self):
+        return lib().b200_params_d(self.h)
+
+    @property
+    def m(self):
+        return lib().b200_params_m(self.h)
+
+    def close(self):
+        if self.h:
+            lib().b200_params_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def prove(self, input_image, timings=False):
+        """One whole proof from a HOST input image; returns the proof bytes (A | B | C, wire format)."""
+        out = ctypes.create_string_buffer(proof_bytes(self.curve))
+        n = ctypes.c_size_t()
+        tm = ProveTimings()
+        check(lib().b200_prove(self.h, _ptr(input_image), _len(input_image), ctypes.addressof(out), ctypes.byref(n),
+                               ctypes.byref(tm)))
+        return (out.raw[:n.value], tm.as_dict()) if timings else out.raw[:n.value]
+
+    def prove_partial(self, input_image, rank, world):
+        out = ctypes.create_string_buffer(partial_bytes(self.curve))
+        n = ctypes.c_size_t()
+        tm = ProveTimings()
+        check(lib().b200_prove_partial(self.h, _ptr(input_image), _len(input_image), rank, world,
+                                       ctypes.addressof(out), ctypes.byref(n), ctypes.byref(tm)))
+        return out.raw[:n.value], tm.as_dict()
+
+
+def _len(x):
+    if hasattr(x, "numel"):
+        return x.numel() * x.element_size()
+    return len(x)
+
+
+def prove_combine(curve, partials_all, world, r_fr):
+    out = ctypes.create_string_buffer(proof_bytes(curve))
+    n = ctypes.c_size_t()
+    pb = ctypes.create_string_buffer(bytes(partials_all), len(partials_all))
+    rb = ctypes.create_string_buffer(bytes(r_fr), FE)
+    check(lib().b200_prove_combine(curve, ctypes.addressof(pb), world, ctypes.addressof(rb), ctypes.addressof(out),
+                                   ctypes.byref(n)))
+    return out.raw[:n.value]
+
+
+def imad_peak():
+    v = (ctypes.c_double * 2)()
+    ms = (ctypes.c_double * 2)()
+    check(lib().b200_imad_peak(v, ms))
+    return {"mad_wide_mac32_per_s": v[0], "carry_chain_mac32_per_s": v[1], "ms": [ms[0], ms[1]]}

@@ -1,0 +1,72 @@
+"""In-tree build of the CUDA library (sm_100a only): csrc/*.cu -> libb200groth16.so next to this file.
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels with the repo snapshot to the GPU box.
+    python -m snark_challenge_prover_reference_b200.build [--force]
+"""
+import concurrent.futures
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+ROOT = os.path.dirname(HERE)
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libb200groth16.so")
+SOURCES = ["msm.cu", "ntt.cu", "devops.cu", "capi.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+         "-ccbin", "/usr/bin/g++"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(ROOT, "include", "b200_groth16.h"))
+    return hs
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    path = os.path.join(CSRC, src)
+    if _newer(obj, [path] + _headers()):
+        return obj, ""
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout[-4000:], r.stderr[-8000:]))
+    return obj, r.stderr
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, f))
+        if os.path.exists(LIB):
+            os.remove(LIB)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+    objs = [o for o, _ in results]
+    logs = "\n".join(l for _, l in results if l)
+    if not _newer(LIB, objs):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart",
+                                                     "-ccbin", "/usr/bin/g++"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    return LIB, logs
+
+
+if __name__ == "__main__":
+    lib, logs = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if logs:
+        print(logs)
+    print("built", lib)

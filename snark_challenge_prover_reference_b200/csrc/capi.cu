@@ -1,0 +1,459 @@
+// extern "C" layer declared in include/b200_groth16.h: runtime plumbing, the O(1) host-side group operations of the
+// prover tail, the device-resident proving key and the whole-proof entry points.
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include "../../include/b200_groth16.h"
+#include "common.cuh"
+#include "curve.cuh"
+#include "devops.h"
+#include "msm.h"
+#include "ntt.h"
+
+namespace b200 {
+std::string &last_error() {
+  static thread_local std::string e;
+  return e;
+}
+int set_error(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- host group helpers, one instantiation per (curve, group) -------------------------------------------------
+template <class G>
+struct HostOps {
+  typedef typename G::F F;
+  typedef typename G::ScalarPrime FrP;
+  static void add(const void *p, const void *q, void *out) {
+    Proj<F> a, b, c;
+    memcpy(&a, p, sizeof(a));
+    memcpy(&b, q, sizeof(b));
+    proj_add<G>(c, a, b);
+    memcpy(out, &c, sizeof(c));
+  }
+  // scalar_mul(base, fr.as_bigint()) - curve_utils.tcc:13-34 via operator* (prover_reference_functions.cpp:166-168)
+  static void scale(const void *fr, const void *p, void *out) {
+    Fp<FrP> k;
+    memcpy(&k, fr, sizeof(k));
+    Fp<FrP>::from_mont(k, k);
+    Proj<F> a, c;
+    memcpy(&a, p, sizeof(a));
+    proj_scalar_mul<G>(c, a, k.l, kLimbs);
+    memcpy(out, &c, sizeof(c));
+  }
+  static void to_affine(const void *p, void *out) {
+    Proj<F> a;
+    Affine<F> o;
+    memcpy(&a, p, sizeof(a));
+    proj_to_affine<G>(o, a);
+    memcpy(out, &o, sizeof(o));
+  }
+  static void from_affine(const void *xy, void *out) {
+    Affine<F> a;
+    Proj<F> p;
+    memcpy(&a, xy, sizeof(a));
+    proj_from_affine(p, a);
+    memcpy(out, &p, sizeof(p));
+  }
+};
+
+#define DISPATCH_GROUP(curve, group, CALL)                                  \
+  do {                                                                      \
+    if ((curve) == 0 && (group) == 1) { HostOps<Mnt4G1>::CALL; return 0; }  \
+    if ((curve) == 0 && (group) == 2) { HostOps<Mnt4G2>::CALL; return 0; }  \
+    if ((curve) == 1 && (group) == 1) { HostOps<Mnt6G1>::CALL; return 0; }  \
+    if ((curve) == 1 && (group) == 2) { HostOps<Mnt6G2>::CALL; return 0; }  \
+    return set_error(-1, "bad curve %d", (int)(curve));                     \
+  } while (0)
+
+static size_t g2_degree(int curve) { return curve == 0 ? 2 : 3; }
+static size_t affine_bytes(int curve, int group) { return 2 * 96 * (group == 1 ? 1 : g2_degree(curve)); }
+static size_t proj_bytes(int curve, int group) { return 3 * 96 * (group == 1 ? 1 : g2_degree(curve)); }
+
+static int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return set_error(-10, "no usable CUDA device (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  return 0;
+}
+}  // namespace b200
+
+using namespace b200;
+
+template <class P>
+static void host_fp_op_t(int op, const void *a, const void *b, void *r) {
+  Fp<P> x, y, z;
+  memcpy(&x, a, 96);
+  if (b) memcpy(&y, b, 96);
+  else Fp<P>::set_zero(y);
+  switch (op) {
+    case 0: Fp<P>::add(z, x, y); break;
+    case 1: Fp<P>::sub(z, x, y); break;
+    case 2: Fp<P>::mul(z, x, y); break;
+    case 3: Fp<P>::inv(z, x); break;
+    case 4: Fp<P>::from_mont(z, x); break;
+    default: Fp<P>::to_mont(z, x); break;
+  }
+  memcpy(r, &z, 96);
+}
+
+struct b200_domain {
+  Domain *impl;
+};
+
+struct b200_params {
+  int curve;
+  size_t d, m;
+  const void *q[5];  // A, B1, B2, L, H (device)
+  DevBuf owned;      // backing store when loaded from a host image
+  b200_domain *dom;
+  DevBuf w, ca, cb, cc, h;  // per-proof device buffers
+};
+
+extern "C" {
+
+const char *b200_version(void) { return "b200-groth16-mnt753 0.1 (sm_100a)"; }
+const char *b200_last_error(void) { return last_error().c_str(); }
+int b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+int b200_set_device(int ordinal) {
+  B200_CHECK(require_device());
+  B200_CUDA_CHECK(cudaSetDevice(ordinal));
+  return 0;
+}
+int b200_sync(void) {
+  B200_CUDA_CHECK(cudaDeviceSynchronize());
+  return 0;
+}
+int b200_malloc(void **d_ptr, size_t bytes) {
+  B200_CHECK(require_device());
+  B200_CUDA_CHECK(cudaMalloc(d_ptr, bytes ? bytes : 16));
+  return 0;
+}
+int b200_free(void *d_ptr) {
+  B200_CUDA_CHECK(cudaFree(d_ptr));
+  return 0;
+}
+int b200_host_alloc(void **h_ptr, size_t bytes) {
+  B200_CHECK(require_device());
+  B200_CUDA_CHECK(cudaMallocHost(h_ptr, bytes ? bytes : 16));
+  return 0;
+}
+int b200_host_free(void *h_ptr) {
+  B200_CUDA_CHECK(cudaFreeHost(h_ptr));
+  return 0;
+}
+int b200_memcpy_h2d(void *d, const void *h, size_t bytes) {
+  B200_CUDA_CHECK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+  return 0;
+}
+int b200_memcpy_d2h(void *h, const void *d, size_t bytes) {
+  B200_CUDA_CHECK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int b200_memcpy_d2d(void *d, const void *s, size_t bytes) {
+  B200_CUDA_CHECK(cudaMemcpy(d, s, bytes, cudaMemcpyDeviceToDevice));
+  return 0;
+}
+int b200_memset_zero(void *d, size_t bytes) {
+  B200_CUDA_CHECK(cudaMemset(d, 0, bytes));
+  return 0;
+}
+
+// ---- Fr vectors
+int b200_fr_muleq(int curve, void *d_a, const void *d_b, size_t n) {
+  B200_CHECK(require_device());
+  return fr_muleq(curve, d_a, d_b, n);
+}
+int b200_fr_subeq(int curve, void *d_a, const void *d_b, size_t n) {
+  B200_CHECK(require_device());
+  return fr_subeq(curve, d_a, d_b, n);
+}
+
+// ---- domain
+int b200_domain_create(int curve, size_t m, b200_domain **out) {
+  B200_CHECK(require_device());
+  if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
+  Domain *impl = nullptr;
+  B200_CHECK(domain_create(curve, m, &impl));
+  *out = new b200_domain{impl};
+  return 0;
+}
+int b200_domain_destroy(b200_domain *dom) {
+  if (dom) {
+    domain_destroy(dom->impl);
+    delete dom;
+  }
+  return 0;
+}
+size_t b200_domain_size(const b200_domain *dom) { return domain_size(dom->impl); }
+int b200_domain_fft(b200_domain *dom, void *d_a) { return domain_transform(dom->impl, d_a, 0); }
+int b200_domain_ifft(b200_domain *dom, void *d_a) { return domain_transform(dom->impl, d_a, 1); }
+int b200_domain_coset_fft(b200_domain *dom, void *d_a) { return domain_transform(dom->impl, d_a, 2); }
+int b200_domain_icoset_fft(b200_domain *dom, void *d_a) { return domain_transform(dom->impl, d_a, 3); }
+int b200_domain_divide_by_z_on_coset(b200_domain *dom, void *d_a) { return domain_divide_by_z(dom->impl, d_a); }
+int b200_compute_h(b200_domain *dom, void *d_ca, void *d_cb, void *d_cc, void *d_out) {
+  return compute_h(dom->impl, d_ca, d_cb, d_cc, d_out);
+}
+
+// ---- MSM
+int b200_msm_g1(int curve, const void *d_scalars, const void *d_points, size_t n, void *h_out) {
+  B200_CHECK(require_device());
+  return msm_dispatch(curve, 1, d_scalars, d_points, n, h_out);
+}
+int b200_msm_g2(int curve, const void *d_scalars, const void *d_points, size_t n, void *h_out) {
+  B200_CHECK(require_device());
+  return msm_dispatch(curve, 2, d_scalars, d_points, n, h_out);
+}
+int b200_msm_set_window(int c) {
+  msm_set_window(c);
+  return 0;
+}
+int b200_msm_last_phase_ms(double *out5) {
+  msm_last_phase_ms(out5);
+  return 0;
+}
+
+// ---- host helpers
+int b200_g1_add(int curve, const void *p, const void *q, void *out) { DISPATCH_GROUP(curve, 1, add(p, q, out)); }
+int b200_g2_add(int curve, const void *p, const void *q, void *out) { DISPATCH_GROUP(curve, 2, add(p, q, out)); }
+int b200_g1_scale(int curve, const void *fr, const void *p, void *out) { DISPATCH_GROUP(curve, 1, scale(fr, p, out)); }
+int b200_g2_scale(int curve, const void *fr, const void *p, void *out) { DISPATCH_GROUP(curve, 2, scale(fr, p, out)); }
+int b200_g1_to_affine(int curve, const void *p, void *out) { DISPATCH_GROUP(curve, 1, to_affine(p, out)); }
+int b200_g2_to_affine(int curve, const void *p, void *out) { DISPATCH_GROUP(curve, 2, to_affine(p, out)); }
+int b200_g1_from_affine(int curve, const void *xy, void *out) { DISPATCH_GROUP(curve, 1, from_affine(xy, out)); }
+int b200_g2_from_affine(int curve, const void *xy, void *out) { DISPATCH_GROUP(curve, 2, from_affine(xy, out)); }
+
+int b200_host_fp_op(int tag, int op, const void *a, const void *b, void *r) {
+  if (op < 0 || op > 5) return set_error(-1, "bad op");
+  if (tag == 0) host_fp_op_t<PrimeA>(op, a, b, r);
+  else host_fp_op_t<PrimeB>(op, a, b, r);
+  return 0;
+}
+
+// ---- test hooks
+int b200_dev_fp_op(int tag, int op, const void *a, const void *b, void *r, size_t n) {
+  B200_CHECK(require_device());
+  return dev_fp_op(tag, op, a, b, r, n);
+}
+int b200_dev_fqe_op(int curve, int op, const void *a, const void *b, void *r, size_t n) {
+  B200_CHECK(require_device());
+  return dev_fqe_op(curve, op, a, b, r, n);
+}
+int b200_dev_group_op(int curve, int group, int op, const void *p, const void *q, void *r, size_t n) {
+  B200_CHECK(require_device());
+  return dev_group_op(curve, group, op, p, q, r, n);
+}
+int b200_gen_points(int curve, int group, void *d_out, size_t n, uint64_t first) {
+  B200_CHECK(require_device());
+  return gen_points(curve, group, d_out, n, first);
+}
+int b200_imad_peak(double *mac32_per_s, double *ms) {
+  B200_CHECK(require_device());
+  return imad_peak(mac32_per_s, ms);
+}
+
+// ---- proving key
+static int params_finish(b200_params *p) {
+  b200_domain *dom = nullptr;
+  B200_CHECK(b200_domain_create(p->curve, p->d + 1, &dom));
+  p->dom = dom;
+  B200_CHECK(p->w.alloc((p->m + 1) * 96));
+  B200_CHECK(p->ca.alloc((p->d + 1) * 96));
+  B200_CHECK(p->cb.alloc((p->d + 1) * 96));
+  B200_CHECK(p->cc.alloc((p->d + 1) * 96));
+  B200_CHECK(p->h.alloc((p->d + 2) * 96));
+  return 0;
+}
+int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_params **out) {
+  B200_CHECK(require_device());
+  if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
+  if (bytes < 16) return set_error(-4, "parameter image too short");
+  size_t d, m;
+  memcpy(&d, h_image, 8);
+  memcpy(&m, (const char *)h_image + 8, 8);
+  size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
+  size_t need = 16 + g1 * (2 * (m + 1) + (m - 1) + d) + g2 * (m + 1);
+  if (m < 2 || bytes != need)
+    return set_error(-4, "parameter image has %zu bytes, expected %zu for d=%zu m=%zu", bytes, need, d, m);
+  b200_params *p = new b200_params();
+  p->curve = curve;
+  p->d = d;
+  p->m = m;
+  p->dom = nullptr;
+  int rc = p->owned.alloc(bytes - 16);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  cudaError_t e = cudaMemcpy(p->owned.p, (const char *)h_image + 16, bytes - 16, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete p;
+    return set_error(-100 - (int)e, "H2D of parameters failed: %s", cudaGetErrorString(e));
+  }
+  char *base = (char *)p->owned.p;
+  p->q[0] = base;
+  p->q[1] = base + g1 * (m + 1);
+  p->q[2] = base + 2 * g1 * (m + 1);
+  p->q[3] = base + 2 * g1 * (m + 1) + g2 * (m + 1);
+  p->q[4] = base + 2 * g1 * (m + 1) + g2 * (m + 1) + g1 * (m - 1);
+  rc = params_finish(p);
+  if (rc) {
+    b200_params_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+int b200_params_from_device(int curve, size_t d, size_t m, const void *A, const void *B1, const void *B2, const void *L,
+                            const void *H, b200_params **out) {
+  B200_CHECK(require_device());
+  if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
+  b200_params *p = new b200_params();
+  p->curve = curve;
+  p->d = d;
+  p->m = m;
+  p->dom = nullptr;
+  p->q[0] = A; p->q[1] = B1; p->q[2] = B2; p->q[3] = L; p->q[4] = H;
+  int rc = params_finish(p);
+  if (rc) {
+    b200_params_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+int b200_params_destroy(b200_params *p) {
+  if (p) {
+    b200_domain_destroy(p->dom);
+    delete p;
+  }
+  return 0;
+}
+size_t b200_params_d(const b200_params *p) { return p->d; }
+size_t b200_params_m(const b200_params *p) { return p->m; }
+const void *b200_params_query(const b200_params *p, int which) { return (which >= 0 && which < 5) ? p->q[which] : nullptr; }
+
+// Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
+// multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
+static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, int rank, int world,
+                          unsigned char *partials, b200_prove_timings *tm) {
+  const size_t d = p->d, m = p->m;
+  const size_t need = 96 * ((m + 1) + 3 * (d + 1) + 1);
+  if (input_bytes != need) return set_error(-4, "input image has %zu bytes, expected %zu", input_bytes, need);
+  if (world < 1 || rank < 0 || rank >= world) return set_error(-1, "bad rank/world %d/%d", rank, world);
+  const char *in = (const char *)h_input;
+  double t0 = now_ms();
+  B200_CUDA_CHECK(cudaMemcpy(p->w.p, in, (m + 1) * 96, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpy(p->ca.p, in + (m + 1) * 96, (d + 1) * 96, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpy(p->cb.p, in + (m + 1) * 96 + (d + 1) * 96, (d + 1) * 96, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpy(p->cc.p, in + (m + 1) * 96 + 2 * (d + 1) * 96, (d + 1) * 96, cudaMemcpyHostToDevice));
+  double t1 = now_ms();
+  B200_CHECK(b200_compute_h(p->dom, p->ca.p, p->cb.p, p->cc.p, p->h.p));
+  B200_CUDA_CHECK(cudaDeviceSynchronize());
+  double t2 = now_ms();
+  const int curve = p->curve;
+  const size_t g1a = affine_bytes(curve, 1), g2a = affine_bytes(curve, 2);
+  const size_t g1p = proj_bytes(curve, 1), g2p = proj_bytes(curve, 2);
+  struct Job { int group; const char *scalars; const char *points; size_t n; size_t stride; size_t outb; double *ms; };
+  double ms[5] = {0, 0, 0, 0, 0};
+  Job jobs[5] = {
+      {1, (const char *)p->w.p, (const char *)p->q[0], m + 1, g1a, g1p, &ms[0]},        // A   main.cpp:227
+      {1, (const char *)p->w.p, (const char *)p->q[1], m + 1, g1a, g1p, &ms[1]},        // B1  main.cpp:232
+      {2, (const char *)p->w.p, (const char *)p->q[2], m + 1, g2a, g2p, &ms[2]},        // B2  main.cpp:237
+      {1, (const char *)p->h.p, (const char *)p->q[4], d, g1a, g1p, &ms[3]},            // H   main.cpp:242
+      {1, (const char *)p->w.p + 2 * 96, (const char *)p->q[3], m - 1, g1a, g1p, &ms[4]} // L   main.cpp:247 (w+2)
+  };
+  unsigned char *o = partials;
+  for (int j = 0; j < 5; j++) {
+    const Job &J = jobs[j];
+    size_t one = J.n / (size_t)world;
+    size_t lo = (size_t)rank * one, hi = (rank == world - 1) ? J.n : lo + one;
+    double a = now_ms();
+    B200_CHECK(msm_dispatch(curve, J.group, J.scalars + lo * 96, J.points + lo * J.stride, hi - lo, o));
+    *J.ms = now_ms() - a;
+    o += J.outb;
+  }
+  if (tm) {
+    tm->h2d_ms = t1 - t0;
+    tm->compute_h_ms = t2 - t1;
+    tm->msm_a_ms = ms[0]; tm->msm_b1_ms = ms[1]; tm->msm_b2_ms = ms[2]; tm->msm_h_ms = ms[3]; tm->msm_l_ms = ms[4];
+    tm->tail_ms = 0;
+    tm->total_ms = now_ms() - t0;
+  }
+  return 0;
+}
+
+static size_t partial_size(int curve) { return 4 * proj_bytes(curve, 1) + proj_bytes(curve, 2); }
+
+int b200_prove_partial(b200_params *p, const void *h_input, size_t input_bytes, int rank, int world, void *h_partials,
+                       size_t *partial_bytes, b200_prove_timings *timings) {
+  B200_CHECK(require_device());
+  B200_CHECK(prove_partials(p, h_input, input_bytes, rank, world, (unsigned char *)h_partials, timings));
+  if (partial_bytes) *partial_bytes = partial_size(p->curve);
+  return 0;
+}
+
+// C = Ht + Lt + r*Bt1 (main.cpp:253), then A | B | C in wire format (main.cpp:94-100)
+int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
+                       size_t *out_bytes) {
+  if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
+  const size_t g1p = proj_bytes(curve, 1), g2p = proj_bytes(curve, 2), ps = partial_size(curve);
+  const size_t off[5] = {0, g1p, 2 * g1p, 2 * g1p + g2p, 3 * g1p + g2p};
+  std::vector<unsigned char> sum(ps);
+  const unsigned char *all = (const unsigned char *)h_partials_all;
+  memcpy(sum.data(), all, ps);
+  for (int r = 1; r < world; r++) {
+    const unsigned char *pr = all + (size_t)r * ps;
+    for (int j = 0; j < 5; j++) {
+      if (j == 2) B200_CHECK(b200_g2_add(curve, sum.data() + off[j], pr + off[j], sum.data() + off[j]));
+      else B200_CHECK(b200_g1_add(curve, sum.data() + off[j], pr + off[j], sum.data() + off[j]));
+    }
+  }
+  std::vector<unsigned char> rb(g1p), c(g1p);
+  B200_CHECK(b200_g1_scale(curve, h_r_fr, sum.data() + off[1], rb.data()));
+  B200_CHECK(b200_g1_add(curve, sum.data() + off[4], rb.data(), c.data()));
+  B200_CHECK(b200_g1_add(curve, sum.data() + off[3], c.data(), c.data()));
+  unsigned char *o = (unsigned char *)h_out;
+  B200_CHECK(b200_g1_to_affine(curve, sum.data() + off[0], o));
+  o += affine_bytes(curve, 1);
+  B200_CHECK(b200_g2_to_affine(curve, sum.data() + off[2], o));
+  o += affine_bytes(curve, 2);
+  B200_CHECK(b200_g1_to_affine(curve, c.data(), o));
+  o += affine_bytes(curve, 1);
+  if (out_bytes) *out_bytes = (size_t)(o - (unsigned char *)h_out);
+  return 0;
+}
+
+int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_out, size_t *out_bytes,
+               b200_prove_timings *timings) {
+  B200_CHECK(require_device());
+  double t0 = now_ms();
+  std::vector<unsigned char> part(partial_size(p->curve));
+  B200_CHECK(prove_partials(p, h_input, input_bytes, 0, 1, part.data(), timings));
+  double t1 = now_ms();
+  const unsigned char *r = (const unsigned char *)h_input + input_bytes - 96;
+  B200_CHECK(b200_prove_combine(p->curve, part.data(), 1, r, h_out, out_bytes));
+  if (timings) {
+    timings->tail_ms = now_ms() - t1;
+    timings->total_ms = now_ms() - t0;
+  }
+  return 0;
+}
+
+}  // extern "C"

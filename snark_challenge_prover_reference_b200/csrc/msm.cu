@@ -1,0 +1,313 @@
+// Pippenger multi-scalar multiplication on one B200 for MNT4753 / MNT6753 G1 and G2.
+//
+// Replaces libff::multi_exp_with_mixed_addition (depends/libff/libff/algebra/scalar_multiplication/multiexp.tcc:443-496
+// -> multi_exp :402-441 -> multi_exp_inner<BDLO12> :165-282) as called by B::multiexp_G1/G2
+// (libsnark/prover_reference_functions.cpp:247-265). Same sum, different schedule:
+//
+//   K3  msm_digits_kernel      scalar -> integer (one Montgomery reduction, fp.tcc:227-238), signed c-bit digits,
+//                              per-(window,bucket) histogram                      [1 thread / scalar]
+//   K4  scan + msm_scatter     counting sort of (window, |digit|) -> contiguous lists of signed point indices
+//   K5  msm_accumulate_kernel  bucket sums by mixed addition, buckets visited largest-first so the threads of a
+//                              warp run equally long loops                        [1 thread / bucket]
+//   K7  msm_reduce_kernel      running-sum reduction of K consecutive buckets + lo*sum fix-up [1 thread / chunk]
+//       msm_sum_kernel         tree sum of the chunk results per window
+//       host                   Horner combine of the <= 95 window sums (753 doublings, serial, microseconds each)
+//
+// Scalars equal to 0 fall out naturally (all digits 0), scalars equal to 1 land in bucket 1 of window 0; points at
+// infinity in the bases (y == 0 on the wire) are skipped; P+P and P+(-P) inside a bucket take the same branches as
+// the reference's mixed_add (curve.cuh).
+#include <cub/cub.cuh>
+#include <chrono>
+#include "common.cuh"
+#include "curve.cuh"
+#include "msm.h"
+
+namespace b200 {
+
+static double g_phase_ms[5] = {0, 0, 0, 0, 0};
+static int g_forced_window = 0;
+void msm_set_window(int c) { g_forced_window = c; }
+void msm_last_phase_ms(double *out5) {
+  for (int i = 0; i < 5; i++) out5[i] = g_phase_ms[i];
+}
+
+// ---------------------------------------------------------------------------------------------- kernels
+template <class FrP>
+__global__ void __launch_bounds__(128) msm_digits_kernel(const Fp<FrP> *__restrict__ scalars, uint32_t n, int c, int W,
+                                                         int32_t *__restrict__ digits, uint32_t *__restrict__ counts) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp<FrP> s = scalars[i];
+  Fp<FrP>::from_mont(s, s);
+  const uint32_t nb = 1u << (c - 1);
+  const uint32_t mask = (1u << c) - 1;
+  uint32_t carry = 0;
+  for (int j = 0; j < W; j++) {
+    uint32_t bitpos = (uint32_t)j * (uint32_t)c;
+    uint32_t word = bitpos >> 5, off = bitpos & 31;
+    uint64_t two = word < (uint32_t)kLimbs ? s.l[word] : 0u;
+    if (word + 1 < (uint32_t)kLimbs) two |= (uint64_t)s.l[word + 1] << 32;
+    uint32_t v = ((uint32_t)(two >> off) & mask) + carry;
+    int32_t d;
+    if (v > nb) {
+      d = (int32_t)v - (int32_t)(1u << c);
+      carry = 1;
+    } else {
+      d = (int32_t)v;
+      carry = 0;
+    }
+    digits[(size_t)j * n + i] = d;
+    if (d != 0) {
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      atomicAdd(&counts[(size_t)j * nb + (mag - 1)], 1u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t *__restrict__ digits, uint32_t n, int W, int c,
+                                                          const uint32_t *__restrict__ offsets,
+                                                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)W * n) return;
+  int32_t d = digits[idx];
+  if (d == 0) return;
+  uint32_t j = (uint32_t)(idx / n), i = (uint32_t)(idx % n);
+  const uint32_t nb = 1u << (c - 1);
+  uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+  size_t b = (size_t)j * nb + (mag - 1);
+  uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);
+  entries[pos] = (i << 1) | (d < 0 ? 1u : 0u);
+}
+
+__global__ void iota_kernel(uint32_t *v, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+
+template <class G>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
+                                                             const uint32_t *__restrict__ entries,
+                                                             const uint32_t *__restrict__ offsets,
+                                                             const uint32_t *__restrict__ counts_sorted,
+                                                             const uint32_t *__restrict__ order, uint32_t nbuckets,
+                                                             Proj<typename G::F> *__restrict__ buckets) {
+  typedef typename G::F F;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbuckets) return;
+  uint32_t b = order[t];
+  uint32_t cnt = counts_sorted[t];
+  uint32_t start = offsets[b];
+  Proj<F> acc;
+  proj_set_zero(acc);
+  for (uint32_t k = 0; k < cnt; k++) {
+    uint32_t e = entries[start + k];
+    Affine<F> q = points[e >> 1];
+    if (affine_is_zero(q)) continue;
+    if (e & 1) F::neg(q.y, q.y);
+    proj_madd<G>(acc, q);
+  }
+  buckets[b] = acc;
+}
+
+// One thread reduces K consecutive buckets of one window: sum_{v in (lo, lo+K]} v * B_v  (bucket value v = index+1)
+template <class G>
+__global__ void __launch_bounds__(128) msm_reduce_kernel(const Proj<typename G::F> *__restrict__ buckets, int W,
+                                                         uint32_t nb, uint32_t K,
+                                                         Proj<typename G::F> *__restrict__ out) {
+  typedef typename G::F F;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nchunks = nb / K;
+  if (t >= (uint32_t)W * nchunks) return;
+  uint32_t j = t / nchunks, q = t % nchunks;
+  uint32_t lo = q * K;
+  const Proj<F> *B = buckets + (size_t)j * nb;
+  Proj<F> run, sum;
+  proj_set_zero(run);
+  proj_set_zero(sum);
+  for (uint32_t k = K; k-- > 0;) {
+    Proj<F> cur = B[lo + k];
+    proj_add<G>(run, run, cur);
+    proj_add<G>(sum, sum, run);
+  }
+  if (lo != 0) {
+    Proj<F> scaled;
+    proj_scalar_mul<G>(scaled, run, &lo, 1);
+    proj_add<G>(sum, sum, scaled);
+  }
+  out[t] = sum;
+}
+
+// out[j][t] = sum_{r<R} in[j][t*R + r]
+template <class G>
+__global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> *__restrict__ in, int W, uint32_t per_in,
+                                                      uint32_t R, Proj<typename G::F> *__restrict__ out) {
+  typedef typename G::F F;
+  uint32_t per_out = (per_in + R - 1) / R;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint32_t)W * per_out) return;
+  uint32_t j = t / per_out, q = t % per_out;
+  Proj<F> acc;
+  proj_set_zero(acc);
+  for (uint32_t r = 0; r < R; r++) {
+    uint32_t idx = q * R + r;
+    if (idx >= per_in) break;
+    Proj<F> cur = in[(size_t)j * per_in + idx];
+    proj_add<G>(acc, acc, cur);
+  }
+  out[(size_t)j * per_out + q] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------- host driver
+// Window width: minimise (bucket accumulation + bucket reduction) field multiplications.
+static int choose_window(size_t n) {
+  if (g_forced_window >= 2 && g_forced_window <= 22) return g_forced_window;
+  double best = 1e300;
+  int best_c = 4;
+  for (int c = 3; c <= 20; c++) {
+    double W = 753 / c + 1;
+    double nb = (double)(1u << (c - 1));
+    double cost = W * ((double)n * 11.0 + nb * 2.0 * 14.0 + nb / 32.0 * 30.0 * 13.0);
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+struct MsmWorkspace {
+  DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b;
+};
+static MsmWorkspace &workspace() {
+  static thread_local MsmWorkspace ws;
+  return ws;
+}
+void msm_release_workspace() {
+  MsmWorkspace &ws = workspace();
+  DevBuf *all[] = {&ws.digits, &ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.order,
+                   &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b};
+  for (DevBuf *b : all) b->release();
+}
+
+template <class G>
+int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) {
+  typedef typename G::F F;
+  typedef typename G::ScalarPrime FrP;
+  Proj<F> result;
+  proj_set_zero(result);
+  if (n == 0) {
+    memcpy(h_out, &result, sizeof(result));
+    return 0;
+  }
+  if (n >= (1ull << 30)) return set_error(-2, "msm: n=%zu too large", n);
+  const int c = choose_window(n);
+  const int W = 753 / c + 1;
+  const uint32_t nb = 1u << (c - 1);
+  const size_t nbuckets = (size_t)W * nb;
+  if ((size_t)W * n >= (1ull << 32)) return set_error(-2, "msm: W*n overflows 32-bit entry positions");
+  MsmWorkspace &ws = workspace();
+  B200_CHECK(ws.digits.reserve((size_t)W * n * sizeof(int32_t)));
+  B200_CHECK(ws.entries.reserve((size_t)W * n * sizeof(uint32_t)));
+  B200_CHECK(ws.counts.reserve(nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.offsets.reserve(nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.cursor.reserve(nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.order.reserve(nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.counts_sorted.reserve(nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.iota.reserve(nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
+  Timer tm;
+
+  // ---- digits + histogram
+  tm.start();
+  B200_CUDA_CHECK(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), 0));
+  B200_CUDA_CHECK(cudaMemsetAsync(ws.cursor.p, 0, nbuckets * sizeof(uint32_t), 0));
+  msm_digits_kernel<FrP><<<grid_for(n, 128), 128>>>((const Fp<FrP> *)d_scalars, (uint32_t)n, c, W,
+                                                    ws.digits.as<int32_t>(), ws.counts.as<uint32_t>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  g_phase_ms[0] = tm.stop();
+
+  // ---- counting sort: scan, scatter; then bucket order by descending size
+  tm.start();
+  size_t tmp_bytes = 0, tmp2 = 0;
+  int end_bit = 1;
+  while ((1ull << end_bit) <= n) end_bit++;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ws.counts.as<uint32_t>(), ws.offsets.as<uint32_t>(), (int)nbuckets);
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, ws.counts.as<uint32_t>(), ws.counts_sorted.as<uint32_t>(),
+                                            ws.iota.as<uint32_t>(), ws.order.as<uint32_t>(), (int)nbuckets, 0, end_bit);
+  if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+  B200_CHECK(ws.cub_tmp.reserve(tmp_bytes));
+  size_t tb = ws.cub_tmp.bytes;
+  B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.p, tb, ws.counts.as<uint32_t>(), ws.offsets.as<uint32_t>(),
+                                                (int)nbuckets));
+  {
+    size_t total = (size_t)W * n;
+    msm_scatter_kernel<<<grid_for(total, 256), 256>>>(ws.digits.as<int32_t>(), (uint32_t)n, W, c,
+                                                      ws.offsets.as<uint32_t>(), ws.cursor.as<uint32_t>(),
+                                                      ws.entries.as<uint32_t>());
+    B200_CUDA_CHECK(cudaGetLastError());
+  }
+  iota_kernel<<<grid_for(nbuckets, 256), 256>>>(ws.iota.as<uint32_t>(), (uint32_t)nbuckets);
+  tb = ws.cub_tmp.bytes;
+  B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(ws.cub_tmp.p, tb, ws.counts.as<uint32_t>(),
+                                                            ws.counts_sorted.as<uint32_t>(), ws.iota.as<uint32_t>(),
+                                                            ws.order.as<uint32_t>(), (int)nbuckets, 0, end_bit));
+  g_phase_ms[1] = tm.stop();
+
+  // ---- bucket accumulation
+  tm.start();
+  msm_accumulate_kernel<G><<<grid_for(nbuckets, 128), 128>>>(
+      (const Affine<F> *)d_points, ws.entries.as<uint32_t>(), ws.offsets.as<uint32_t>(),
+      ws.counts_sorted.as<uint32_t>(), ws.order.as<uint32_t>(), (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  g_phase_ms[2] = tm.stop();
+
+  // ---- bucket reduction: chunks of K buckets, then tree sum per window
+  tm.start();
+  uint32_t K = nb < 32 ? nb : 32;
+  uint32_t per = nb / K;
+  B200_CHECK(ws.red_a.reserve((size_t)W * per * sizeof(Proj<F>)));
+  B200_CHECK(ws.red_b.reserve((size_t)W * ((per + 7) / 8) * sizeof(Proj<F>) + 16));
+  msm_reduce_kernel<G><<<grid_for((size_t)W * per, 128), 128>>>(ws.buckets.as<Proj<F>>(), W, nb, K,
+                                                               ws.red_a.as<Proj<F>>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  Proj<F> *cur = ws.red_a.as<Proj<F>>(), *nxt = ws.red_b.as<Proj<F>>();
+  while (per > 1) {
+    uint32_t R = 8;
+    uint32_t per_out = (per + R - 1) / R;
+    msm_sum_kernel<G><<<grid_for((size_t)W * per_out, 128), 128>>>(cur, W, per, R, nxt);
+    B200_CUDA_CHECK(cudaGetLastError());
+    Proj<F> *t = cur;
+    cur = nxt;
+    nxt = t;
+    per = per_out;
+  }
+  std::vector<Proj<F>> win(W);
+  B200_CUDA_CHECK(cudaMemcpy(win.data(), cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost));
+  g_phase_ms[3] = tm.stop();
+
+  // ---- host: result = sum_j 2^(c*j) * S_j  (Horner, most significant window first)
+  auto t0 = std::chrono::steady_clock::now();
+  for (int j = W - 1; j >= 0; j--) {
+    if (!proj_is_zero(result))
+      for (int k = 0; k < c; k++) proj_dbl<G>(result, result);
+    proj_add<G>(result, result, win[j]);
+  }
+  g_phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  memcpy(h_out, &result, sizeof(result));
+  return 0;
+}
+
+template int msm_run<Mnt4G1>(const void *, const void *, size_t, void *);
+template int msm_run<Mnt4G2>(const void *, const void *, size_t, void *);
+template int msm_run<Mnt6G1>(const void *, const void *, size_t, void *);
+template int msm_run<Mnt6G2>(const void *, const void *, size_t, void *);
+
+int msm_dispatch(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out) {
+  if (curve == 0 && group == 1) return msm_run<Mnt4G1>(d_scalars, d_points, n, h_out);
+  if (curve == 0 && group == 2) return msm_run<Mnt4G2>(d_scalars, d_points, n, h_out);
+  if (curve == 1 && group == 1) return msm_run<Mnt6G1>(d_scalars, d_points, n, h_out);
+  if (curve == 1 && group == 2) return msm_run<Mnt6G2>(d_scalars, d_points, n, h_out);
+  return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
+}
+
+}  // namespace b200

@@ -1,0 +1,10 @@
+// Host-callable entry points of msm.cu (internal; the public surface is include/b200_groth16.h).
+#pragma once
+#include <stddef.h>
+namespace b200 {
+// group: 1 = G1, 2 = G2. d_scalars: n Fr (Montgomery). d_points: n affine wire-format points. h_out: projective.
+int msm_dispatch(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out);
+void msm_set_window(int c);
+void msm_last_phase_ms(double *out5);
+void msm_release_workspace();
+}  // namespace b200

@@ -1,0 +1,15 @@
+// Host-callable entry points of ntt.cu (internal; the public surface is include/b200_groth16.h).
+#pragma once
+#include <stddef.h>
+namespace b200 {
+struct Domain;
+int domain_create(int curve, size_t m, Domain **out);
+void domain_destroy(Domain *d);
+size_t domain_size(const Domain *d);
+// kind: 0 FFT, 1 iFFT, 2 cosetFFT, 3 icosetFFT
+int domain_transform(Domain *d, void *d_a, int kind);
+int domain_divide_by_z(Domain *d, void *d_a);
+int fr_muleq(int curve, void *d_a, const void *d_b, size_t n);
+int fr_subeq(int curve, void *d_a, const void *d_b, size_t n);
+int compute_h(Domain *d, void *d_ca, void *d_cb, void *d_cc, void *d_out);
+}  // namespace b200

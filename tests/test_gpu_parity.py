@@ -1,0 +1,347 @@
+"""GPU suite (-m gpu): every CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs,
+against the committed golden proofs of the reference, and - at sizes the oracle cannot reach - through
+size-independent properties (linearity of the MSM, transform round trips). Integer work: the bar is bit-exact."""
+import ctypes
+import random
+
+import pytest
+
+import mnt753 as M
+import util
+
+pytestmark = pytest.mark.gpu
+FE = 96
+
+
+@pytest.fixture(scope="module")
+def dev(b200):
+    import torch
+    assert torch.cuda.is_available()
+    b200.check(b200.lib().b200_set_device(0))
+    return torch.device("cuda:0")
+
+
+def _edge_values(p):
+    return [0, 1, 2, p - 1, p - 2, (1 << 752) % p, M.R % p, (p + 1) // 2, 0xFFFFFFFF, 1 << 32, (1 << 736) - 1]
+
+
+# ------------------------------------------------------------------------------------------------ field layer
+@pytest.mark.parametrize("tag", [0, 1])
+def test_fp_ops_vs_python_ints(b200, dev, tag):
+    p = M.PRIMES["AB"[tag]]
+    rng = random.Random(1000 + tag)
+    ev = _edge_values(p)
+    xs = [a for a in ev for _ in ev] + [rng.randrange(p) for _ in range(3000)]
+    ys = [b for _ in ev for b in ev] + [rng.randrange(p) for _ in range(3000)]
+    n = len(xs)
+    da = b200.to_device(b"".join(util.fe_bytes(v) for v in xs))
+    db = b200.to_device(b"".join(util.fe_bytes(v) for v in ys))
+    import torch
+    dr = torch.empty(n * FE, dtype=torch.uint8, device=dev)
+    rinv = pow(M.R, -1, p)
+    expect = {0: lambda a, b: (a + b) % p, 1: lambda a, b: (a - b) % p, 2: lambda a, b: a * b * rinv % p,
+              3: lambda a, b: a * a * rinv % p, 4: lambda a, b: a * rinv % p, 5: lambda a, b: a * M.R % p}
+    for op, f in expect.items():
+        b200.check(b200.lib().b200_dev_fp_op(tag, op, da.data_ptr(), db.data_ptr(), dr.data_ptr(), n))
+        out = b200.from_device(dr)
+        for i in range(n):
+            assert util.fe_int(out[i * FE:(i + 1) * FE]) == f(xs[i], ys[i]), (op, i)
+    # inversion on a few elements
+    k = 64
+    b200.check(b200.lib().b200_dev_fp_op(tag, 6, da.data_ptr() + 20 * FE * 11, None, dr.data_ptr(), k))
+    out = b200.from_device(dr)
+    for i in range(k):
+        a = xs[220 + i]
+        if a:
+            assert M.from_mont(util.fe_int(out[i * FE:(i + 1) * FE]), p) * M.from_mont(a, p) % p == 1
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_tower_ops_vs_oracle(b200, oracle, dev, curve):
+    import torch
+    c = util.curve_obj(curve)
+    d = c.ext_deg
+    rng = random.Random(2000 + curve)
+    n = 96
+    a = b"".join(util.rand_fe_bytes(rng, c.q, d) for _ in range(n))
+    bb = b"".join(util.rand_fe_bytes(rng, c.q, d) for _ in range(n))
+    da, db = b200.to_device(a), b200.to_device(bb)
+    dr = torch.empty(n * d * FE, dtype=torch.uint8, device=dev)
+    for op in (0, 1, 2, 3):
+        b200.check(b200.lib().b200_dev_fqe_op(curve, op, da.data_ptr(), db.data_ptr(), dr.data_ptr(), n))
+        out = b200.from_device(dr)
+        sz = d * FE
+        for i in range(n):
+            exp = util.orc_fqe(oracle, curve, 2, op, a[i * sz:(i + 1) * sz], bb[i * sz:(i + 1) * sz])
+            assert out[i * sz:(i + 1) * sz] == exp, (op, i)
+
+
+# ------------------------------------------------------------------------------------------------ group layer
+def _some_points(b200, oracle, curve, group, n, seed):
+    """n projective points (random multiples of the generator, randomised Z) + their affine forms, via the oracle"""
+    c = util.curve_obj(curve)
+    rng = random.Random(seed)
+    G = b200.g_from_affine(curve, group, util.generator_affine(curve, group))
+    proj, aff = [], []
+    for _ in range(n):
+        k = util.fe_bytes(M.to_mont(rng.randrange(1, c.r), c.r))
+        P = util.orc_group(oracle, curve, group, 3, G, k)
+        proj.append(P)
+        aff.append(util.orc_to_affine(oracle, curve, group, P))
+    return proj, aff
+
+
+@pytest.mark.parametrize("curve,group", [(0, 1), (0, 2), (1, 1), (1, 2)])
+def test_group_ops_vs_oracle(b200, oracle, dev, curve, group):
+    import torch
+    proj, aff = _some_points(b200, oracle, curve, group, 12, 3000 + 10 * curve + group)
+    pb, ab = b200.proj_bytes(curve, group), b200.affine_bytes(curve, group)
+    zero_p = b200.g_from_affine(curve, group, bytes(ab))
+    neg = lambda P: util.orc_group(oracle, curve, group, 0, zero_p, P)  # placeholder, replaced below
+    # build operand lists with the special cases the reference handles: O+P, P+O, P+P, P+(-P), O+O
+    negs = []
+    for a in aff:
+        d = util.deg(curve, group)
+        x, y = a[:d * FE], a[d * FE:]
+        q = util.curve_obj(curve).q
+        ny = b"".join(util.fe_bytes((q - util.fe_int(y[i * FE:(i + 1) * FE])) % q) for i in range(d))
+        negs.append(x + ny)
+    P = proj + [zero_p, proj[0], proj[1], proj[2], zero_p]
+    Qp = proj[1:] + proj[:1] + [proj[3], zero_p, proj[1], b200.g_from_affine(curve, group, negs[2]), zero_p]
+    Qa = aff[1:] + aff[:1] + [aff[3], bytes(ab), aff[1], negs[2], bytes(ab)]
+    n = len(P)
+    dP, dQp, dQa = b200.to_device(b"".join(P)), b200.to_device(b"".join(Qp)), b200.to_device(b"".join(Qa))
+    dR = torch.empty(n * pb, dtype=torch.uint8, device=dev)
+    dA = torch.empty(n * ab, dtype=torch.uint8, device=dev)
+
+    def affine_of(dproj):
+        b200.check(b200.lib().b200_dev_group_op(curve, group, 3, dproj.data_ptr(), None, dA.data_ptr(), n))
+        out = b200.from_device(dA)
+        return [out[i * ab:(i + 1) * ab] for i in range(n)]
+
+    b200.check(b200.lib().b200_dev_group_op(curve, group, 0, dP.data_ptr(), dQp.data_ptr(), dR.data_ptr(), n))
+    got = affine_of(dR)
+    for i in range(n):
+        exp = util.orc_to_affine(oracle, curve, group, util.orc_group(oracle, curve, group, 0, P[i], Qp[i]))
+        assert got[i] == exp, ("add", i)
+    b200.check(b200.lib().b200_dev_group_op(curve, group, 1, dP.data_ptr(), None, dR.data_ptr(), n))
+    got = affine_of(dR)
+    for i in range(n):
+        exp = util.orc_to_affine(oracle, curve, group, util.orc_group(oracle, curve, group, 1, P[i]))
+        assert got[i] == exp, ("dbl", i)
+    b200.check(b200.lib().b200_dev_group_op(curve, group, 2, dP.data_ptr(), dQa.data_ptr(), dR.data_ptr(), n))
+    got = affine_of(dR)
+    for i in range(n):
+        exp = util.orc_to_affine(oracle, curve, group, util.orc_group(oracle, curve, group, 2, P[i], Qa[i]))
+        assert got[i] == exp, ("mixed_add", i)
+
+
+@pytest.mark.parametrize("curve,group", [(0, 1), (0, 2), (1, 1), (1, 2)])
+def test_gen_points_are_multiples_of_generator(b200, dev, curve, group):
+    import torch
+    n, first = 21, 5
+    ab = b200.affine_bytes(curve, group)
+    out = torch.empty(n * ab, dtype=torch.uint8, device=dev)
+    b200.check(b200.lib().b200_gen_points(curve, group, out.data_ptr(), n, first))
+    got = b200.from_device(out)
+    F, a, b, G = util.group_params(curve, group)
+    P = M.ec_mul(F, a, first, G)
+    for i in range(n):
+        assert got[i * ab:(i + 1) * ab] == util.encode_affine(curve, P, group), i
+        P = M.ec_add(F, a, P, G)
+
+
+# ------------------------------------------------------------------------------------------------ MSM
+def _msm_case(b200, oracle, dev, curve, group, n, seed, special=True, window=0):
+    import torch
+    c = util.curve_obj(curve)
+    rng = random.Random(seed)
+    ab = b200.affine_bytes(curve, group)
+    pts = torch.empty(max(n, 1) * ab, dtype=torch.uint8, device=dev)
+    b200.check(b200.lib().b200_gen_points(curve, group, pts.data_ptr(), n, 1 + rng.randrange(1000)))
+    points = bytearray(b200.from_device(pts)[:n * ab])
+    scalars = [rng.randrange(c.r) for _ in range(n)]
+    if special and n >= 16:
+        # the structure observed in real keys (SURVEY.md 8 pitfalls): O entries, one point repeated many times,
+        # a duplicate pair, P / -P with equal scalars; scalars 0, 1 (Montgomery one), r-1
+        points[0:ab] = bytes(ab)
+        points[(n - 1) * ab:n * ab] = bytes(ab)
+        for i in range(2, n - 2, 2):
+            points[i * ab:(i + 1) * ab] = points[2 * ab:3 * ab]
+        d = util.deg(curve, group)
+        x, y = points[5 * ab:5 * ab + d * FE], points[5 * ab + d * FE:6 * ab]
+        ny = b"".join(util.fe_bytes((c.q - util.fe_int(y[i * FE:(i + 1) * FE])) % c.q) for i in range(d))
+        points[7 * ab:8 * ab] = bytes(x) + ny
+        scalars[7] = scalars[5]
+        scalars[1] = 0
+        scalars[3] = 1
+        scalars[9] = c.r - 1
+        scalars[11] = 1
+    sc = b"".join(util.fe_bytes(M.to_mont(s, c.r)) for s in scalars)
+    d_s, d_p = b200.to_device(sc), b200.to_device(bytes(points))
+    b200.lib().b200_msm_set_window(window)
+    try:
+        got = b200.g_to_affine(curve, group, b200.msm(curve, group, d_s, d_p, n))
+    finally:
+        b200.lib().b200_msm_set_window(0)
+    exp = util.orc_msm_affine(oracle, curve, group, sc, bytes(points), n)
+    assert got == exp, (curve, group, n, window)
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 256, 1000])
+def test_msm_g1_vs_oracle(b200, oracle, dev, curve, n):
+    _msm_case(b200, oracle, dev, curve, 1, n, 4000 + n + curve)
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+@pytest.mark.parametrize("n", [1, 5, 64, 300])
+def test_msm_g2_vs_oracle(b200, oracle, dev, curve, n):
+    _msm_case(b200, oracle, dev, curve, 2, n, 5000 + n + curve)
+
+
+@pytest.mark.parametrize("window", [3, 8, 13, 16])
+def test_msm_window_widths(b200, oracle, dev, window):
+    _msm_case(b200, oracle, dev, 0, 1, 200, 6000 + window, window=window)
+    _msm_case(b200, oracle, dev, 1, 2, 40, 6100 + window, window=window)
+
+
+def test_msm_degenerate_scalars(b200, oracle, dev):
+    import torch
+    for curve in (0, 1):
+        c = util.curve_obj(curve)
+        n = 64
+        ab = b200.affine_bytes(curve, 1)
+        pts = torch.empty(n * ab, dtype=torch.uint8, device=dev)
+        b200.check(b200.lib().b200_gen_points(curve, 1, pts.data_ptr(), n, 3))
+        points = b200.from_device(pts)
+        for val in (0, 1, c.r - 1):
+            sc = util.fe_bytes(M.to_mont(val, c.r)) * n
+            got = b200.g_to_affine(curve, 1, b200.msm(curve, 1, b200.to_device(sc), pts, n))
+            assert got == util.orc_msm_affine(oracle, curve, 1, sc, points, n), val
+        # empty input -> O
+        assert b200.g_to_affine(curve, 1, b200.msm(curve, 1, pts, pts, 0)) == bytes(ab)
+
+
+def test_msm_linearity_large(b200, dev):
+    """n = 2^15 (beyond what the oracle does in seconds): msm(s,P) + msm(t,P) == msm(s+t,P), and the same sum from
+    two different window widths."""
+    import torch
+    curve, n = 0, 1 << 15
+    c = util.curve_obj(curve)
+    ab = b200.affine_bytes(curve, 1)
+    pts = torch.empty(n * ab, dtype=torch.uint8, device=dev)
+    b200.check(b200.lib().b200_gen_points(curve, 1, pts.data_ptr(), n, 77))
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    raw = torch.randint(0, 256, (2, n, FE), dtype=torch.uint8, generator=g)
+    raw[:, :, 94:] = 0  # < 2^752 < r: any such value is a valid Montgomery representation
+    s, t = raw[0].contiguous().to(dev), raw[1].contiguous().to(dev)
+    st = torch.empty_like(s)
+    b200.check(b200.lib().b200_dev_fp_op(0, 0, s.data_ptr(), t.data_ptr(), st.data_ptr(), n))
+    a = b200.msm(curve, 1, s, pts, n)
+    b = b200.msm(curve, 1, t, pts, n)
+    b200.lib().b200_msm_set_window(11)
+    try:
+        cc = b200.msm(curve, 1, st, pts, n)
+    finally:
+        b200.lib().b200_msm_set_window(0)
+    assert b200.g_to_affine(curve, 1, b200.g_add(curve, 1, a, b)) == b200.g_to_affine(curve, 1, cc)
+
+
+# ------------------------------------------------------------------------------------------------ NTT / compute_H
+@pytest.mark.parametrize("curve,logm", [(0, 1), (0, 2), (0, 5), (0, 8), (0, 9), (0, 13), (1, 1), (1, 3), (1, 8), (1, 12)])
+def test_domain_ops_vs_oracle(b200, oracle, dev, curve, logm):
+    c = util.curve_obj(curve)
+    m = 1 << logm
+    rng = random.Random(7000 + 100 * curve + logm)
+    data = util.rand_fe_bytes(rng, c.r, m)
+    dom = b200.Domain(curve, m)
+    for kind, fn in ((0, dom.fft), (1, dom.ifft), (2, dom.coset_fft), (3, dom.icoset_fft), (4, dom.divide_by_z_on_coset)):
+        d = b200.to_device(data)
+        fn(d)
+        assert b200.from_device(d) == util.orc_domain(oracle, curve, kind, data, m), (kind, logm)
+    dom.close()
+
+
+def test_domain_rejects_bad_sizes(b200, dev):
+    for curve, m in ((0, 3), (0, 1), (1, 1 << 16), (0, 100)):
+        with pytest.raises(b200.B200Error):
+            b200.Domain(curve, m)
+
+
+@pytest.mark.parametrize("curve,logm", [(0, 6), (1, 6), (0, 11), (1, 10)])
+def test_compute_h_vs_oracle(b200, oracle, dev, curve, logm):
+    import torch
+    c = util.curve_obj(curve)
+    m = 1 << logm
+    rng = random.Random(8000 + curve + logm)
+    ca, cb, cc = (util.rand_fe_bytes(rng, c.r, m) for _ in range(3))
+    dom = b200.Domain(curve, m)
+    out = torch.empty((m + 1) * FE, dtype=torch.uint8, device=dev)
+    dom.compute_h(b200.to_device(ca), b200.to_device(cb), b200.to_device(cc), out)
+    assert b200.from_device(out) == util.orc_compute_h(oracle, curve, m - 1, ca, cb, cc)
+    dom.close()
+
+
+def test_vector_ops_vs_oracle(b200, oracle, dev):
+    for curve in (0, 1):
+        c = util.curve_obj(curve)
+        tag = 0 if curve == 0 else 1
+        rng = random.Random(8100 + curve)
+        n = 333
+        a, b = util.rand_fe_bytes(rng, c.r, n), util.rand_fe_bytes(rng, c.r, n)
+        da, db = b200.to_device(a), b200.to_device(b)
+        b200.check(b200.lib().b200_fr_muleq(curve, da.data_ptr(), db.data_ptr(), n))
+        out = b200.from_device(da)
+        for i in range(n):
+            assert out[i * FE:(i + 1) * FE] == util.orc_fp(oracle, tag, 2, a[i * FE:(i + 1) * FE], b[i * FE:(i + 1) * FE])
+        da = b200.to_device(a)
+        b200.check(b200.lib().b200_fr_subeq(curve, da.data_ptr(), db.data_ptr(), n))
+        out = b200.from_device(da)
+        for i in range(n):
+            assert out[i * FE:(i + 1) * FE] == util.orc_fp(oracle, tag, 1, a[i * FE:(i + 1) * FE], b[i * FE:(i + 1) * FE])
+
+
+def test_ntt_roundtrip_full_size(b200, dev):
+    """2^20 (MNT4753 challenge size) and 2^15 (MNT6753): icosetFFT(cosetFFT(x)) == x and iFFT(FFT(x)) == x."""
+    import torch
+    for curve, logm in ((0, 20), (1, 15)):
+        m = 1 << logm
+        g = torch.Generator(device="cpu").manual_seed(99 + curve)
+        raw = torch.randint(0, 256, (m, FE), dtype=torch.uint8, generator=g)
+        raw[:, 94:] = 0
+        x = raw.to(dev)
+        y = x.clone()
+        dom = b200.Domain(curve, m)
+        dom.coset_fft(y)
+        assert not torch.equal(x, y)
+        dom.icoset_fft(y)
+        assert torch.equal(x, y)
+        dom.fft(y)
+        dom.ifft(y)
+        assert torch.equal(x, y)
+        dom.close()
+
+
+# ------------------------------------------------------------------------------------------------ whole prover
+@pytest.mark.parametrize("curve,k", [(0, 5), (1, 5), (0, 8), (1, 8)])
+def test_prover_matches_reference_golden(b200, dev, curve, k):
+    params, inp, expected = util.golden(curve, k)
+    P = b200.Params.from_bytes(curve, params)
+    assert (P.d, P.m) == ((1 << k) - 1, 1 << k)
+    got = P.prove(inp)
+    assert got == expected
+    again, tm = P.prove(inp, timings=True)  # second proof on the same resident key
+    assert again == expected and tm["total_ms"] > 0
+    P.close()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_sharded_prover_matches_reference_golden(b200, dev, curve):
+    """MSMs split by point range over `world` ranks (run sequentially on one GPU here) + host combine."""
+    params, inp, expected = util.golden(curve, 8)
+    P = b200.Params.from_bytes(curve, params)
+    for world in (2, 3):
+        parts = b"".join(P.prove_partial(inp, r, world)[0] for r in range(world))
+        assert b200.prove_combine(curve, parts, world, inp[-FE:]) == expected
+    P.close()
