@@ -55,6 +55,9 @@ typedef struct b200_domain b200_domain;
 int b200_domain_create(int curve, size_t m, b200_domain **out);
 int b200_domain_destroy(b200_domain *dom);
 size_t b200_domain_size(const b200_domain *dom); /* B::domain_get_m */
+/* test hook: copy the first `count` entries of a precomputed table to the host.
+ * which: 0 omega^i, 1 omega^-i, 2 g^i, 3 g^-i/m, 4 {1/m, 1/Z(g)} */
+int b200_domain_table(const b200_domain *dom, int which, void *h_out, size_t count);
 int b200_domain_fft(b200_domain *dom, void *d_a);       /* basic_radix2_domain::FFT       (:62-68)  */
 int b200_domain_ifft(b200_domain *dom, void *d_a);      /* B::domain_iFFT                  (:70-82)  */
 int b200_domain_coset_fft(b200_domain *dom, void *d_a); /* B::domain_cosetFFT, g = 17      (:84-89)  */

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "b200_domain_create": (_i, [_i, _sz, ctypes.POINTER(_vp)]),
     "b200_domain_destroy": (_i, [_vp]),
     "b200_domain_size": (_sz, [_vp]),
+    "b200_domain_table": (_i, [_vp, _i, _vp, _sz]),
     "b200_domain_fft": (_i, [_vp, _vp]),
     "b200_domain_ifft": (_i, [_vp, _vp]),
     "b200_domain_coset_fft": (_i, [_vp, _vp]),
@@ -214,11 +215,16 @@ class Domain:
         self.h, self.curve, self.m = h, curve, m
 
     def close(self):
-        if self.h:
+        if self.h and lib is not None:
             lib().b200_domain_destroy(self.h)
-            self.h = None
+        self.h = None
 
     __del__ = close
+
+    def table(self, which, count):
+        out = ctypes.create_string_buffer(count * FE)
+        check(lib().b200_domain_table(self.h, which, ctypes.addressof(out), count))
+        return out.raw
 
     def fft(self, a):
         check(lib().b200_domain_fft(self.h, _ptr(a)))

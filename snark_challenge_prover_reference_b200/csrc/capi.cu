@@ -202,6 +202,9 @@ int b200_domain_destroy(b200_domain *dom) {
   return 0;
 }
 size_t b200_domain_size(const b200_domain *dom) { return domain_size(dom->impl); }
+int b200_domain_table(const b200_domain *dom, int which, void *h_out, size_t count) {
+  return domain_table(dom->impl, which, h_out, count);
+}
 int b200_domain_fft(b200_domain *dom, void *d_a) { return domain_transform(dom->impl, d_a, 0); }
 int b200_domain_ifft(b200_domain *dom, void *d_a) { return domain_transform(dom->impl, d_a, 1); }
 int b200_domain_coset_fft(b200_domain *dom, void *d_a) { return domain_transform(dom->impl, d_a, 2); }

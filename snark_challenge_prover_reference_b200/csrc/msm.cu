@@ -32,25 +32,31 @@ void msm_last_phase_ms(double *out5) {
 }
 
 // ---------------------------------------------------------------------------------------------- kernels
+// Window plan: W windows tile bits [0, 753) of the scalar. plan[j] = start_bit | width << 16. All windows but the top
+// one are recoded to signed digits in [-2^(w-1), 2^(w-1)] (carry into the next window); the top window has width c-1
+// and stays unsigned, so it needs the same 2^(c-1) buckets as a full signed window and never carries out. Widths
+// are c or c-1, chosen so that no window is a narrow left-over: uniformly distributed scalars give uniformly filled
+// buckets in every window (a short top window would put ~n/2 points into one bucket).
 template <class FrP>
 __global__ void __launch_bounds__(128) msm_digits_kernel(const Fp<FrP> *__restrict__ scalars, uint32_t n, int c, int W,
+                                                         const uint32_t *__restrict__ plan,
                                                          int32_t *__restrict__ digits, uint32_t *__restrict__ counts) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp<FrP> s = scalars[i];
   Fp<FrP>::from_mont(s, s);
   const uint32_t nb = 1u << (c - 1);
-  const uint32_t mask = (1u << c) - 1;
   uint32_t carry = 0;
   for (int j = 0; j < W; j++) {
-    uint32_t bitpos = (uint32_t)j * (uint32_t)c;
-    uint32_t word = bitpos >> 5, off = bitpos & 31;
+    const uint32_t pj = plan[j];
+    const uint32_t bitpos = pj & 0xffffu, cw = pj >> 16;
+    const uint32_t word = bitpos >> 5, off = bitpos & 31;
     uint64_t two = word < (uint32_t)kLimbs ? s.l[word] : 0u;
     if (word + 1 < (uint32_t)kLimbs) two |= (uint64_t)s.l[word + 1] << 32;
-    uint32_t v = ((uint32_t)(two >> off) & mask) + carry;
+    uint32_t v = ((uint32_t)(two >> off) & ((1u << cw) - 1)) + carry;
     int32_t d;
-    if (v > nb) {
-      d = (int32_t)v - (int32_t)(1u << c);
+    if (j < W - 1 && v > (1u << (cw - 1))) {
+      d = (int32_t)v - (int32_t)(1u << cw);
       carry = 1;
     } else {
       d = (int32_t)v;
@@ -160,11 +166,11 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 // ---------------------------------------------------------------------------------------------- host driver
 // Window width: minimise (bucket accumulation + bucket reduction) field multiplications.
 static int choose_window(size_t n) {
-  if (g_forced_window >= 2 && g_forced_window <= 22) return g_forced_window;
+  if (g_forced_window >= 3 && g_forced_window <= 22) return g_forced_window;
   double best = 1e300;
   int best_c = 4;
   for (int c = 3; c <= 20; c++) {
-    double W = 753 / c + 1;
+    double W = (754 + c - 1) / c;
     double nb = (double)(1u << (c - 1));
     double cost = W * ((double)n * 11.0 + nb * 2.0 * 14.0 + nb / 32.0 * 30.0 * 13.0);
     if (cost < best) {
@@ -176,7 +182,7 @@ static int choose_window(size_t n) {
 }
 
 struct MsmWorkspace {
-  DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b;
+  DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b, plan;
 };
 static MsmWorkspace &workspace() {
   static thread_local MsmWorkspace ws;
@@ -185,7 +191,7 @@ static MsmWorkspace &workspace() {
 void msm_release_workspace() {
   MsmWorkspace &ws = workspace();
   DevBuf *all[] = {&ws.digits, &ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.order,
-                   &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b};
+                   &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan};
   for (DevBuf *b : all) b->release();
 }
 
@@ -201,8 +207,20 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   }
   if (n >= (1ull << 30)) return set_error(-2, "msm: n=%zu too large", n);
   const int c = choose_window(n);
-  const int W = 753 / c + 1;
+  const int W = (754 + c - 1) / c;
   const uint32_t nb = 1u << (c - 1);
+  // window plan (see msm_digits_kernel): top window c-1 bits, `excess` low windows c-1 bits, the rest c bits
+  std::vector<uint32_t> plan(W);
+  {
+    int excess = W * c - 1 - 753;
+    uint32_t start = 0;
+    for (int j = 0; j < W; j++) {
+      uint32_t width = (j == W - 1 || j < excess) ? (uint32_t)(c - 1) : (uint32_t)c;
+      plan[j] = start | (width << 16);
+      start += width;
+    }
+    if (start != 753 || excess > W - 1) return set_error(-2, "msm: bad window plan c=%d", c);
+  }
   const size_t nbuckets = (size_t)W * nb;
   if ((size_t)W * n >= (1ull << 32)) return set_error(-2, "msm: W*n overflows 32-bit entry positions");
   MsmWorkspace &ws = workspace();
@@ -215,6 +233,8 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   B200_CHECK(ws.counts_sorted.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.iota.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
+  B200_CHECK(ws.plan.reserve(256 * sizeof(uint32_t)));
+  B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
   Timer tm;
 
   // ---- digits + histogram
@@ -222,7 +242,8 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   B200_CUDA_CHECK(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), 0));
   B200_CUDA_CHECK(cudaMemsetAsync(ws.cursor.p, 0, nbuckets * sizeof(uint32_t), 0));
   msm_digits_kernel<FrP><<<grid_for(n, 128), 128>>>((const Fp<FrP> *)d_scalars, (uint32_t)n, c, W,
-                                                    ws.digits.as<int32_t>(), ws.counts.as<uint32_t>());
+                                                    ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
+                                                    ws.counts.as<uint32_t>());
   B200_CUDA_CHECK(cudaGetLastError());
   g_phase_ms[0] = tm.stop();
 
@@ -289,7 +310,7 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   auto t0 = std::chrono::steady_clock::now();
   for (int j = W - 1; j >= 0; j--) {
     if (!proj_is_zero(result))
-      for (int k = 0; k < c; k++) proj_dbl<G>(result, result);
+      for (uint32_t k = 0; k < (plan[j] >> 16); k++) proj_dbl<G>(result, result);
     proj_add<G>(result, result, win[j]);
   }
   g_phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

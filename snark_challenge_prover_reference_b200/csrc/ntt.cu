@@ -21,11 +21,13 @@ namespace b200 {
 
 // ---------------------------------------------------------------------------------------------- kernels
 template <class P>
-__global__ void __launch_bounds__(128) powers_kernel(Fp<P> *__restrict__ out, size_t n, Fp<P> base, Fp<P> scale, uint32_t L) {
+__global__ void __launch_bounds__(128) powers_kernel(Fp<P> *__restrict__ out, size_t n, const Fp<P> *__restrict__ base_p,
+                                                     const Fp<P> *__restrict__ scale_p, uint32_t L) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t start = t * L;
   if (start >= n) return;
   uint32_t e[2] = {(uint32_t)start, (uint32_t)(start >> 32)};
+  const Fp<P> base = *base_p, scale = *scale_p;
   Fp<P> cur;
   Fp<P>::pow_words(cur, base, e, 2);
   Fp<P>::mul(cur, cur, scale);
@@ -36,7 +38,7 @@ __global__ void __launch_bounds__(128) powers_kernel(Fp<P> *__restrict__ out, si
 }
 
 template <class P>
-__global__ void __launch_bounds__(128) ntt_pass_kernel(const Fp<P> *__restrict__ src, Fp<P> *__restrict__ dst, int k,
+__global__ void __launch_bounds__(128) ntt_pass_kernel(const Fp<P> *src, Fp<P> *dst, int k,
                                                        int s0, int r, const Fp<P> *__restrict__ tw, int bitrev_in,
                                                        const Fp<P> *__restrict__ pre_tab,
                                                        const Fp<P> *__restrict__ post_tab,
@@ -142,10 +144,15 @@ static void load_const(Fp<P> &r, uint32_t (*f)(int)) {
 template <class P>
 static int fill_powers(DevBuf &buf, size_t n, const Fp<P> &base, const Fp<P> &scale) {
   B200_CHECK(buf.alloc(n * sizeof(Fp<P>)));
+  DevBuf args;
+  B200_CHECK(args.alloc(2 * sizeof(Fp<P>)));
+  Fp<P> hargs[2] = {base, scale};
+  B200_CUDA_CHECK(cudaMemcpy(args.p, hargs, sizeof(hargs), cudaMemcpyHostToDevice));
   const uint32_t L = 64;
   size_t threads = (n + L - 1) / L;
-  powers_kernel<P><<<grid_for(threads, 128), 128>>>(buf.as<Fp<P>>(), n, base, scale, L);
+  powers_kernel<P><<<grid_for(threads, 128), 128>>>(buf.as<Fp<P>>(), n, args.as<Fp<P>>(), args.as<Fp<P>>() + 1, L);
   B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaDeviceSynchronize());
   return 0;
 }
 
@@ -206,6 +213,13 @@ int domain_create(int curve, size_t m, Domain **out) {
   return 0;
 }
 void domain_destroy(Domain *d) { delete d; }
+int domain_table(const Domain *d, int which, void *h_out, size_t count) {
+  const DevBuf *t[6] = {&d->tw_fwd, &d->tw_inv, &d->coset, &d->icoset_scaled, &d->consts, &d->scratch};
+  if (which < 0 || which > 5) return set_error(-1, "bad table");
+  if (count * 96 > t[which]->bytes) return set_error(-1, "table has fewer entries");
+  B200_CUDA_CHECK(cudaMemcpy(h_out, t[which]->p, count * 96, cudaMemcpyDeviceToHost));
+  return 0;
+}
 size_t domain_size(const Domain *d) { return d->m; }
 
 enum { kPlain = 0, kInverse = 1, kCoset = 2, kInverseCoset = 3 };

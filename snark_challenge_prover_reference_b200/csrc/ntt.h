@@ -6,6 +6,8 @@ struct Domain;
 int domain_create(int curve, size_t m, Domain **out);
 void domain_destroy(Domain *d);
 size_t domain_size(const Domain *d);
+// test hook: first `count` entries of table 0 omega^i, 1 omega^-i, 2 g^i, 3 g^-i/m, 4 {1/m, 1/Z(g)}
+int domain_table(const Domain *d, int which, void *h_out, size_t count);
 // kind: 0 FFT, 1 iFFT, 2 cosetFFT, 3 icosetFFT
 int domain_transform(Domain *d, void *d_a, int kind);
 int domain_divide_by_z(Domain *d, void *d_a);
