@@ -130,6 +130,11 @@ int b200_dev_group_op(int curve, int group, int op, const void *d_p, const void 
 int b200_gen_points(int curve, int group, void *d_out_affine, size_t n, uint64_t first);
 /* IMAD roofline microbenchmark: independent IMAD.WIDE chains on every SM; returns MAC32/s */
 int b200_imad_peak(double *mac32_per_s, double *ms);
+/* number of CUDA kernels this library has launched so far (bench.py: gpu_launches) */
+unsigned long long b200_launch_count(void);
+/* accumulated MSM phase times (ms) since the last reset: out10 = G1 {digits, sort, accumulate, reduce, host tail},
+ * then the same five for G2 calls */
+int b200_msm_phase_totals(double *out10, int reset);
 /* time of the last MSM phases (ms): 0 digits, 1 sort, 2 accumulate, 3 reduce, 4 host tail */
 int b200_msm_last_phase_ms(double *out5);
 

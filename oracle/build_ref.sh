@@ -57,4 +57,15 @@ if [ ! -x "$OUT/piecewise_host" ]; then
      "$OUT"/obj/*.o $LIBS -o "$OUT/piecewise_host" &
 fi
 wait
+# Drop-in check of the boundary: the reference's OWN, unmodified prover driver (cuda_prover_piecewise.cu) compiled
+# against THIS repo's prover_reference_functions.hpp and linked to the B200 library instead of libff.
+PKG="$HERE/../snark_challenge_prover_reference_b200"
+if [ -f "$PKG/libb200groth16.so" ]; then
+  if [ ! -x "$OUT/piecewise_b200" ] || [ "$PKG/libb200groth16.so" -nt "$OUT/piecewise_b200" ]; then
+    g++ -std=c++14 -O2 -w -I"$PKG/csrc/host" -I"$HERE/../include" -I"$OUT/stub" \
+       -x c++ "$R/cuda_prover_piecewise.cu" -x c++ "$PKG/csrc/host/prover_reference_functions.cpp" -x none \
+       -L"$PKG" -lb200groth16 -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../../snark_challenge_prover_reference_b200' \
+       -o "$OUT/piecewise_b200"
+  fi
+fi
 ls -la "$OUT" | grep -v obj

@@ -81,6 +81,8 @@ _SIGNATURES = {
     "b200_msm_g2": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_msm_set_window": (_i, [_i]),
     "b200_msm_last_phase_ms": (_i, [ctypes.POINTER(ctypes.c_double)]),
+    "b200_msm_phase_totals": (_i, [ctypes.POINTER(ctypes.c_double), _i]),
+    "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200_g1_add": (_i, [_i, _vp, _vp, _vp]),
     "b200_g2_add": (_i, [_i, _vp, _vp, _vp]),
     "b200_g1_scale": (_i, [_i, _vp, _vp, _vp]),
@@ -202,6 +204,17 @@ def msm_phase_ms():
     arr = (ctypes.c_double * 5)()
     check(lib().b200_msm_last_phase_ms(arr))
     return dict(zip(("digits", "sort", "accumulate", "reduce", "host_tail"), list(arr)))
+
+
+def msm_phase_totals(reset=False):
+    arr = (ctypes.c_double * 10)()
+    check(lib().b200_msm_phase_totals(arr, 1 if reset else 0))
+    names = ("digits", "sort", "accumulate", "reduce", "host_tail")
+    return {"g1": dict(zip(names, list(arr)[:5])), "g2": dict(zip(names, list(arr)[5:]))}
+
+
+def launch_count():
+    return int(lib().b200_launch_count())
 
 
 class Domain:

@@ -65,8 +65,28 @@ def build(force=False, verbose=False):
     return LIB, logs
 
 
+def build_driver():
+    """Host-side C++ (the reference is C++): the B:: bundle over the C ABI + the command-line driver ->
+    bin/cuda_prover_piecewise, linked against the in-tree CUDA library (rpath $ORIGIN/..)."""
+    host = os.path.join(CSRC, "host")
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    exe = os.path.join(bindir, "cuda_prover_piecewise")
+    srcs = [os.path.join(host, "prover_reference_functions.cpp"), os.path.join(host, "cuda_prover_piecewise.cpp")]
+    deps = srcs + [os.path.join(host, "prover_reference_functions.hpp"), LIB]
+    if _newer(exe, deps):
+        return exe
+    cmd = ["/usr/bin/g++", "-std=c++14", "-O2", "-I", host, "-I", os.path.join(ROOT, "include")] + srcs + [
+        "-L", HERE, "-lb200groth16", "-Wl,-rpath,$ORIGIN/..", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host driver build failed:\n" + r.stderr[-4000:])
+    return exe
+
+
 if __name__ == "__main__":
     lib, logs = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     if logs:
         print(logs)
     print("built", lib)
+    print("built", build_driver())

@@ -25,6 +25,11 @@ int set_error(int code, const char *fmt, ...) {
   return code;
 }
 
+unsigned long long &launch_counter() {
+  static unsigned long long n = 0;
+  return n;
+}
+
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -227,6 +232,11 @@ int b200_msm_set_window(int c) {
   msm_set_window(c);
   return 0;
 }
+unsigned long long b200_launch_count(void) { return launch_counter(); }
+int b200_msm_phase_totals(double *out5, int reset) {
+  msm_phase_totals(out5, reset);
+  return 0;
+}
 int b200_msm_last_phase_ms(double *out5) {
   msm_last_phase_ms(out5);
   return 0;
@@ -362,10 +372,10 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   if (world < 1 || rank < 0 || rank >= world) return set_error(-1, "bad rank/world %d/%d", rank, world);
   const char *in = (const char *)h_input;
   double t0 = now_ms();
-  B200_CUDA_CHECK(cudaMemcpy(p->w.p, in, (m + 1) * 96, cudaMemcpyHostToDevice));
-  B200_CUDA_CHECK(cudaMemcpy(p->ca.p, in + (m + 1) * 96, (d + 1) * 96, cudaMemcpyHostToDevice));
-  B200_CUDA_CHECK(cudaMemcpy(p->cb.p, in + (m + 1) * 96 + (d + 1) * 96, (d + 1) * 96, cudaMemcpyHostToDevice));
-  B200_CUDA_CHECK(cudaMemcpy(p->cc.p, in + (m + 1) * 96 + 2 * (d + 1) * 96, (d + 1) * 96, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpy(p->w.p, in, (m + 1) * 96, cudaMemcpyDefault));
+  B200_CUDA_CHECK(cudaMemcpy(p->ca.p, in + (m + 1) * 96, (d + 1) * 96, cudaMemcpyDefault));
+  B200_CUDA_CHECK(cudaMemcpy(p->cb.p, in + (m + 1) * 96 + (d + 1) * 96, (d + 1) * 96, cudaMemcpyDefault));
+  B200_CUDA_CHECK(cudaMemcpy(p->cc.p, in + (m + 1) * 96 + 2 * (d + 1) * 96, (d + 1) * 96, cudaMemcpyDefault));
   double t1 = now_ms();
   B200_CHECK(b200_compute_h(p->dom, p->ca.p, p->cb.p, p->cc.p, p->h.p));
   B200_CUDA_CHECK(cudaDeviceSynchronize());

@@ -79,6 +79,10 @@ struct Timer {  // CUDA-event timer on the default stream
   }
 };
 
+// number of kernels this library launched (bench.py reports it as gpu_launches)
+unsigned long long &launch_counter();
+static inline void note_launch(unsigned n = 1) { launch_counter() += n; }
+
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 }  // namespace b200

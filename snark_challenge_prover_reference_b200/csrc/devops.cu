@@ -207,6 +207,7 @@ int imad_peak(double *mac32_per_s2, double *ms2) {
       if (rep > 0 && ms < best) best = ms;
     }
     B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
     mac32_per_s2[variant] = macs / (best * 1e-3);
     ms2[variant] = best;
   }
@@ -221,6 +222,7 @@ static int fp_op_t(int op, const void *a, const void *b, void *r, size_t n) {
   else
     fp_conv_kernel<P><<<grid_for(n, 128), 128>>>(op, (const Fp<P> *)a, (Fp<P> *)r, n);
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 int dev_fp_op(int tag, int op, const void *a, const void *b, void *r, size_t n) {
@@ -239,12 +241,14 @@ int dev_fqe_op(int curve, int op, const void *a, const void *b, void *r, size_t 
     field_op_kernel<F><<<grid_for(n, 128), 128>>>(op, (const F *)a, (const F *)b, (F *)r, n);
   }
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 template <class G>
 static int group_op_t(int op, const void *p, const void *q, void *r, size_t n) {
   group_op_kernel<G><<<grid_for(n, 128), 128>>>(op, p, q, r, n);
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 int dev_group_op(int curve, int group, int op, const void *p, const void *q, void *r, size_t n) {
@@ -262,6 +266,7 @@ static int gen_points_t(void *out, size_t n, uint64_t first) {
   size_t threads = (n + L - 1) / L;
   gen_points_kernel<G><<<grid_for(threads, 128), 128>>>((Affine<typename G::F> *)out, n, first, L);
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 int gen_points(int curve, int group, void *out, size_t n, uint64_t first) {

@@ -1,0 +1,245 @@
+// `B::` over the C ABI (include/b200_groth16.h). Host code only: files are read with one bulk read each, vectors are
+// handles to device memory, the O(1) group operations of the prover tail run on the host inside the library.
+// Reference counterpart: libsnark/prover_reference_functions.cpp (libff-backed, CPU).
+//
+// Error behaviour: the reference returns void / pointers and never reports failure (unchecked fopen/fread,
+// SURVEY.md 8b). Here any failing C-ABI call or short file aborts with a message on stderr - there is no CPU fallback.
+#include "prover_reference_functions.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "b200_groth16.h"
+
+namespace b200_host {
+
+[[noreturn]] static void die(const char *what) {
+  fprintf(stderr, "b200 prover: %s failed: %s\n", what, b200_last_error());
+  exit(1);
+}
+#define B200_OK(call)            \
+  do {                           \
+    if ((call) != 0) die(#call); \
+  } while (0)
+
+struct device_mem {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  explicit device_mem(size_t n) : bytes(n) { B200_OK(b200_malloc(&ptr, n)); }
+  device_mem(const device_mem &) = delete;
+  ~device_mem() { b200_free(ptr); }
+  char *at(size_t element) const { return (char *)ptr + element * B200_FE_BYTES; }
+};
+struct params_box {
+  b200_params *h = nullptr;
+  ~params_box() { b200_params_destroy(h); }
+};
+struct domain_box {
+  b200_domain *h = nullptr;
+  ~domain_box() { b200_domain_destroy(h); }
+};
+
+static std::vector<unsigned char> slurp(const char *path) {
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    fprintf(stderr, "b200 prover: cannot open %s\n", path);
+    exit(1);
+  }
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<unsigned char> buf((size_t)n);
+  if (n > 0 && fread(buf.data(), 1, (size_t)n, f) != (size_t)n) {
+    fprintf(stderr, "b200 prover: short read on %s\n", path);
+    exit(1);
+  }
+  fclose(f);
+  return buf;
+}
+
+static void print_hex_elems(const unsigned char *p, size_t count) {
+  for (size_t e = 0; e < count; e++) {
+    printf(e ? ", 0x" : "0x");
+    for (int i = 95; i >= 0; i--) printf("%02x", p[e * 96 + i]);
+  }
+}
+}  // namespace b200_host
+
+using namespace b200_host;
+
+#define BUNDLE template <int CURVE>
+#define B b200_groth16_bundle<CURVE>
+
+BUNDLE void B::init_public_params() {
+  // libff's init_*_params fills global constants (mnt4753_pp.cpp:18-21); here they are compile-time constants of the
+  // CUDA library. Selecting the device is the only run-time initialisation.
+  const char *dev = getenv("B200_DEVICE");
+  B200_OK(b200_set_device(dev ? atoi(dev) : 0));
+}
+
+BUNDLE void B::print_G1(G1 *a) {
+  unsigned char xy[2 * 96];
+  B200_OK(b200_g1_to_affine(CURVE, a->bytes, xy));
+  printf("(");
+  print_hex_elems(xy, 2);
+  printf(")  [affine, Montgomery limbs]\n");
+}
+BUNDLE void B::print_G2(G2 *a) {
+  const size_t deg = CURVE == 0 ? 2 : 3;
+  std::vector<unsigned char> xy(2 * deg * 96);
+  B200_OK(b200_g2_to_affine(CURVE, a->bytes, xy.data()));
+  printf("(");
+  print_hex_elems(xy.data(), 2 * deg);
+  printf(")  [affine, Montgomery limbs]\n");
+}
+
+BUNDLE typename B::evaluation_domain *B::get_evaluation_domain(size_t d) {
+  auto box = std::make_shared<domain_box>();
+  B200_OK(b200_domain_create(CURVE, d, &box->h));
+  return new evaluation_domain{box};
+}
+
+BUNDLE typename B::G1 *B::G1_add(G1 *a, G1 *b) {
+  G1 *r = new G1();
+  B200_OK(b200_g1_add(CURVE, a->bytes, b->bytes, r->bytes));
+  return r;
+}
+BUNDLE typename B::G1 *B::G1_scale(field *a, G1 *b) {
+  G1 *r = new G1();
+  B200_OK(b200_g1_scale(CURVE, a->bytes, b->bytes, r->bytes));
+  return r;
+}
+
+BUNDLE void B::vector_Fr_muleq(vector_Fr *a, vector_Fr *b, size_t size) {
+  B200_OK(b200_fr_muleq(CURVE, a->data->at(a->offset), b->data->at(b->offset), size));
+}
+BUNDLE void B::vector_Fr_subeq(vector_Fr *a, vector_Fr *b, size_t size) {
+  B200_OK(b200_fr_subeq(CURVE, a->data->at(a->offset), b->data->at(b->offset), size));
+}
+BUNDLE typename B::vector_Fr *B::vector_Fr_offset(vector_Fr *a, size_t offset) {
+  return new vector_Fr{a->data, a->offset + offset};
+}
+BUNDLE void B::vector_Fr_copy_into(vector_Fr *src, vector_Fr *dst, size_t length) {
+  // (the mnt4753 reference ignores src->offset here, prover_reference_functions.cpp:200-214; the mnt6753 one honours
+  // it, :515-520. Every call site passes offset 0; offsets are honoured.)
+  B200_OK(b200_memcpy_d2d(dst->data->at(dst->offset), src->data->at(src->offset), length * B200_FE_BYTES));
+}
+BUNDLE typename B::vector_Fr *B::vector_Fr_zeros(size_t length) {
+  auto mem = std::make_shared<device_mem>(length * B200_FE_BYTES);
+  B200_OK(b200_memset_zero(mem->ptr, length * B200_FE_BYTES));
+  return new vector_Fr{mem, 0};
+}
+
+BUNDLE void B::domain_iFFT(evaluation_domain *domain, vector_Fr *a) {
+  B200_OK(b200_domain_ifft(domain->box->h, a->data->at(a->offset)));
+}
+BUNDLE void B::domain_cosetFFT(evaluation_domain *domain, vector_Fr *a) {
+  B200_OK(b200_domain_coset_fft(domain->box->h, a->data->at(a->offset)));
+}
+BUNDLE void B::domain_icosetFFT(evaluation_domain *domain, vector_Fr *a) {
+  B200_OK(b200_domain_icoset_fft(domain->box->h, a->data->at(a->offset)));
+}
+BUNDLE void B::domain_divide_by_Z_on_coset(evaluation_domain *domain, vector_Fr *a) {
+  B200_OK(b200_domain_divide_by_z_on_coset(domain->box->h, a->data->at(a->offset)));
+}
+BUNDLE size_t B::domain_get_m(evaluation_domain *domain) { return b200_domain_size(domain->box->h); }
+
+BUNDLE typename B::G1 *B::multiexp_G1(vector_Fr *scalar_start, vector_G1 *g_start, size_t length) {
+  G1 *r = new G1();
+  B200_OK(b200_msm_g1(CURVE, scalar_start->data->at(scalar_start->offset), g_start->data, length, r->bytes));
+  return r;
+}
+BUNDLE typename B::G2 *B::multiexp_G2(vector_Fr *scalar_start, vector_G2 *g_start, size_t length) {
+  G2 *r = new G2();
+  B200_OK(b200_msm_g2(CURVE, scalar_start->data->at(scalar_start->offset), g_start->data, length, r->bytes));
+  return r;
+}
+
+BUNDLE typename B::groth16_input *B::read_input(const char *path, groth16_params *params) {
+  // file layout: w[m+1], ca[d+1], cb[d+1], cc[d+1], r  (libsnark/main.cpp:63-83)
+  const size_t d = params->d, m = params->m;
+  std::vector<unsigned char> img = slurp(path);
+  const size_t need = B200_FE_BYTES * ((m + 1) + 3 * (d + 1) + 1);
+  if (img.size() != need) {
+    fprintf(stderr, "b200 prover: %s has %zu bytes, expected %zu\n", path, img.size(), need);
+    exit(1);
+  }
+  groth16_input *in = new groth16_input();
+  const unsigned char *p = img.data();
+  auto upload = [&](size_t count) {
+    auto mem = std::make_shared<device_mem>(count * B200_FE_BYTES);
+    B200_OK(b200_memcpy_h2d(mem->ptr, p, count * B200_FE_BYTES));
+    p += count * B200_FE_BYTES;
+    return mem;
+  };
+  in->w = upload(m + 1);
+  in->ca = upload(d + 1);
+  in->cb = upload(d + 1);
+  in->cc = upload(d + 1);
+  memcpy(in->r.bytes, p, B200_FE_BYTES);
+  return in;
+}
+
+BUNDLE typename B::vector_Fr *B::input_w(groth16_input *input) { return new vector_Fr{input->w, 0}; }
+BUNDLE typename B::vector_Fr *B::input_ca(groth16_input *input) { return new vector_Fr{input->ca, 0}; }
+BUNDLE typename B::vector_Fr *B::input_cb(groth16_input *input) { return new vector_Fr{input->cb, 0}; }
+BUNDLE typename B::vector_Fr *B::input_cc(groth16_input *input) { return new vector_Fr{input->cc, 0}; }
+BUNDLE typename B::field *B::input_r(groth16_input *input) { return new field(input->r); }
+
+BUNDLE typename B::groth16_params *B::read_params(const char *path) {
+  std::vector<unsigned char> img = slurp(path);
+  auto box = std::make_shared<params_box>();
+  B200_OK(b200_params_from_host(CURVE, img.data(), img.size(), &box->h));
+  groth16_params *p = new groth16_params();
+  p->d = b200_params_d(box->h);
+  p->m = b200_params_m(box->h);
+  p->box = box;
+  return p;
+}
+BUNDLE size_t B::params_d(groth16_params *params) { return params->d; }
+BUNDLE size_t B::params_m(groth16_params *params) { return params->m; }
+BUNDLE typename B::vector_G1 *B::params_A(groth16_params *params) {
+  return new vector_G1{params->box, b200_params_query(params->box->h, 0)};
+}
+BUNDLE typename B::vector_G1 *B::params_B1(groth16_params *params) {
+  return new vector_G1{params->box, b200_params_query(params->box->h, 1)};
+}
+BUNDLE typename B::vector_G2 *B::params_B2(groth16_params *params) {
+  return new vector_G2{params->box, b200_params_query(params->box->h, 2)};
+}
+BUNDLE typename B::vector_G1 *B::params_L(groth16_params *params) {
+  return new vector_G1{params->box, b200_params_query(params->box->h, 3)};
+}
+BUNDLE typename B::vector_G1 *B::params_H(groth16_params *params) {
+  return new vector_G1{params->box, b200_params_query(params->box->h, 4)};
+}
+
+BUNDLE void B::delete_G1(G1 *a) { delete a; }
+BUNDLE void B::delete_G2(G1 *a) { delete a; }
+BUNDLE void B::delete_G2(G2 *a) { delete a; }
+BUNDLE void B::delete_vector_Fr(vector_Fr *a) { delete a; }
+BUNDLE void B::delete_vector_G1(vector_G1 *a) { delete a; }
+BUNDLE void B::delete_vector_G2(vector_G2 *a) { delete a; }
+BUNDLE void B::delete_groth16_input(groth16_input *a) { delete a; }
+BUNDLE void B::delete_groth16_params(groth16_params *a) { delete a; }
+BUNDLE void B::delete_evaluation_domain(evaluation_domain *a) { delete a; }
+
+BUNDLE void B::groth16_output_write(G1 *A, G2 *Bp, G1 *C, const char *output_path) {
+  // A (G1) | B (G2) | C (G1), affine, O -> zero bytes  (main.cpp:94-100, serialization.hpp:43-67)
+  const size_t deg = CURVE == 0 ? 2 : 3;
+  std::vector<unsigned char> out(2 * 96 + 2 * deg * 96 + 2 * 96);
+  B200_OK(b200_g1_to_affine(CURVE, A->bytes, out.data()));
+  B200_OK(b200_g2_to_affine(CURVE, Bp->bytes, out.data() + 2 * 96));
+  B200_OK(b200_g1_to_affine(CURVE, C->bytes, out.data() + 2 * 96 + 2 * deg * 96));
+  FILE *f = fopen(output_path, "wb");
+  if (!f || fwrite(out.data(), 1, out.size(), f) != out.size()) {
+    fprintf(stderr, "b200 prover: cannot write %s\n", output_path);
+    exit(1);
+  }
+  fclose(f);
+}
+
+template class b200_groth16_bundle<0>;
+template class b200_groth16_bundle<1>;

@@ -25,8 +25,16 @@
 namespace b200 {
 
 static double g_phase_ms[5] = {0, 0, 0, 0, 0};
+static double g_phase_total[2][5];  // [0] = G1 calls, [1] = G2 calls; accumulated until reset
 static int g_forced_window = 0;
 void msm_set_window(int c) { g_forced_window = c; }
+void msm_phase_totals(double *out10, int reset) {
+  for (int g = 0; g < 2; g++)
+    for (int i = 0; i < 5; i++) {
+      out10[g * 5 + i] = g_phase_total[g][i];
+      if (reset) g_phase_total[g][i] = 0;
+    }
+}
 void msm_last_phase_ms(double *out5) {
   for (int i = 0; i < 5; i++) out5[i] = g_phase_ms[i];
 }
@@ -245,6 +253,7 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
                                                     ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
                                                     ws.counts.as<uint32_t>());
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   g_phase_ms[0] = tm.stop();
 
   // ---- counting sort: scan, scatter; then bucket order by descending size
@@ -266,8 +275,10 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
                                                       ws.offsets.as<uint32_t>(), ws.cursor.as<uint32_t>(),
                                                       ws.entries.as<uint32_t>());
     B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   }
   iota_kernel<<<grid_for(nbuckets, 256), 256>>>(ws.iota.as<uint32_t>(), (uint32_t)nbuckets);
+  note_launch();
   tb = ws.cub_tmp.bytes;
   B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(ws.cub_tmp.p, tb, ws.counts.as<uint32_t>(),
                                                             ws.counts_sorted.as<uint32_t>(), ws.iota.as<uint32_t>(),
@@ -280,6 +291,7 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
       (const Affine<F> *)d_points, ws.entries.as<uint32_t>(), ws.offsets.as<uint32_t>(),
       ws.counts_sorted.as<uint32_t>(), ws.order.as<uint32_t>(), (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   g_phase_ms[2] = tm.stop();
 
   // ---- bucket reduction: chunks of K buckets, then tree sum per window
@@ -291,12 +303,14 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   msm_reduce_kernel<G><<<grid_for((size_t)W * per, 128), 128>>>(ws.buckets.as<Proj<F>>(), W, nb, K,
                                                                ws.red_a.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   Proj<F> *cur = ws.red_a.as<Proj<F>>(), *nxt = ws.red_b.as<Proj<F>>();
   while (per > 1) {
     uint32_t R = 8;
     uint32_t per_out = (per + R - 1) / R;
     msm_sum_kernel<G><<<grid_for((size_t)W * per_out, 128), 128>>>(cur, W, per, R, nxt);
     B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
     Proj<F> *t = cur;
     cur = nxt;
     nxt = t;
@@ -314,6 +328,7 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
     proj_add<G>(result, result, win[j]);
   }
   g_phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  for (int i = 0; i < 5; i++) g_phase_total[F::kDegree == 1 ? 0 : 1][i] += g_phase_ms[i];
   memcpy(h_out, &result, sizeof(result));
   return 0;
 }

@@ -6,5 +6,7 @@ namespace b200 {
 int msm_dispatch(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out);
 void msm_set_window(int c);
 void msm_last_phase_ms(double *out5);
+// accumulated phase times since the last reset: out10 = G1 {digits, sort, accumulate, reduce, host}, then G2
+void msm_phase_totals(double *out10, int reset);
 void msm_release_workspace();
 }  // namespace b200

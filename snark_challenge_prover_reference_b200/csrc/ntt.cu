@@ -152,6 +152,7 @@ static int fill_powers(DevBuf &buf, size_t n, const Fp<P> &base, const Fp<P> &sc
   size_t threads = (n + L - 1) / L;
   powers_kernel<P><<<grid_for(threads, 128), 128>>>(buf.as<Fp<P>>(), n, args.as<Fp<P>>(), args.as<Fp<P>>() + 1, L);
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   B200_CUDA_CHECK(cudaDeviceSynchronize());
   return 0;
 }
@@ -247,6 +248,7 @@ static int transform(Domain *d, void *d_a, int kind) {
     ntt_pass_kernel<P><<<(unsigned)blocks, threads, smem>>>(src, dst, k, s0, r, tw, p == 0 ? 1 : 0, p == 0 ? pre : nullptr,
                                                             last ? post_tab : nullptr, last ? post_const : nullptr);
     B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
     s0 += r;
   }
   if (npass == 1) B200_CUDA_CHECK(cudaMemcpyAsync(a, scr, d->m * sizeof(F), cudaMemcpyDeviceToDevice, 0));
@@ -261,6 +263,7 @@ template <class P>
 static int scale_by(Domain *d, void *d_a, int which) {
   fr_scale_kernel<P><<<grid_for(d->m, 128), 128>>>((Fp<P> *)d_a, d->consts.as<Fp<P>>() + which, d->m);
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 int domain_divide_by_z(Domain *d, void *d_a) {
@@ -274,6 +277,7 @@ int fr_muleq(int curve, void *d_a, const void *d_b, size_t n) {
   else
     fr_muleq_kernel<PrimeB><<<grid_for(n, 128), 128>>>((Fp<PrimeB> *)d_a, (const Fp<PrimeB> *)d_b, n);
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 int fr_subeq(int curve, void *d_a, const void *d_b, size_t n) {
@@ -283,6 +287,7 @@ int fr_subeq(int curve, void *d_a, const void *d_b, size_t n) {
   else
     fr_subeq_kernel<PrimeB><<<grid_for(n, 128), 128>>>((Fp<PrimeB> *)d_a, (const Fp<PrimeB> *)d_b, n);
   B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
   return 0;
 }
 
