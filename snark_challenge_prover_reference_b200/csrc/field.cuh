@@ -173,26 +173,22 @@ struct alignas(16) Fp {
     sub(r, z, a);
   }
 #if defined(__CUDACC__)
-  // out-of-line device multiply: operands come from (local/shared/global) memory, limbs live in registers only
-  // inside the body. One copy per modulus per module keeps the instruction footprint inside the 32 KB L1.5 I-cache.
-  static __device__ __noinline__ void mul_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
-    uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
-#pragma unroll
-    for (int i = 0; i < kLimbs; i++) {
-      x[i] = a[i];
-      y[i] = b[i];
-    }
+  // out-of-line device multiply (one copy of the ~1.3k-instruction body per modulus per module keeps the instruction
+  // footprint inside the 32 KB L1.5 I-cache). Operands and result are passed BY VALUE: the device ABI carries the
+  // 2 x 24 input words and the 24 result words in registers, so field elements stay in registers across the call
+  // and only what the register allocator cannot hold is spilled.
+  static __device__ __noinline__ Fp mul_val(Fp a, Fp b) {
+    Fp r;
     if (P::kTag == 'A')
-      fp_mul_ptx_A(z, x, y);
+      fp_mul_ptx_A(r.l, a.l, b.l);
     else
-      fp_mul_ptx_B(z, x, y);
-#pragma unroll
-    for (int i = 0; i < kLimbs; i++) r[i] = z[i];
+      fp_mul_ptx_B(r.l, a.l, b.l);
+    return r;
   }
 #endif
   B200_HD static B200_INLINE void mul(Fp &r, const Fp &a, const Fp &b) {
 #if defined(__CUDA_ARCH__)
-    mul_dev(r.l, a.l, b.l);
+    r = mul_val(a, b);
 #else
     host_mul(r, a, b);
 #endif
