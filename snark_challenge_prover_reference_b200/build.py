@@ -13,7 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200groth16.so")
-SOURCES = ["msm.cu", "ntt.cu", "devops.cu", "capi.cu"]
+SOURCES = ["msm_g_mnt6g2.cu", "devops_g_mnt6g2.cu", "msm_g_mnt4g2.cu", "devops_g_mnt4g2.cu", "msm_g_mnt4g1.cu", "msm_g_mnt6g1.cu",
+           "devops_g_mnt4g1.cu", "devops_g_mnt6g1.cu", "devops.cu", "msm.cu", "ntt.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
@@ -52,7 +53,7 @@ def build(force=False, verbose=False):
             os.remove(os.path.join(OBJ, f))
         if os.path.exists(LIB):
             os.remove(LIB)
-    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     objs = [o for o, _ in results]
     logs = "\n".join(l for _, l in results if l)

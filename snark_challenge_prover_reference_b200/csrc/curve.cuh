@@ -80,7 +80,7 @@ B200_HD inline void proj_from_affine(Proj<F> &r, const Affine<F> &a) {
 }
 
 template <class G>
-B200_HD void proj_dbl(Proj<typename G::F> &r, const Proj<typename G::F> &p) {
+B200_HD B200_NOINLINE void proj_dbl(Proj<typename G::F> &r, const Proj<typename G::F> &p) {
   typedef typename G::F F;
   if (proj_is_zero(p)) {
     r = p;

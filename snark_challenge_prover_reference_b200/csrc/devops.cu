@@ -35,83 +35,6 @@ __global__ void __launch_bounds__(128) fp_conv_kernel(int op, const Fp<P> *__res
   r[i] = z;
 }
 
-template <class G>
-__global__ void __launch_bounds__(128) group_op_kernel(int op, const void *__restrict__ p, const void *__restrict__ q,
-                                                       void *__restrict__ r, size_t n) {
-  typedef typename G::F F;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Proj<F> a = ((const Proj<F> *)p)[i], c;
-  if (op == 0) {
-    Proj<F> b = ((const Proj<F> *)q)[i];
-    proj_add<G>(c, a, b);
-    ((Proj<F> *)r)[i] = c;
-  } else if (op == 1) {
-    proj_dbl<G>(c, a);
-    ((Proj<F> *)r)[i] = c;
-  } else if (op == 2) {
-    Affine<F> b = ((const Affine<F> *)q)[i];
-    if (!affine_is_zero(b)) proj_madd<G>(a, b);
-    ((Proj<F> *)r)[i] = a;
-  } else {
-    Affine<F> o;
-    proj_to_affine<G>(o, a);
-    ((Affine<F> *)r)[i] = o;
-  }
-}
-
-// ---- generators ------------------------------------------------------------------------------------------------
-template <class G> struct GenOf;
-template <> struct GenOf<Mnt4G1> {
-  B200_HD static void get(Affine<Mnt4G1::F> &g) {
-    for (int i = 0; i < kLimbs; i++) { g.x.l[i] = MNT4753Gen::g1x(i); g.y.l[i] = MNT4753Gen::g1y(i); }
-  }
-};
-template <> struct GenOf<Mnt6G1> {
-  B200_HD static void get(Affine<Mnt6G1::F> &g) {
-    for (int i = 0; i < kLimbs; i++) { g.x.l[i] = MNT6753Gen::g1x(i); g.y.l[i] = MNT6753Gen::g1y(i); }
-  }
-};
-template <> struct GenOf<Mnt4G2> {
-  B200_HD static void get(Affine<Mnt4G2::F> &g) {
-    for (int i = 0; i < kLimbs; i++) {
-      g.x.c0.l[i] = MNT4753Gen::g2x0(i); g.x.c1.l[i] = MNT4753Gen::g2x1(i);
-      g.y.c0.l[i] = MNT4753Gen::g2y0(i); g.y.c1.l[i] = MNT4753Gen::g2y1(i);
-    }
-  }
-};
-template <> struct GenOf<Mnt6G2> {
-  B200_HD static void get(Affine<Mnt6G2::F> &g) {
-    for (int i = 0; i < kLimbs; i++) {
-      g.x.c0.l[i] = MNT6753Gen::g2x0(i); g.x.c1.l[i] = MNT6753Gen::g2x1(i); g.x.c2.l[i] = MNT6753Gen::g2x2(i);
-      g.y.c0.l[i] = MNT6753Gen::g2y0(i); g.y.c1.l[i] = MNT6753Gen::g2y1(i); g.y.c2.l[i] = MNT6753Gen::g2y2(i);
-    }
-  }
-};
-
-// out[i] = (first + i) * G, affine wire format. One thread walks a run of L consecutive multiples.
-template <class G>
-__global__ void __launch_bounds__(128) gen_points_kernel(Affine<typename G::F> *__restrict__ out, size_t n,
-                                                         unsigned long long first, uint32_t L) {
-  typedef typename G::F F;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t start = t * L;
-  if (start >= n) return;
-  Affine<F> g;
-  GenOf<G>::get(g);
-  Proj<F> gp, cur;
-  proj_from_affine(gp, g);
-  unsigned long long k0 = first + start;
-  uint32_t kw[2] = {(uint32_t)k0, (uint32_t)(k0 >> 32)};
-  proj_scalar_mul<G>(cur, gp, kw, 2);
-  for (uint32_t i = 0; i < L && start + i < n; i++) {
-    Affine<F> a;
-    proj_to_affine<G>(a, cur);
-    out[start + i] = a;
-    proj_madd<G>(cur, g);
-  }
-}
-
 // ---- IMAD roofline microbenchmarks -----------------------------------------------------------------------------
 // (1) independent mad.wide.u32 chains (8 per thread): the raw IMAD.WIDE issue rate of the chip.
 __global__ void __launch_bounds__(256) imad_wide_kernel(unsigned long long *out, uint32_t b, int iters) {
@@ -244,37 +167,29 @@ int dev_fqe_op(int curve, int op, const void *a, const void *b, void *r, size_t 
   note_launch();
   return 0;
 }
-template <class G>
-static int group_op_t(int op, const void *p, const void *q, void *r, size_t n) {
-  group_op_kernel<G><<<grid_for(n, 128), 128>>>(op, p, q, r, n);
-  B200_CUDA_CHECK(cudaGetLastError());
-  note_launch();
-  return 0;
-}
+int group_op_mnt4g1(int, const void *, const void *, void *, size_t);
+int group_op_mnt4g2(int, const void *, const void *, void *, size_t);
+int group_op_mnt6g1(int, const void *, const void *, void *, size_t);
+int group_op_mnt6g2(int, const void *, const void *, void *, size_t);
+int gen_points_mnt4g1(void *, size_t, uint64_t);
+int gen_points_mnt4g2(void *, size_t, uint64_t);
+int gen_points_mnt6g1(void *, size_t, uint64_t);
+int gen_points_mnt6g2(void *, size_t, uint64_t);
 int dev_group_op(int curve, int group, int op, const void *p, const void *q, void *r, size_t n) {
   if (n == 0) return 0;
   if (op < 0 || op > 3) return set_error(-1, "dev_group_op: bad op %d", op);
-  if (curve == 0 && group == 1) return group_op_t<Mnt4G1>(op, p, q, r, n);
-  if (curve == 0 && group == 2) return group_op_t<Mnt4G2>(op, p, q, r, n);
-  if (curve == 1 && group == 1) return group_op_t<Mnt6G1>(op, p, q, r, n);
-  if (curve == 1 && group == 2) return group_op_t<Mnt6G2>(op, p, q, r, n);
+  if (curve == 0 && group == 1) return group_op_mnt4g1(op, p, q, r, n);
+  if (curve == 0 && group == 2) return group_op_mnt4g2(op, p, q, r, n);
+  if (curve == 1 && group == 1) return group_op_mnt6g1(op, p, q, r, n);
+  if (curve == 1 && group == 2) return group_op_mnt6g2(op, p, q, r, n);
   return set_error(-1, "dev_group_op: bad curve/group");
-}
-template <class G>
-static int gen_points_t(void *out, size_t n, uint64_t first) {
-  const uint32_t L = 8;
-  size_t threads = (n + L - 1) / L;
-  gen_points_kernel<G><<<grid_for(threads, 128), 128>>>((Affine<typename G::F> *)out, n, first, L);
-  B200_CUDA_CHECK(cudaGetLastError());
-  note_launch();
-  return 0;
 }
 int gen_points(int curve, int group, void *out, size_t n, uint64_t first) {
   if (n == 0) return 0;
-  if (curve == 0 && group == 1) return gen_points_t<Mnt4G1>(out, n, first);
-  if (curve == 0 && group == 2) return gen_points_t<Mnt4G2>(out, n, first);
-  if (curve == 1 && group == 1) return gen_points_t<Mnt6G1>(out, n, first);
-  if (curve == 1 && group == 2) return gen_points_t<Mnt6G2>(out, n, first);
+  if (curve == 0 && group == 1) return gen_points_mnt4g1(out, n, first);
+  if (curve == 0 && group == 2) return gen_points_mnt4g2(out, n, first);
+  if (curve == 1 && group == 1) return gen_points_mnt6g1(out, n, first);
+  if (curve == 1 && group == 2) return gen_points_mnt6g2(out, n, first);
   return set_error(-1, "gen_points: bad curve/group");
 }
 

@@ -1,0 +1,6 @@
+// Mnt4G1 instantiation of the group test/bench kernels (see devops_group.cuh).
+#include "devops_group.cuh"
+namespace b200 {
+int group_op_mnt4g1(int op, const void *p, const void *q, void *r, size_t n) { return group_op_t<Mnt4G1>(op, p, q, r, n); }
+int gen_points_mnt4g1(void *out, size_t n, uint64_t first) { return gen_points_t<Mnt4G1>(out, n, first); }
+}  // namespace b200

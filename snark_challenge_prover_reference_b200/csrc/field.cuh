@@ -18,9 +18,14 @@
 #include "fp_ptx_gen.cuh"
 #define B200_DEV __device__
 #define B200_INLINE __forceinline__
+// Tower-field operations are kept out of line on the device: a G2 mixed addition inlines to >300 KB of straight-line
+// add/sub chains otherwise, which thrashes the instruction cache (ncu: no_instruction was the top stall) and gives
+// every inlined temporary its own stack slot (6.5 KB / thread of local memory spilling to DRAM).
+#define B200_NOINLINE __noinline__
 #else
 #define B200_DEV
 #define B200_INLINE inline
+#define B200_NOINLINE
 #endif
 
 namespace b200 {
@@ -173,22 +178,26 @@ struct alignas(16) Fp {
     sub(r, z, a);
   }
 #if defined(__CUDACC__)
-  // out-of-line device multiply (one copy of the ~1.3k-instruction body per modulus per module keeps the instruction
-  // footprint inside the 32 KB L1.5 I-cache). Operands and result are passed BY VALUE: the device ABI carries the
-  // 2 x 24 input words and the 24 result words in registers, so field elements stay in registers across the call
-  // and only what the register allocator cannot hold is spilled.
-  static __device__ __noinline__ Fp mul_val(Fp a, Fp b) {
-    Fp r;
+  // out-of-line device multiply: operands come from (local/shared/global) memory, limbs live in registers only
+  // inside the body. One copy per modulus per module keeps the instruction footprint inside the 32 KB L1.5 I-cache.
+  static __device__ __noinline__ void mul_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) {
+      x[i] = a[i];
+      y[i] = b[i];
+    }
     if (P::kTag == 'A')
-      fp_mul_ptx_A(r.l, a.l, b.l);
+      fp_mul_ptx_A(z, x, y);
     else
-      fp_mul_ptx_B(r.l, a.l, b.l);
-    return r;
+      fp_mul_ptx_B(z, x, y);
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) r[i] = z[i];
   }
 #endif
   B200_HD static B200_INLINE void mul(Fp &r, const Fp &a, const Fp &b) {
 #if defined(__CUDA_ARCH__)
-    r = mul_val(a, b);
+    mul_dev(r.l, a.l, b.l);
 #else
     host_mul(r, a, b);
 #endif
@@ -264,11 +273,11 @@ struct alignas(16) Fp2 {
   B200_HD static void set_one(Fp2 &r) { B::set_one(r.c0); B::set_zero(r.c1); }
   B200_HD static bool is_zero(const Fp2 &a) { return B::is_zero(a.c0) && B::is_zero(a.c1); }
   B200_HD static bool eq(const Fp2 &a, const Fp2 &b) { return B::eq(a.c0, b.c0) && B::eq(a.c1, b.c1); }
-  B200_HD static void add(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::add(r.c0, a.c0, b.c0); B::add(r.c1, a.c1, b.c1); }
-  B200_HD static void sub(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::sub(r.c0, a.c0, b.c0); B::sub(r.c1, a.c1, b.c1); }
-  B200_HD static void dbl(Fp2 &r, const Fp2 &a) { B::dbl(r.c0, a.c0); B::dbl(r.c1, a.c1); }
-  B200_HD static void neg(Fp2 &r, const Fp2 &a) { B::neg(r.c0, a.c0); B::neg(r.c1, a.c1); }
-  B200_HD static void mul(Fp2 &r, const Fp2 &a, const Fp2 &b) {  // Karatsuba, 3 base multiplications
+  B200_HD static B200_NOINLINE void add(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::add(r.c0, a.c0, b.c0); B::add(r.c1, a.c1, b.c1); }
+  B200_HD static B200_NOINLINE void sub(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::sub(r.c0, a.c0, b.c0); B::sub(r.c1, a.c1, b.c1); }
+  B200_HD static B200_NOINLINE void dbl(Fp2 &r, const Fp2 &a) { B::dbl(r.c0, a.c0); B::dbl(r.c1, a.c1); }
+  B200_HD static B200_NOINLINE void neg(Fp2 &r, const Fp2 &a) { B::neg(r.c0, a.c0); B::neg(r.c1, a.c1); }
+  B200_HD static B200_NOINLINE void mul(Fp2 &r, const Fp2 &a, const Fp2 &b) {  // Karatsuba, 3 base multiplications
     B aA, bB, s, t;
     B::mul(aA, a.c0, b.c0);
     B::mul(bB, a.c1, b.c1);
@@ -280,7 +289,7 @@ struct alignas(16) Fp2 {
     B::template mul_small<NR>(t, bB);
     B::add(r.c0, aA, t);
   }
-  B200_HD static void sqr(Fp2 &r, const Fp2 &a) {  // complex squaring, 2 base multiplications
+  B200_HD static B200_NOINLINE void sqr(Fp2 &r, const Fp2 &a) {  // complex squaring, 2 base multiplications
     B ab, s, t;
     B::mul(ab, a.c0, a.c1);
     B::add(s, a.c0, a.c1);
@@ -320,15 +329,15 @@ struct alignas(16) Fp3 {
   B200_HD static bool eq(const Fp3 &a, const Fp3 &b) {
     return B::eq(a.c0, b.c0) && B::eq(a.c1, b.c1) && B::eq(a.c2, b.c2);
   }
-  B200_HD static void add(Fp3 &r, const Fp3 &a, const Fp3 &b) {
+  B200_HD static B200_NOINLINE void add(Fp3 &r, const Fp3 &a, const Fp3 &b) {
     B::add(r.c0, a.c0, b.c0); B::add(r.c1, a.c1, b.c1); B::add(r.c2, a.c2, b.c2);
   }
-  B200_HD static void sub(Fp3 &r, const Fp3 &a, const Fp3 &b) {
+  B200_HD static B200_NOINLINE void sub(Fp3 &r, const Fp3 &a, const Fp3 &b) {
     B::sub(r.c0, a.c0, b.c0); B::sub(r.c1, a.c1, b.c1); B::sub(r.c2, a.c2, b.c2);
   }
-  B200_HD static void dbl(Fp3 &r, const Fp3 &a) { B::dbl(r.c0, a.c0); B::dbl(r.c1, a.c1); B::dbl(r.c2, a.c2); }
-  B200_HD static void neg(Fp3 &r, const Fp3 &a) { B::neg(r.c0, a.c0); B::neg(r.c1, a.c1); B::neg(r.c2, a.c2); }
-  B200_HD static void mul(Fp3 &r, const Fp3 &a, const Fp3 &b) {  // Karatsuba, 6 base multiplications
+  B200_HD static B200_NOINLINE void dbl(Fp3 &r, const Fp3 &a) { B::dbl(r.c0, a.c0); B::dbl(r.c1, a.c1); B::dbl(r.c2, a.c2); }
+  B200_HD static B200_NOINLINE void neg(Fp3 &r, const Fp3 &a) { B::neg(r.c0, a.c0); B::neg(r.c1, a.c1); B::neg(r.c2, a.c2); }
+  B200_HD static B200_NOINLINE void mul(Fp3 &r, const Fp3 &a, const Fp3 &b) {  // Karatsuba, 6 base multiplications
     B aA, bB, cC, s, t, u;
     B::mul(aA, a.c0, b.c0);
     B::mul(bB, a.c1, b.c1);
@@ -359,7 +368,7 @@ struct alignas(16) Fp3 {
     B::add(r.c0, aA, s);
     r.c1 = t;
   }
-  B200_HD static void sqr(Fp3 &r, const Fp3 &a) {  // CH-SQR2: 3 squarings + 2 multiplications
+  B200_HD static B200_NOINLINE void sqr(Fp3 &r, const Fp3 &a) {  // CH-SQR2: 3 squarings + 2 multiplications
     B s0, s1, s2, s3, s4, t;
     B::sqr(s0, a.c0);
     B::mul(s1, a.c0, a.c1);

@@ -17,26 +17,26 @@
 // infinity in the bases (y == 0 on the wire) are skipped; P+P and P+(-P) inside a bucket take the same branches as
 // the reference's mixed_add (curve.cuh).
 #include <cub/cub.cuh>
-#include <chrono>
 #include "common.cuh"
-#include "curve.cuh"
+#include "field.cuh"
 #include "msm.h"
+#include "msm_internal.h"
 
 namespace b200 {
 
-static double g_phase_ms[5] = {0, 0, 0, 0, 0};
-static double g_phase_total[2][5];  // [0] = G1 calls, [1] = G2 calls; accumulated until reset
+double g_msm_phase_ms[5] = {0, 0, 0, 0, 0};
+double g_msm_phase_total[2][5];
 static int g_forced_window = 0;
 void msm_set_window(int c) { g_forced_window = c; }
 void msm_phase_totals(double *out10, int reset) {
   for (int g = 0; g < 2; g++)
     for (int i = 0; i < 5; i++) {
-      out10[g * 5 + i] = g_phase_total[g][i];
-      if (reset) g_phase_total[g][i] = 0;
+      out10[g * 5 + i] = g_msm_phase_total[g][i];
+      if (reset) g_msm_phase_total[g][i] = 0;
     }
 }
 void msm_last_phase_ms(double *out5) {
-  for (int i = 0; i < 5; i++) out5[i] = g_phase_ms[i];
+  for (int i = 0; i < 5; i++) out5[i] = g_msm_phase_ms[i];
 }
 
 // ---------------------------------------------------------------------------------------------- kernels
@@ -98,80 +98,8 @@ __global__ void iota_kernel(uint32_t *v, uint32_t n) {
   if (i < n) v[i] = i;
 }
 
-template <class G>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
-                                                             const uint32_t *__restrict__ entries,
-                                                             const uint32_t *__restrict__ offsets,
-                                                             const uint32_t *__restrict__ counts_sorted,
-                                                             const uint32_t *__restrict__ order, uint32_t nbuckets,
-                                                             Proj<typename G::F> *__restrict__ buckets) {
-  typedef typename G::F F;
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nbuckets) return;
-  uint32_t b = order[t];
-  uint32_t cnt = counts_sorted[t];
-  uint32_t start = offsets[b];
-  Proj<F> acc;
-  proj_set_zero(acc);
-  for (uint32_t k = 0; k < cnt; k++) {
-    uint32_t e = entries[start + k];
-    Affine<F> q = points[e >> 1];
-    if (affine_is_zero(q)) continue;
-    if (e & 1) F::neg(q.y, q.y);
-    proj_madd<G>(acc, q);
-  }
-  buckets[b] = acc;
-}
 
-// One thread reduces K consecutive buckets of one window: sum_{v in (lo, lo+K]} v * B_v  (bucket value v = index+1)
-template <class G>
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const Proj<typename G::F> *__restrict__ buckets, int W,
-                                                         uint32_t nb, uint32_t K,
-                                                         Proj<typename G::F> *__restrict__ out) {
-  typedef typename G::F F;
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t nchunks = nb / K;
-  if (t >= (uint32_t)W * nchunks) return;
-  uint32_t j = t / nchunks, q = t % nchunks;
-  uint32_t lo = q * K;
-  const Proj<F> *B = buckets + (size_t)j * nb;
-  Proj<F> run, sum;
-  proj_set_zero(run);
-  proj_set_zero(sum);
-  for (uint32_t k = K; k-- > 0;) {
-    Proj<F> cur = B[lo + k];
-    proj_add<G>(run, run, cur);
-    proj_add<G>(sum, sum, run);
-  }
-  if (lo != 0) {
-    Proj<F> scaled;
-    proj_scalar_mul<G>(scaled, run, &lo, 1);
-    proj_add<G>(sum, sum, scaled);
-  }
-  out[t] = sum;
-}
-
-// out[j][t] = sum_{r<R} in[j][t*R + r]
-template <class G>
-__global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> *__restrict__ in, int W, uint32_t per_in,
-                                                      uint32_t R, Proj<typename G::F> *__restrict__ out) {
-  typedef typename G::F F;
-  uint32_t per_out = (per_in + R - 1) / R;
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint32_t)W * per_out) return;
-  uint32_t j = t / per_out, q = t % per_out;
-  Proj<F> acc;
-  proj_set_zero(acc);
-  for (uint32_t r = 0; r < R; r++) {
-    uint32_t idx = q * R + r;
-    if (idx >= per_in) break;
-    Proj<F> cur = in[(size_t)j * per_in + idx];
-    proj_add<G>(acc, acc, cur);
-  }
-  out[(size_t)j * per_out + q] = acc;
-}
-
-// ---------------------------------------------------------------------------------------------- host driver
+// ---------------------------------------------------------------------------------------------- host side
 // Window width: minimise (bucket accumulation + bucket reduction) field multiplications.
 static int choose_window(size_t n) {
   if (g_forced_window >= 3 && g_forced_window <= 22) return g_forced_window;
@@ -189,49 +117,41 @@ static int choose_window(size_t n) {
   return best_c;
 }
 
-struct MsmWorkspace {
-  DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b, plan;
-};
-static MsmWorkspace &workspace() {
+MsmWorkspace &msm_workspace() {
   static thread_local MsmWorkspace ws;
   return ws;
 }
 void msm_release_workspace() {
-  MsmWorkspace &ws = workspace();
+  MsmWorkspace &ws = msm_workspace();
   DevBuf *all[] = {&ws.digits, &ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.order,
                    &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan};
   for (DevBuf *b : all) b->release();
 }
 
-template <class G>
-int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) {
-  typedef typename G::F F;
-  typedef typename G::ScalarPrime FrP;
-  Proj<F> result;
-  proj_set_zero(result);
-  if (n == 0) {
-    memcpy(h_out, &result, sizeof(result));
-    return 0;
-  }
+int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   if (n >= (1ull << 30)) return set_error(-2, "msm: n=%zu too large", n);
   const int c = choose_window(n);
   const int W = (754 + c - 1) / c;
   const uint32_t nb = 1u << (c - 1);
   // window plan (see msm_digits_kernel): top window c-1 bits, `excess` low windows c-1 bits, the rest c bits
-  std::vector<uint32_t> plan(W);
+  plan.c = c;
+  plan.W = W;
+  plan.nb = nb;
+  plan.nbuckets = (size_t)W * nb;
+  plan.windows.resize(W);
   {
     int excess = W * c - 1 - 753;
     uint32_t start = 0;
     for (int j = 0; j < W; j++) {
       uint32_t width = (j == W - 1 || j < excess) ? (uint32_t)(c - 1) : (uint32_t)c;
-      plan[j] = start | (width << 16);
+      plan.windows[j] = start | (width << 16);
       start += width;
     }
     if (start != 753 || excess > W - 1) return set_error(-2, "msm: bad window plan c=%d", c);
   }
-  const size_t nbuckets = (size_t)W * nb;
+  const size_t nbuckets = plan.nbuckets;
   if ((size_t)W * n >= (1ull << 32)) return set_error(-2, "msm: W*n overflows 32-bit entry positions");
-  MsmWorkspace &ws = workspace();
+  MsmWorkspace &ws = msm_workspace();
   B200_CHECK(ws.digits.reserve((size_t)W * n * sizeof(int32_t)));
   B200_CHECK(ws.entries.reserve((size_t)W * n * sizeof(uint32_t)));
   B200_CHECK(ws.counts.reserve(nbuckets * sizeof(uint32_t)));
@@ -240,21 +160,25 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   B200_CHECK(ws.order.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.counts_sorted.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.iota.reserve(nbuckets * sizeof(uint32_t)));
-  B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
   B200_CHECK(ws.plan.reserve(256 * sizeof(uint32_t)));
-  B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
+  B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.windows.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
   Timer tm;
 
   // ---- digits + histogram
   tm.start();
   B200_CUDA_CHECK(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), 0));
   B200_CUDA_CHECK(cudaMemsetAsync(ws.cursor.p, 0, nbuckets * sizeof(uint32_t), 0));
-  msm_digits_kernel<FrP><<<grid_for(n, 128), 128>>>((const Fp<FrP> *)d_scalars, (uint32_t)n, c, W,
-                                                    ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
-                                                    ws.counts.as<uint32_t>());
+  if (fr_tag == 0)
+    msm_digits_kernel<PrimeA><<<grid_for(n, 128), 128>>>((const Fp<PrimeA> *)d_scalars, (uint32_t)n, c, W,
+                                                         ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
+                                                         ws.counts.as<uint32_t>());
+  else
+    msm_digits_kernel<PrimeB><<<grid_for(n, 128), 128>>>((const Fp<PrimeB> *)d_scalars, (uint32_t)n, c, W,
+                                                         ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
+                                                         ws.counts.as<uint32_t>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
-  g_phase_ms[0] = tm.stop();
+  g_msm_phase_ms[0] = tm.stop();
 
   // ---- counting sort: scan, scatter; then bucket order by descending size
   tm.start();
@@ -275,7 +199,7 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
                                                       ws.offsets.as<uint32_t>(), ws.cursor.as<uint32_t>(),
                                                       ws.entries.as<uint32_t>());
     B200_CUDA_CHECK(cudaGetLastError());
-  note_launch();
+    note_launch();
   }
   iota_kernel<<<grid_for(nbuckets, 256), 256>>>(ws.iota.as<uint32_t>(), (uint32_t)nbuckets);
   note_launch();
@@ -283,66 +207,20 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(ws.cub_tmp.p, tb, ws.counts.as<uint32_t>(),
                                                             ws.counts_sorted.as<uint32_t>(), ws.iota.as<uint32_t>(),
                                                             ws.order.as<uint32_t>(), (int)nbuckets, 0, end_bit));
-  g_phase_ms[1] = tm.stop();
-
-  // ---- bucket accumulation
-  tm.start();
-  msm_accumulate_kernel<G><<<grid_for(nbuckets, 128), 128>>>(
-      (const Affine<F> *)d_points, ws.entries.as<uint32_t>(), ws.offsets.as<uint32_t>(),
-      ws.counts_sorted.as<uint32_t>(), ws.order.as<uint32_t>(), (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
-  B200_CUDA_CHECK(cudaGetLastError());
-  note_launch();
-  g_phase_ms[2] = tm.stop();
-
-  // ---- bucket reduction: chunks of K buckets, then tree sum per window
-  tm.start();
-  uint32_t K = nb < 32 ? nb : 32;
-  uint32_t per = nb / K;
-  B200_CHECK(ws.red_a.reserve((size_t)W * per * sizeof(Proj<F>)));
-  B200_CHECK(ws.red_b.reserve((size_t)W * ((per + 7) / 8) * sizeof(Proj<F>) + 16));
-  msm_reduce_kernel<G><<<grid_for((size_t)W * per, 128), 128>>>(ws.buckets.as<Proj<F>>(), W, nb, K,
-                                                               ws.red_a.as<Proj<F>>());
-  B200_CUDA_CHECK(cudaGetLastError());
-  note_launch();
-  Proj<F> *cur = ws.red_a.as<Proj<F>>(), *nxt = ws.red_b.as<Proj<F>>();
-  while (per > 1) {
-    uint32_t R = 8;
-    uint32_t per_out = (per + R - 1) / R;
-    msm_sum_kernel<G><<<grid_for((size_t)W * per_out, 128), 128>>>(cur, W, per, R, nxt);
-    B200_CUDA_CHECK(cudaGetLastError());
-  note_launch();
-    Proj<F> *t = cur;
-    cur = nxt;
-    nxt = t;
-    per = per_out;
-  }
-  std::vector<Proj<F>> win(W);
-  B200_CUDA_CHECK(cudaMemcpy(win.data(), cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost));
-  g_phase_ms[3] = tm.stop();
-
-  // ---- host: result = sum_j 2^(c*j) * S_j  (Horner, most significant window first)
-  auto t0 = std::chrono::steady_clock::now();
-  for (int j = W - 1; j >= 0; j--) {
-    if (!proj_is_zero(result))
-      for (uint32_t k = 0; k < (plan[j] >> 16); k++) proj_dbl<G>(result, result);
-    proj_add<G>(result, result, win[j]);
-  }
-  g_phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  for (int i = 0; i < 5; i++) g_phase_total[F::kDegree == 1 ? 0 : 1][i] += g_phase_ms[i];
-  memcpy(h_out, &result, sizeof(result));
+  g_msm_phase_ms[1] = tm.stop();
   return 0;
 }
 
-template int msm_run<Mnt4G1>(const void *, const void *, size_t, void *);
-template int msm_run<Mnt4G2>(const void *, const void *, size_t, void *);
-template int msm_run<Mnt6G1>(const void *, const void *, size_t, void *);
-template int msm_run<Mnt6G2>(const void *, const void *, size_t, void *);
+int msm_run_mnt4g1(const void *, const void *, size_t, void *);
+int msm_run_mnt4g2(const void *, const void *, size_t, void *);
+int msm_run_mnt6g1(const void *, const void *, size_t, void *);
+int msm_run_mnt6g2(const void *, const void *, size_t, void *);
 
 int msm_dispatch(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out) {
-  if (curve == 0 && group == 1) return msm_run<Mnt4G1>(d_scalars, d_points, n, h_out);
-  if (curve == 0 && group == 2) return msm_run<Mnt4G2>(d_scalars, d_points, n, h_out);
-  if (curve == 1 && group == 1) return msm_run<Mnt6G1>(d_scalars, d_points, n, h_out);
-  if (curve == 1 && group == 2) return msm_run<Mnt6G2>(d_scalars, d_points, n, h_out);
+  if (curve == 0 && group == 1) return msm_run_mnt4g1(d_scalars, d_points, n, h_out);
+  if (curve == 0 && group == 2) return msm_run_mnt4g2(d_scalars, d_points, n, h_out);
+  if (curve == 1 && group == 1) return msm_run_mnt6g1(d_scalars, d_points, n, h_out);
+  if (curve == 1 && group == 2) return msm_run_mnt6g2(d_scalars, d_points, n, h_out);
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 

@@ -1,0 +1,153 @@
+// Group-dependent half of the MSM: bucket accumulation, bucket reduction, window combine. Instantiated once per
+// (curve, group) in msm_g_*.cu. See msm.cu for the overall schedule.
+#pragma once
+#include <chrono>
+#include "common.cuh"
+#include "curve.cuh"
+#include "msm.h"
+#include "msm_internal.h"
+
+namespace b200 {
+
+template <class G>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
+                                                             const uint32_t *__restrict__ entries,
+                                                             const uint32_t *__restrict__ offsets,
+                                                             const uint32_t *__restrict__ counts_sorted,
+                                                             const uint32_t *__restrict__ order, uint32_t nbuckets,
+                                                             Proj<typename G::F> *__restrict__ buckets) {
+  typedef typename G::F F;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbuckets) return;
+  uint32_t b = order[t];
+  uint32_t cnt = counts_sorted[t];
+  uint32_t start = offsets[b];
+  Proj<F> acc;
+  proj_set_zero(acc);
+  for (uint32_t k = 0; k < cnt; k++) {
+    uint32_t e = entries[start + k];
+    Affine<F> q = points[e >> 1];
+    if (affine_is_zero(q)) continue;
+    if (e & 1) F::neg(q.y, q.y);
+    proj_madd<G>(acc, q);
+  }
+  buckets[b] = acc;
+}
+
+// One thread reduces K consecutive buckets of one window: sum_{v in (lo, lo+K]} v * B_v  (bucket value v = index+1)
+template <class G>
+__global__ void __launch_bounds__(128) msm_reduce_kernel(const Proj<typename G::F> *__restrict__ buckets, int W,
+                                                         uint32_t nb, uint32_t K,
+                                                         Proj<typename G::F> *__restrict__ out) {
+  typedef typename G::F F;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t nchunks = nb / K;
+  if (t >= (uint32_t)W * nchunks) return;
+  uint32_t j = t / nchunks, q = t % nchunks;
+  uint32_t lo = q * K;
+  const Proj<F> *B = buckets + (size_t)j * nb;
+  Proj<F> run, sum;
+  proj_set_zero(run);
+  proj_set_zero(sum);
+  for (uint32_t k = K; k-- > 0;) {
+    Proj<F> cur = B[lo + k];
+    proj_add<G>(run, run, cur);
+    proj_add<G>(sum, sum, run);
+  }
+  if (lo != 0) {
+    Proj<F> scaled;
+    proj_scalar_mul<G>(scaled, run, &lo, 1);
+    proj_add<G>(sum, sum, scaled);
+  }
+  out[t] = sum;
+}
+
+// out[j][t] = sum_{r<R} in[j][t*R + r]
+template <class G>
+__global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> *__restrict__ in, int W, uint32_t per_in,
+                                                      uint32_t R, Proj<typename G::F> *__restrict__ out) {
+  typedef typename G::F F;
+  uint32_t per_out = (per_in + R - 1) / R;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint32_t)W * per_out) return;
+  uint32_t j = t / per_out, q = t % per_out;
+  Proj<F> acc;
+  proj_set_zero(acc);
+  for (uint32_t r = 0; r < R; r++) {
+    uint32_t idx = q * R + r;
+    if (idx >= per_in) break;
+    Proj<F> cur = in[(size_t)j * per_in + idx];
+    proj_add<G>(acc, acc, cur);
+  }
+  out[(size_t)j * per_out + q] = acc;
+}
+
+
+template <class G>
+int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) {
+  typedef typename G::F F;
+  typedef typename G::ScalarPrime FrP;
+  Proj<F> result;
+  proj_set_zero(result);
+  if (n == 0) {
+    memcpy(h_out, &result, sizeof(result));
+    return 0;
+  }
+  MsmPlan plan;
+  B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan));
+  MsmWorkspace &ws = msm_workspace();
+  const int W = plan.W;
+  const uint32_t nb = plan.nb;
+  const size_t nbuckets = plan.nbuckets;
+  B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
+  Timer tm;
+
+  // ---- bucket accumulation
+  tm.start();
+  msm_accumulate_kernel<G><<<grid_for(nbuckets, 128), 128>>>(
+      (const Affine<F> *)d_points, ws.entries.as<uint32_t>(), ws.offsets.as<uint32_t>(),
+      ws.counts_sorted.as<uint32_t>(), ws.order.as<uint32_t>(), (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  g_msm_phase_ms[2] = tm.stop();
+
+  // ---- bucket reduction: chunks of K buckets, then tree sum per window
+  tm.start();
+  uint32_t K = nb < 32 ? nb : 32;
+  uint32_t per = nb / K;
+  B200_CHECK(ws.red_a.reserve((size_t)W * per * sizeof(Proj<F>)));
+  B200_CHECK(ws.red_b.reserve((size_t)W * ((per + 7) / 8) * sizeof(Proj<F>) + 16));
+  msm_reduce_kernel<G><<<grid_for((size_t)W * per, 128), 128>>>(ws.buckets.as<Proj<F>>(), W, nb, K,
+                                                               ws.red_a.as<Proj<F>>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  Proj<F> *cur = ws.red_a.as<Proj<F>>(), *nxt = ws.red_b.as<Proj<F>>();
+  while (per > 1) {
+    uint32_t R = 8;
+    uint32_t per_out = (per + R - 1) / R;
+    msm_sum_kernel<G><<<grid_for((size_t)W * per_out, 128), 128>>>(cur, W, per, R, nxt);
+    B200_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    Proj<F> *t = cur;
+    cur = nxt;
+    nxt = t;
+    per = per_out;
+  }
+  std::vector<Proj<F>> win(W);
+  B200_CUDA_CHECK(cudaMemcpy(win.data(), cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost));
+  g_msm_phase_ms[3] = tm.stop();
+
+  // ---- host: result = sum_j 2^(start_j) * S_j  (Horner, most significant window first)
+  auto t0 = std::chrono::steady_clock::now();
+  for (int j = W - 1; j >= 0; j--) {
+    if (!proj_is_zero(result))
+      for (uint32_t k = 0; k < (plan.windows[j] >> 16); k++) proj_dbl<G>(result, result);
+    proj_add<G>(result, result, win[j]);
+  }
+  g_msm_phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  for (int i = 0; i < 5; i++) g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i] += g_msm_phase_ms[i];
+  memcpy(h_out, &result, sizeof(result));
+  return 0;
+}
+
+}  // namespace b200
