@@ -17,7 +17,7 @@ SOURCES = ["msm_g_mnt6g2.cu", "devops_g_mnt6g2.cu", "msm_g_mnt4g2.cu", "devops_g
            "devops_g_mnt4g1.cu", "devops_g_mnt6g1.cu", "devops.cu", "msm.cu", "ntt.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-mbmi2", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
          "-ccbin", "/usr/bin/g++"]
 
 
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
     objs = [o for o, _ in results]
     logs = "\n".join(l for _, l in results if l)
     if not _newer(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart",
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lpthread",
                                                      "-ccbin", "/usr/bin/g++"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

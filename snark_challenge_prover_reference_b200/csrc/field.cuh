@@ -12,6 +12,9 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#if defined(__x86_64__) && !defined(__CUDA_ARCH__)
+#include <immintrin.h>
+#endif
 #include "constants_gen.h"
 
 #if defined(__CUDACC__)
@@ -108,6 +111,48 @@ struct alignas(16) Fp {
     }
     for (int i = 0; i < 12; i++) st64(r, i, t[i]);
   }
+#if defined(__x86_64__) && defined(__BMI2__)
+  // x86-64 fast path (mulx + two add-with-carry chains per row): t[0..13] += a[0..11] * b
+  static inline __attribute__((always_inline)) void host_mac_row(unsigned long long *t, const unsigned long long *a,
+                                                                 unsigned long long b) {
+    unsigned long long lo[12], hi[12];
+#pragma GCC unroll 12
+    for (int j = 0; j < 12; j++) lo[j] = _mulx_u64(a[j], b, &hi[j]);
+    unsigned char c = 0;
+#pragma GCC unroll 12
+    for (int j = 0; j < 12; j++) c = _addcarry_u64(c, t[j], lo[j], &t[j]);
+    c = _addcarry_u64(c, t[12], 0, &t[12]);
+    t[13] += c;
+    c = 0;
+#pragma GCC unroll 12
+    for (int j = 0; j < 12; j++) c = _addcarry_u64(c, t[j + 1], hi[j], &t[j + 1]);
+    t[13] += c;
+  }
+  static inline void host_mul(Fp &r, const Fp &a, const Fp &b) {
+    static const unsigned long long inv64 = []() {
+      unsigned long long p0 = p64(0), x = 1;
+      for (int i = 0; i < 6; i++) x *= 2 - p0 * x;
+      return (unsigned long long)(0 - x);
+    }();
+    unsigned long long t[14], av[12], pv[12];
+    for (int i = 0; i < 14; i++) t[i] = 0;
+    for (int i = 0; i < 12; i++) {
+      av[i] = ld64(a, i);
+      pv[i] = p64(i);
+    }
+    for (int i = 0; i < 12; i++) {
+      host_mac_row(t, av, ld64(b, i));
+      host_mac_row(t, pv, t[0] * inv64);
+#pragma GCC unroll 13
+      for (int j = 0; j < 13; j++) t[j] = t[j + 1];
+      t[13] = 0;
+    }
+    uint64_t tt[12];
+    for (int i = 0; i < 12; i++) tt[i] = t[i];
+    host_cond_sub_p(tt);
+    for (int i = 0; i < 12; i++) st64(r, i, tt[i]);
+  }
+#else
   static inline void host_mul(Fp &r, const Fp &a, const Fp &b) {
     // CIOS Montgomery, 12 x u64, inv64 derived from the 32-bit constant by one Newton step.
     static const uint64_t inv64 = []() {
@@ -148,6 +193,7 @@ struct alignas(16) Fp {
     host_cond_sub_p(t);
     for (int i = 0; i < 12; i++) st64(r, i, t[i]);
   }
+#endif
 #endif
 
   // ---------------------------------------------------------------- dispatch

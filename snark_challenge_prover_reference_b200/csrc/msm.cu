@@ -17,6 +17,7 @@
 // infinity in the bases (y == 0 on the wire) are skipped; P+P and P+(-P) inside a bucket take the same branches as
 // the reference's mixed_add (curve.cuh).
 #include <cub/cub.cuh>
+#include <functional>
 #include "common.cuh"
 #include "field.cuh"
 #include "msm.h"
@@ -215,6 +216,20 @@ int msm_run_mnt4g1(const void *, const void *, size_t, void *);
 int msm_run_mnt4g2(const void *, const void *, size_t, void *);
 int msm_run_mnt6g1(const void *, const void *, size_t, void *);
 int msm_run_mnt6g2(const void *, const void *, size_t, void *);
+
+int msm_run_deferred_mnt4g1(const void *, const void *, size_t, void *, std::function<void()> &);
+int msm_run_deferred_mnt4g2(const void *, const void *, size_t, void *, std::function<void()> &);
+int msm_run_deferred_mnt6g1(const void *, const void *, size_t, void *, std::function<void()> &);
+int msm_run_deferred_mnt6g2(const void *, const void *, size_t, void *, std::function<void()> &);
+
+int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out,
+                          std::function<void()> &tail) {
+  if (curve == 0 && group == 1) return msm_run_deferred_mnt4g1(d_scalars, d_points, n, h_out, tail);
+  if (curve == 0 && group == 2) return msm_run_deferred_mnt4g2(d_scalars, d_points, n, h_out, tail);
+  if (curve == 1 && group == 1) return msm_run_deferred_mnt6g1(d_scalars, d_points, n, h_out, tail);
+  if (curve == 1 && group == 2) return msm_run_deferred_mnt6g2(d_scalars, d_points, n, h_out, tail);
+  return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
+}
 
 int msm_dispatch(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out) {
   if (curve == 0 && group == 1) return msm_run_mnt4g1(d_scalars, d_points, n, h_out);

@@ -1,9 +1,13 @@
 // Host-callable entry points of msm.cu (internal; the public surface is include/b200_groth16.h).
 #pragma once
 #include <stddef.h>
+#include <functional>
 namespace b200 {
 // group: 1 = G1, 2 = G2. d_scalars: n Fr (Montgomery). d_points: n affine wire-format points. h_out: projective.
 int msm_dispatch(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out);
+// GPU work done on return; `tail` finishes the result into h_out (serial host Horner) - run it on any thread.
+int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out,
+                          std::function<void()> &tail);
 void msm_set_window(int c);
 void msm_last_phase_ms(double *out5);
 // accumulated phase times since the last reset: out10 = G1 {digits, sort, accumulate, reduce, host}, then G2

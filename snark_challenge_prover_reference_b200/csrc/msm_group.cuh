@@ -2,6 +2,8 @@
 // (curve, group) in msm_g_*.cu. See msm.cu for the overall schedule.
 #pragma once
 #include <chrono>
+#include <functional>
+#include <memory>
 #include "common.cuh"
 #include "curve.cuh"
 #include "msm.h"
@@ -83,17 +85,12 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 }
 
 
+// GPU half of one MSM: everything up to the per-window sums, copied to the host (the copy synchronises).
 template <class G>
-int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) {
+int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan,
+                  std::vector<Proj<typename G::F>> &win) {
   typedef typename G::F F;
   typedef typename G::ScalarPrime FrP;
-  Proj<F> result;
-  proj_set_zero(result);
-  if (n == 0) {
-    memcpy(h_out, &result, sizeof(result));
-    return 0;
-  }
-  MsmPlan plan;
   B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan));
   MsmWorkspace &ws = msm_workspace();
   const int W = plan.W;
@@ -133,20 +130,62 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
     nxt = t;
     per = per_out;
   }
-  std::vector<Proj<F>> win(W);
+  win.resize(W);
   B200_CUDA_CHECK(cudaMemcpy(win.data(), cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost));
   g_msm_phase_ms[3] = tm.stop();
+  for (int i = 0; i < 4; i++) g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i] += g_msm_phase_ms[i];
+  return 0;
+}
 
-  // ---- host: result = sum_j 2^(start_j) * S_j  (Horner, most significant window first)
+// Host half: result = sum_j 2^(start_j) * S_j (Horner, most significant window first) - 753 serial doublings.
+template <class G>
+double msm_host_phase(const MsmPlan &plan, const std::vector<Proj<typename G::F>> &win, void *h_out) {
+  typedef typename G::F F;
+  Proj<F> result;
+  proj_set_zero(result);
   auto t0 = std::chrono::steady_clock::now();
-  for (int j = W - 1; j >= 0; j--) {
+  for (int j = plan.W - 1; j >= 0; j--) {
     if (!proj_is_zero(result))
       for (uint32_t k = 0; k < (plan.windows[j] >> 16); k++) proj_dbl<G>(result, result);
     proj_add<G>(result, result, win[j]);
   }
-  g_msm_phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  for (int i = 0; i < 5; i++) g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i] += g_msm_phase_ms[i];
   memcpy(h_out, &result, sizeof(result));
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+template <class G>
+int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) {
+  typedef typename G::F F;
+  if (n == 0) {
+    Proj<F> zero;
+    proj_set_zero(zero);
+    memcpy(h_out, &zero, sizeof(zero));
+    return 0;
+  }
+  MsmPlan plan;
+  std::vector<Proj<F>> win;
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, plan, win));
+  g_msm_phase_ms[4] = msm_host_phase<G>(plan, win, h_out);
+  g_msm_phase_total[F::kDegree == 1 ? 0 : 1][4] += g_msm_phase_ms[4];
+  return 0;
+}
+
+// Same sum, but the serial host tail is returned as a closure so that the caller can run it on another thread while
+// the next MSM already occupies the GPU (b200_prove does this for its five MSMs).
+template <class G>
+int msm_run_deferred(const void *d_scalars, const void *d_points, size_t n, void *h_out, std::function<void()> &tail) {
+  typedef typename G::F F;
+  if (n == 0) {
+    Proj<F> zero;
+    proj_set_zero(zero);
+    memcpy(h_out, &zero, sizeof(zero));
+    tail = []() {};
+    return 0;
+  }
+  auto plan = std::make_shared<MsmPlan>();
+  auto win = std::make_shared<std::vector<Proj<F>>>();
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, *plan, *win));
+  tail = [plan, win, h_out]() { msm_host_phase<G>(*plan, *win, h_out); };
   return 0;
 }
 
