@@ -1,0 +1,62 @@
+"""CPU suite, part 4: the N>1 protocol of bench.py / b200_prove_partial on world_size 2 over gloo.
+Each rank owns the contiguous point range [rank*n/world, ...) of every MSM (last rank takes the remainder, as
+multiexp.tcc:417-431), the 5 partial group elements per rank are all_gather'ed, rank 0 combines them with the product's
+host tail (b200_prove_combine) and must reproduce the reference's proof. The per-rank partial sums are computed by
+the oracle here (no GPU on this box); on the GPU box test_gpu_parity.py::test_sharded_prover_* does the same with
+the CUDA path."""
+import ctypes
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import util
+
+
+def shard_range(n, rank, world):
+    one = n // world
+    return rank * one, (n if rank == world - 1 else (rank + 1) * one)
+
+
+def _worker(rank, world, port, curve, k, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import snark_challenge_prover_reference_b200 as b200
+    O = util.load_oracle()
+    params, inp, expected = util.golden(curve, k)
+    d, m, q = util.split_params(curve, params)
+    x = util.split_input(inp, d, m)
+    H = util.orc_compute_h(O, curve, d, x["ca"], x["cb"], x["cc"])  # replicated on every rank
+    jobs = [(1, x["w"], q["A"], m + 1), (1, x["w"], q["B1"], m + 1), (2, x["w"], q["B2"], m + 1),
+            (1, H, q["H"], d), (1, x["w"][2 * 96:], q["L"], m - 1)]
+    part = b""
+    for group, sc, pts, n in jobs:
+        lo, hi = shard_range(n, rank, world)
+        ab = b200.affine_bytes(curve, group)
+        out = ctypes.create_string_buffer(b200.proj_bytes(curve, group))
+        sb, pb = util.buf(sc[lo * 96:hi * 96]), util.buf(pts[lo * ab:hi * ab])
+        O.orc_msm(curve, group, ctypes.addressof(sb), ctypes.addressof(pb), hi - lo, ctypes.addressof(out), 1)
+        part += out.raw
+    assert len(part) == b200.partial_bytes(curve)
+    mine = torch.frombuffer(bytearray(part), dtype=torch.uint8)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        allp = b"".join(t.numpy().tobytes() for t in gathered)
+        proof = b200.prove_combine(curve, allp, world, x["r"])
+        ret["ok"] = proof == expected
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_two_rank_sharded_proof_over_gloo(curve):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29600 + curve + (os.getpid() % 200)
+    mp.spawn(_worker, args=(world, port, curve, 5, ret), nprocs=world, join=True)
+    assert ret.get("ok") is True
