@@ -233,6 +233,10 @@ def b200_arm(args):
 
     shapes = ((0, args.log2_mnt4), (1, args.log2_mnt6))
     keys = [make_key(pkg, torch, c, k, dev) for c, k in shapes]
+    # key-only preprocessing (tables of pre-shifted bases in the spare HBM), outside every timed region like the
+    # reference's own key loading (main.cpp:200-203); `no_tables` below reports the same step without it
+    pkg.set_precompute(True)
+    preprocess_s = [key.precompute(rank, world) for key in keys]
     host_inputs = [make_input(torch, c, k, 77 + c) for c, k in shapes]
     dev_inputs = [h.to(dev) for h in host_inputs]
     constraints = sum(1 << k for _, k in shapes)
@@ -283,6 +287,11 @@ def b200_arm(args):
     launches = pkg.launch_count() - launches0
     phases = pkg.msm_phase_totals(reset=True)
     ms_e2e, tms_e2e, proofs_e2e = timed(host_inputs, args.steps)
+    pkg.set_precompute(False)
+    prove_all(dev_inputs)
+    ms_nt, _, proofs_nt = timed(dev_inputs, max(1, min(2, args.steps)))
+    nt_steps = max(1, min(2, args.steps))
+    pkg.set_precompute(True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -291,6 +300,7 @@ def b200_arm(args):
             dist.destroy_process_group()
         return
     assert proofs_dev == proofs_e2e, "device-resident and host-buffer runs disagree"
+    assert proofs_dev == proofs_nt, "table and table-free MSM paths disagree"
     value = constraints * args.steps / (ms_dev / 1e3)
     e2e = constraints * args.steps / (ms_e2e / 1e3)
     h2d = sum(h.numel() for h in host_inputs)
@@ -310,7 +320,10 @@ def b200_arm(args):
                 "unit": "TMAC32/s", "frac": achieved / peak if peak else None, "traffic": None,
                 "launches": g1_launches, "avg_launch_ms": acc_ms_g1 / g1_launches,
                 "peak_source": "measured live by b200_imad_peak (IMAD.WIDE carry-chain microbenchmark on all SMs)",
-                "share_of_step": acc_ms_g1 / ms_dev}
+                "share_of_step": acc_ms_g1 / ms_dev,
+                "note": "achieved uses SURVEY 8d's algorithmic 620928 MAC32/point (48 windows); with the pre-shifted "
+                        "base tables the kernel really runs 36-42 windows, so frac > 1 means fewer windows, not a "
+                        "faster pipe: ncu shows the fmaheavy pipe ~94% busy (profiles/)"}
     g2_mac = args.steps * (MAC32_PER_POINT["g2_fq2"] * n4 + MAC32_PER_POINT["g2_fq3"] * n6)
     acc_ms_g2 = phases["g2"]["accumulate"]
     roofline_g2 = {"kernel": "msm_accumulate_kernel<G2>", "achieved": g2_mac / (acc_ms_g2 / 1e3) / 1e12 if acc_ms_g2 else None,
@@ -344,7 +357,11 @@ def b200_arm(args):
             "config": {"workload": "MNT4753 2^%d + MNT6753 2^%d Groth16 prove (7 NTT + 5 MSM each), MSMs sharded over %d GPU(s) by point range"
                                    % (args.log2_mnt4, args.log2_mnt6, world),
                        "l2": "inputs larger than L2: each step streams >1.6 GB of bases and 416 MB of scalars",
-                       "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys"},
+                       "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys",
+                       "key_preprocess": "pre-shifted base tables 2^(start_j)*P_i per MSM window, built once per key "
+                                         "in %s s (MNT4753, MNT6753), outside the timed region; see no_tables" % json.dumps([round(x, 2) for x in preprocess_s])},
+            "no_tables": {"value": constraints * nt_steps / (ms_nt / 1e3), "unit": UNIT, "ms_per_step": ms_nt / nt_steps,
+                          "note": "same step with B200_PRECOMPUTE=0 (per-window buckets + host window combine)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_g2": roofline_g2,
@@ -353,6 +370,7 @@ def b200_arm(args):
             "msm_points_per_s": {
                 "g1": 4 * args.steps * (n4 + n6) * world / (sum(phases["g1"].values()) / 1e3) if sum(phases["g1"].values()) else None,
                 "g2": args.steps * (n4 + n6) * world / (sum(phases["g2"].values()) / 1e3) if sum(phases["g2"].values()) else None},
+            "msm_phase_ms_per_step": {g: {k: v / args.steps for k, v in ph.items()} for g, ph in phases.items()},
             "imad_peak": imad}
     if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REF_DIR, "main")):
         cores = os.cpu_count() or 1

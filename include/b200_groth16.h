@@ -98,6 +98,13 @@ int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_par
 int b200_params_from_device(int curve, size_t d, size_t m, const void *d_A, const void *d_B1, const void *d_B2,
                             const void *d_L, const void *d_H, b200_params **out);
 int b200_params_destroy(b200_params *p);
+/* Pre-shifted base tables: for rank's slice of each query build table[j][i] = 2^(start_j) * P_i for the W windows of
+ * the MSM (key-only preprocessing, 36-48x the size of the query, lives in the spare HBM). b200_prove* use them when
+ * precomputation is enabled (default; B200_PRECOMPUTE=0 or b200_set_precompute(0) selects the table-free MSM) and
+ * build them on first use if this was not called. Idempotent per (rank, world). */
+int b200_params_precompute(b200_params *p, int rank, int world);
+double b200_params_precompute_ms(const b200_params *p);
+int b200_set_precompute(int on);
 size_t b200_params_d(const b200_params *p);
 size_t b200_params_m(const b200_params *p);
 const void *b200_params_query(const b200_params *p, int which); /* 0 A, 1 B1, 2 B2, 3 L, 4 H (device pointers) */

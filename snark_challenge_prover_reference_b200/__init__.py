@@ -95,6 +95,9 @@ _SIGNATURES = {
     "b200_params_from_host": (_i, [_i, _vp, _sz, ctypes.POINTER(_vp)]),
     "b200_params_from_device": (_i, [_i, _sz, _sz, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "b200_params_destroy": (_i, [_vp]),
+    "b200_params_precompute": (_i, [_vp, _i, _i]),
+    "b200_params_precompute_ms": (ctypes.c_double, [_vp]),
+    "b200_set_precompute": (_i, [_i]),
     "b200_params_d": (_sz, [_vp]),
     "b200_params_m": (_sz, [_vp]),
     "b200_params_query": (_vp, [_vp, _i]),
@@ -292,6 +295,11 @@ class Params:
 
     __del__ = close
 
+    def precompute(self, rank=0, world=1):
+        """build the pre-shifted base tables for this rank's slice (key-only preprocessing); returns seconds"""
+        check(lib().b200_params_precompute(self.h, rank, world))
+        return lib().b200_params_precompute_ms(self.h) / 1e3
+
     def prove(self, input_image, timings=False):
         """One whole proof from a HOST input image; returns the proof bytes (A | B | C, wire format)."""
         out = ctypes.create_string_buffer(proof_bytes(self.curve))
@@ -324,6 +332,10 @@ def prove_combine(curve, partials_all, world, r_fr):
     check(lib().b200_prove_combine(curve, ctypes.addressof(pb), world, ctypes.addressof(rb), ctypes.addressof(out),
                                    ctypes.byref(n)))
     return out.raw[:n.value]
+
+
+def set_precompute(on):
+    check(lib().b200_set_precompute(1 if on else 0))
 
 
 def imad_peak():

@@ -10,6 +10,7 @@
 #include "curve.cuh"
 #include "devops.h"
 #include "msm.h"
+#include "msm_internal.h"
 #include "ntt.h"
 
 namespace b200 {
@@ -120,6 +121,14 @@ struct b200_domain {
   Domain *impl;
 };
 
+// Pre-shifted base tables for one (rank, world) slicing of the five queries (see msm_precompute_kernel).
+struct Precomputed {
+  int rank = -1, world = -1;
+  DevBuf table[5];
+  MsmPlan plan[5];
+  double build_ms = 0;
+};
+
 struct b200_params {
   int curve;
   size_t d, m;
@@ -127,7 +136,17 @@ struct b200_params {
   DevBuf owned;      // backing store when loaded from a host image
   b200_domain *dom;
   DevBuf w, ca, cb, cc, h;  // per-proof device buffers
+  Precomputed pre;
 };
+
+static int g_use_precompute = -1;  // -1: read B200_PRECOMPUTE from the environment (default on)
+static bool use_precompute() {
+  if (g_use_precompute < 0) {
+    const char *e = getenv("B200_PRECOMPUTE");
+    g_use_precompute = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_use_precompute != 0;
+}
 
 extern "C" {
 
@@ -364,6 +383,36 @@ size_t b200_params_d(const b200_params *p) { return p->d; }
 size_t b200_params_m(const b200_params *p) { return p->m; }
 const void *b200_params_query(const b200_params *p, int which) { return (which >= 0 && which < 5) ? p->q[which] : nullptr; }
 
+// Build (once per key and slicing) the tables of pre-shifted bases for this rank's slice of the five queries.
+int b200_params_precompute(b200_params *p, int rank, int world) {
+  B200_CHECK(require_device());
+  if (world < 1 || rank < 0 || rank >= world) return set_error(-1, "bad rank/world %d/%d", rank, world);
+  if (p->pre.rank == rank && p->pre.world == world) return 0;
+  double t0 = now_ms();
+  const size_t d = p->d, m = p->m;
+  const size_t ns[5] = {m + 1, m + 1, m + 1, m - 1, d};   // A, B1, B2, L, H (order of p->q)
+  const int jobq[5] = {0, 1, 2, 4, 3};                     // job order A, B1, B2, H, L -> query index
+  p->pre.rank = p->pre.world = -1;
+  for (int j = 0; j < 5; j++) {
+    const int qi = jobq[j];
+    const int group = qi == 2 ? 2 : 1;
+    const size_t n = ns[qi], one = n / (size_t)world;
+    const size_t lo = (size_t)rank * one, hi = (rank == world - 1) ? n : lo + one;
+    const char *pts = (const char *)p->q[qi] + lo * affine_bytes(p->curve, group);
+    p->pre.plan[j] = MsmPlan();
+    if (hi > lo) B200_CHECK(msm_precompute_dispatch(p->curve, group, pts, hi - lo, p->pre.plan[j], p->pre.table[j]));
+  }
+  p->pre.rank = rank;
+  p->pre.world = world;
+  p->pre.build_ms = now_ms() - t0;
+  return 0;
+}
+double b200_params_precompute_ms(const b200_params *p) { return p->pre.build_ms; }
+int b200_set_precompute(int on) {
+  g_use_precompute = on ? 1 : 0;
+  return 0;
+}
+
 // Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
 // multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
 static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, int rank, int world,
@@ -385,6 +434,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   const int curve = p->curve;
   const size_t g1a = affine_bytes(curve, 1), g2a = affine_bytes(curve, 2);
   const size_t g1p = proj_bytes(curve, 1), g2p = proj_bytes(curve, 2);
+  if (use_precompute()) B200_CHECK(b200_params_precompute(p, rank, world));
   struct Job { int group; const char *scalars; const char *points; size_t n; size_t stride; size_t outb; double *ms; };
   double ms[5] = {0, 0, 0, 0, 0};
   Job jobs[5] = {
@@ -409,7 +459,11 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     size_t lo = (size_t)rank * one, hi = (rank == world - 1) ? J.n : lo + one;
     double a = now_ms();
     std::function<void()> tail;
-    rc_all = msm_dispatch_deferred(curve, J.group, J.scalars + lo * 96, J.points + lo * J.stride, hi - lo, o, tail);
+    if (use_precompute())
+      rc_all = msm_table_dispatch_deferred(curve, J.group, J.scalars + lo * 96, p->pre.table[j].p, hi - lo,
+                                           p->pre.plan[j], o, tail);
+    else
+      rc_all = msm_dispatch_deferred(curve, J.group, J.scalars + lo * 96, J.points + lo * J.stride, hi - lo, o, tail);
     if (rc_all == 0) tails.push_back(std::async(std::launch::async, tail));
     *J.ms = now_ms() - a;
   }

@@ -48,7 +48,7 @@ void msm_last_phase_ms(double *out5) {
 // buckets in every window (a short top window would put ~n/2 points into one bucket).
 template <class FrP>
 __global__ void __launch_bounds__(128) msm_digits_kernel(const Fp<FrP> *__restrict__ scalars, uint32_t n, int c, int W,
-                                                         const uint32_t *__restrict__ plan,
+                                                         int merged, const uint32_t *__restrict__ plan,
                                                          int32_t *__restrict__ digits, uint32_t *__restrict__ counts) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -74,13 +74,16 @@ __global__ void __launch_bounds__(128) msm_digits_kernel(const Fp<FrP> *__restri
     digits[(size_t)j * n + i] = d;
     if (d != 0) {
       uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      atomicAdd(&counts[(size_t)j * nb + (mag - 1)], 1u);
+      atomicAdd(&counts[(merged ? (size_t)0 : (size_t)j * nb) + (mag - 1)], 1u);
     }
   }
 }
 
+// merged == 0: bucket space is (window, |digit|), an entry is a point index into the n bases.
+// merged == 1: all windows share one bucket set, an entry is j*n + i, an index into the table of pre-shifted bases
+//              2^(start_j) * P_i (see msm_precompute_kernel).
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t *__restrict__ digits, uint32_t n, int W, int c,
-                                                          const uint32_t *__restrict__ offsets,
+                                                          int merged, const uint32_t *__restrict__ offsets,
                                                           uint32_t *__restrict__ cursor, uint32_t *__restrict__ entries) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)W * n) return;
@@ -89,9 +92,10 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t *__restr
   uint32_t j = (uint32_t)(idx / n), i = (uint32_t)(idx % n);
   const uint32_t nb = 1u << (c - 1);
   uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-  size_t b = (size_t)j * nb + (mag - 1);
+  size_t b = (merged ? (size_t)0 : (size_t)j * nb) + (mag - 1);
   uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);
-  entries[pos] = (i << 1) | (d < 0 ? 1u : 0u);
+  uint32_t e = merged ? (uint32_t)idx : i;
+  entries[pos] = (e << 1) | (d < 0 ? 1u : 0u);
 }
 
 __global__ void iota_kernel(uint32_t *v, uint32_t n) {
@@ -101,21 +105,45 @@ __global__ void iota_kernel(uint32_t *v, uint32_t n) {
 
 
 // ---------------------------------------------------------------------------------------------- host side
-// Window width: minimise (bucket accumulation + bucket reduction) field multiplications.
-static int choose_window(size_t n) {
+// Window width: minimise (bucket accumulation + bucket reduction) field multiplications. With pre-shifted bases
+// (merged) the bucket reduction is paid once instead of once per window, which moves the optimum to wider windows.
+static int choose_window(size_t n, bool merged) {
   if (g_forced_window >= 3 && g_forced_window <= 22) return g_forced_window;
   double best = 1e300;
   int best_c = 4;
-  for (int c = 3; c <= 20; c++) {
+  for (int c = 3; c <= (merged ? 22 : 20); c++) {
     double W = (754 + c - 1) / c;
     double nb = (double)(1u << (c - 1));
-    double cost = W * ((double)n * 11.0 + nb * 2.0 * 14.0 + nb / 32.0 * 30.0 * 13.0);
+    double red = nb * 2.0 * 14.0 + nb / 32.0 * 30.0 * 13.0;
+    double cost = merged ? W * (double)n * 11.0 + red : W * ((double)n * 11.0 + red);
     if (cost < best) {
       best = cost;
       best_c = c;
     }
   }
   return best_c;
+}
+
+// window plan (see msm_digits_kernel): top window c-1 bits, `excess` low windows c-1 bits, the rest c bits
+int msm_make_plan(size_t n, bool merged, MsmPlan &plan) {
+  const int c = choose_window(n, merged);
+  const int W = (754 + c - 1) / c;
+  plan.c = c;
+  plan.W = W;
+  plan.merged = merged;
+  plan.nb = 1u << (c - 1);
+  plan.nbuckets = merged ? (size_t)plan.nb : (size_t)W * plan.nb;
+  plan.windows.resize(W);
+  int excess = W * c - 1 - 753;
+  uint32_t start = 0;
+  for (int j = 0; j < W; j++) {
+    uint32_t width = (j == W - 1 || j < excess) ? (uint32_t)(c - 1) : (uint32_t)c;
+    plan.windows[j] = start | (width << 16);
+    start += width;
+  }
+  if (start != 753 || excess > W - 1) return set_error(-2, "msm: bad window plan c=%d", c);
+  if ((size_t)W * n >= (1ull << 31)) return set_error(-2, "msm: W*n = %zu overflows 31-bit entry indices", (size_t)W * n);
+  return 0;
 }
 
 MsmWorkspace &msm_workspace() {
@@ -131,27 +159,10 @@ void msm_release_workspace() {
 
 int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   if (n >= (1ull << 30)) return set_error(-2, "msm: n=%zu too large", n);
-  const int c = choose_window(n);
-  const int W = (754 + c - 1) / c;
-  const uint32_t nb = 1u << (c - 1);
-  // window plan (see msm_digits_kernel): top window c-1 bits, `excess` low windows c-1 bits, the rest c bits
-  plan.c = c;
-  plan.W = W;
-  plan.nb = nb;
-  plan.nbuckets = (size_t)W * nb;
-  plan.windows.resize(W);
-  {
-    int excess = W * c - 1 - 753;
-    uint32_t start = 0;
-    for (int j = 0; j < W; j++) {
-      uint32_t width = (j == W - 1 || j < excess) ? (uint32_t)(c - 1) : (uint32_t)c;
-      plan.windows[j] = start | (width << 16);
-      start += width;
-    }
-    if (start != 753 || excess > W - 1) return set_error(-2, "msm: bad window plan c=%d", c);
-  }
+  if (plan.W == 0) B200_CHECK(msm_make_plan(n, false, plan));  // caller did not fix a plan: per-window buckets
+  const int c = plan.c, W = plan.W;
+  const int merged = plan.merged ? 1 : 0;
   const size_t nbuckets = plan.nbuckets;
-  if ((size_t)W * n >= (1ull << 32)) return set_error(-2, "msm: W*n overflows 32-bit entry positions");
   MsmWorkspace &ws = msm_workspace();
   B200_CHECK(ws.digits.reserve((size_t)W * n * sizeof(int32_t)));
   B200_CHECK(ws.entries.reserve((size_t)W * n * sizeof(uint32_t)));
@@ -170,11 +181,11 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   B200_CUDA_CHECK(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), 0));
   B200_CUDA_CHECK(cudaMemsetAsync(ws.cursor.p, 0, nbuckets * sizeof(uint32_t), 0));
   if (fr_tag == 0)
-    msm_digits_kernel<PrimeA><<<grid_for(n, 128), 128>>>((const Fp<PrimeA> *)d_scalars, (uint32_t)n, c, W,
+    msm_digits_kernel<PrimeA><<<grid_for(n, 128), 128>>>((const Fp<PrimeA> *)d_scalars, (uint32_t)n, c, W, merged,
                                                          ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
                                                          ws.counts.as<uint32_t>());
   else
-    msm_digits_kernel<PrimeB><<<grid_for(n, 128), 128>>>((const Fp<PrimeB> *)d_scalars, (uint32_t)n, c, W,
+    msm_digits_kernel<PrimeB><<<grid_for(n, 128), 128>>>((const Fp<PrimeB> *)d_scalars, (uint32_t)n, c, W, merged,
                                                          ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
                                                          ws.counts.as<uint32_t>());
   B200_CUDA_CHECK(cudaGetLastError());
@@ -185,7 +196,7 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   tm.start();
   size_t tmp_bytes = 0, tmp2 = 0;
   int end_bit = 1;
-  while ((1ull << end_bit) <= n) end_bit++;
+  while ((1ull << end_bit) <= (merged ? (size_t)W * n : n)) end_bit++;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ws.counts.as<uint32_t>(), ws.offsets.as<uint32_t>(), (int)nbuckets);
   cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, ws.counts.as<uint32_t>(), ws.counts_sorted.as<uint32_t>(),
                                             ws.iota.as<uint32_t>(), ws.order.as<uint32_t>(), (int)nbuckets, 0, end_bit);
@@ -196,7 +207,7 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
                                                 (int)nbuckets));
   {
     size_t total = (size_t)W * n;
-    msm_scatter_kernel<<<grid_for(total, 256), 256>>>(ws.digits.as<int32_t>(), (uint32_t)n, W, c,
+    msm_scatter_kernel<<<grid_for(total, 256), 256>>>(ws.digits.as<int32_t>(), (uint32_t)n, W, c, merged,
                                                       ws.offsets.as<uint32_t>(), ws.cursor.as<uint32_t>(),
                                                       ws.entries.as<uint32_t>());
     B200_CUDA_CHECK(cudaGetLastError());
@@ -228,6 +239,28 @@ int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const voi
   if (curve == 0 && group == 2) return msm_run_deferred_mnt4g2(d_scalars, d_points, n, h_out, tail);
   if (curve == 1 && group == 1) return msm_run_deferred_mnt6g1(d_scalars, d_points, n, h_out, tail);
   if (curve == 1 && group == 2) return msm_run_deferred_mnt6g2(d_scalars, d_points, n, h_out, tail);
+  return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
+}
+
+#define B200_DECL_G(name)                                                                                   \
+  int msm_precompute_##name(const void *, size_t, MsmPlan &, DevBuf &);                                     \
+  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, std::function<void()> &);
+B200_DECL_G(mnt4g1) B200_DECL_G(mnt4g2) B200_DECL_G(mnt6g1) B200_DECL_G(mnt6g2)
+#undef B200_DECL_G
+
+int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n, MsmPlan &plan, DevBuf &table) {
+  if (curve == 0 && group == 1) return msm_precompute_mnt4g1(d_points, n, plan, table);
+  if (curve == 0 && group == 2) return msm_precompute_mnt4g2(d_points, n, plan, table);
+  if (curve == 1 && group == 1) return msm_precompute_mnt6g1(d_points, n, plan, table);
+  if (curve == 1 && group == 2) return msm_precompute_mnt6g2(d_points, n, plan, table);
+  return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
+}
+int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
+                                const MsmPlan &plan, void *h_out, std::function<void()> &tail) {
+  if (curve == 0 && group == 1) return msm_run_table_deferred_mnt4g1(d_scalars, d_table, n, plan, h_out, tail);
+  if (curve == 0 && group == 2) return msm_run_table_deferred_mnt4g2(d_scalars, d_table, n, plan, h_out, tail);
+  if (curve == 1 && group == 1) return msm_run_table_deferred_mnt6g1(d_scalars, d_table, n, plan, h_out, tail);
+  if (curve == 1 && group == 2) return msm_run_table_deferred_mnt6g2(d_scalars, d_table, n, plan, h_out, tail);
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 

@@ -5,4 +5,9 @@ int msm_run_mnt6g2(const void *s, const void *p, size_t n, void *out) { return m
 int msm_run_deferred_mnt6g2(const void *s, const void *p, size_t n, void *out, std::function<void()> &tail) {
   return msm_run_deferred<Mnt6G2>(s, p, n, out, tail);
 }
+int msm_precompute_mnt6g2(const void *p, size_t n, MsmPlan &plan, DevBuf &table) { return msm_precompute<Mnt6G2>(p, n, plan, table); }
+int msm_run_table_deferred_mnt6g2(const void *s, const void *t, size_t n, const MsmPlan &plan, void *out,
+                                  std::function<void()> &tail) {
+  return msm_run_table_deferred<Mnt6G2>(s, t, n, plan, out, tail);
+}
 }  // namespace b200

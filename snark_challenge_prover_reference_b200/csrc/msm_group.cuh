@@ -93,7 +93,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   typedef typename G::ScalarPrime FrP;
   B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan));
   MsmWorkspace &ws = msm_workspace();
-  const int W = plan.W;
+  const int W = plan.merged ? 1 : plan.W;  // number of independent bucket sets to reduce
   const uint32_t nb = plan.nb;
   const size_t nbuckets = plan.nbuckets;
   B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
@@ -110,7 +110,10 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
 
   // ---- bucket reduction: chunks of K buckets, then tree sum per window
   tm.start();
-  uint32_t K = nb < 32 ? nb : 32;
+  // chunk length: long chunks amortise the lo*sum fix-up, short ones keep enough threads in flight (>= ~32 K)
+  uint32_t K = 32;
+  while (K > 2 && (size_t)W * (nb / K) < 32768) K >>= 1;
+  if (K > nb) K = nb;
   uint32_t per = nb / K;
   B200_CHECK(ws.red_a.reserve((size_t)W * per * sizeof(Proj<F>)));
   B200_CHECK(ws.red_b.reserve((size_t)W * ((per + 7) / 8) * sizeof(Proj<F>) + 16));
@@ -144,7 +147,8 @@ double msm_host_phase(const MsmPlan &plan, const std::vector<Proj<typename G::F>
   Proj<F> result;
   proj_set_zero(result);
   auto t0 = std::chrono::steady_clock::now();
-  for (int j = plan.W - 1; j >= 0; j--) {
+  if (plan.merged) result = win[0];  // pre-shifted bases: the single bucket set already carries the 2^start_j weights
+  for (int j = plan.merged ? -1 : plan.W - 1; j >= 0; j--) {
     if (!proj_is_zero(result))
       for (uint32_t k = 0; k < (plan.windows[j] >> 16); k++) proj_dbl<G>(result, result);
     proj_add<G>(result, result, win[j]);
@@ -185,6 +189,97 @@ int msm_run_deferred(const void *d_scalars, const void *d_points, size_t n, void
   auto plan = std::make_shared<MsmPlan>();
   auto win = std::make_shared<std::vector<Proj<F>>>();
   B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, *plan, *win));
+  tail = [plan, win, h_out]() { msm_host_phase<G>(*plan, *win, h_out); };
+  return 0;
+}
+
+
+// ---- pre-shifted bases ------------------------------------------------------------------------------------------
+// table[j*n + i] = 2^(start_j) * P_i in affine wire format, for the W windows of `plan`. One thread per base: W-1 runs
+// of doublings in projective coordinates, then ONE field inversion for all W points (Montgomery's trick).
+// With this table every window's digits land in one shared bucket set (weights are baked into the bases), so the
+// bucket reduction runs once instead of W times and the serial 753-doubling window combine disappears; the saved
+// work also moves the optimal window width up (fewer windows). The table depends only on the proving key: it is
+// built when the key is loaded, like the reference parses and stores the key before its timer starts (main.cpp:200-203).
+template <class G, int MAXW>
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<typename G::F> *__restrict__ points, uint32_t n,
+                                                             int W, const uint32_t *__restrict__ plan,
+                                                             Affine<typename G::F> *__restrict__ table) {
+  typedef typename G::F F;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> a = points[i];
+  if (affine_is_zero(a)) {
+    for (int j = 0; j < W; j++) table[(size_t)j * n + i] = a;
+    return;
+  }
+  F zs[MAXW], prefix[MAXW];
+  Proj<F> cur;
+  proj_from_affine(cur, a);
+  for (int j = 0; j < W; j++) {
+    // stash X, Y in the output slot, keep Z and the running product of Z's
+    Affine<F> xy;
+    xy.x = cur.X;
+    xy.y = cur.Y;
+    table[(size_t)j * n + i] = xy;
+    zs[j] = cur.Z;
+    if (j == 0) prefix[0] = cur.Z;
+    else F::mul(prefix[j], prefix[j - 1], cur.Z);
+    if (j + 1 < W) {
+      uint32_t width = plan[j] >> 16;
+      for (uint32_t k = 0; k < width; k++) proj_dbl<G>(cur, cur);
+    }
+  }
+  F inv;
+  F::inv(inv, prefix[W - 1]);
+  for (int j = W - 1; j >= 0; j--) {
+    F zinv;
+    if (j > 0) F::mul(zinv, inv, prefix[j - 1]);
+    else zinv = inv;
+    F::mul(inv, inv, zs[j]);
+    Affine<F> xy = table[(size_t)j * n + i];
+    F::mul(xy.x, xy.x, zinv);
+    F::mul(xy.y, xy.y, zinv);
+    table[(size_t)j * n + i] = xy;
+  }
+}
+
+template <class G>
+int msm_precompute(const void *d_points, size_t n, MsmPlan &plan, DevBuf &table) {
+  typedef typename G::F F;
+  B200_CHECK(msm_make_plan(n, true, plan));
+  if (plan.W > 96) return set_error(-2, "msm_precompute: %d windows exceed the kernel's limit", plan.W);
+  B200_CHECK(table.alloc((size_t)plan.W * n * sizeof(Affine<F>)));
+  DevBuf dplan;
+  B200_CHECK(dplan.alloc(plan.W * sizeof(uint32_t)));
+  B200_CUDA_CHECK(cudaMemcpy(dplan.p, plan.windows.data(), plan.W * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  if (plan.W <= 48)
+    msm_precompute_kernel<G, 48><<<grid_for(n, 128), 128>>>((const Affine<F> *)d_points, (uint32_t)n, plan.W,
+                                                            dplan.as<uint32_t>(), table.as<Affine<F>>());
+  else
+    msm_precompute_kernel<G, 96><<<grid_for(n, 128), 128>>>((const Affine<F> *)d_points, (uint32_t)n, plan.W,
+                                                            dplan.as<uint32_t>(), table.as<Affine<F>>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  B200_CUDA_CHECK(cudaDeviceSynchronize());
+  return 0;
+}
+
+// MSM over a table built by msm_precompute (plan must be the table's plan).
+template <class G>
+int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n, const MsmPlan &table_plan, void *h_out,
+                           std::function<void()> &tail) {
+  typedef typename G::F F;
+  if (n == 0) {
+    Proj<F> zero;
+    proj_set_zero(zero);
+    memcpy(h_out, &zero, sizeof(zero));
+    tail = []() {};
+    return 0;
+  }
+  auto plan = std::make_shared<MsmPlan>(table_plan);
+  auto win = std::make_shared<std::vector<Proj<F>>>();
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, *win));
   tail = [plan, win, h_out]() { msm_host_phase<G>(*plan, *win, h_out); };
   return 0;
 }

@@ -3,6 +3,7 @@
 // Split this way so the slow-to-compile group code builds in parallel.
 #pragma once
 #include <stdint.h>
+#include <functional>
 #include <vector>
 #include "common.cuh"
 
@@ -15,8 +16,9 @@ MsmWorkspace &msm_workspace();
 
 struct MsmPlan {
   int c = 0, W = 0;
+  bool merged = false;          // all windows share one bucket set (entries index a table of pre-shifted bases)
   uint32_t nb = 0;              // buckets per window = 2^(c-1)
-  size_t nbuckets = 0;          // W * nb
+  size_t nbuckets = 0;          // W * nb, or nb when merged
   std::vector<uint32_t> windows;  // start_bit | width << 16
 };
 
@@ -25,6 +27,12 @@ extern double g_msm_phase_total[2][5];   // accumulated, [0] G1 calls, [1] G2 ca
 
 // Phase 1+2 (group independent): window plan, signed digits, histogram, counting sort of point indices by
 // (window, bucket), bucket visiting order by descending size. fr_tag: 0 = modulus A, 1 = modulus B.
+// plan.W == 0 on entry: choose a per-window plan for n. Otherwise the caller's plan (e.g. the one a table was built for).
 int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan);
+int msm_make_plan(size_t n, bool merged, MsmPlan &plan);
+// pre-shifted base tables (merged buckets), see msm_group.cuh
+int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n, MsmPlan &plan, DevBuf &table);
+int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
+                                const MsmPlan &plan, void *h_out, std::function<void()> &tail);
 
 }  // namespace b200

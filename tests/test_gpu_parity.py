@@ -324,10 +324,20 @@ def test_ntt_roundtrip_full_size(b200, dev):
 
 
 # ------------------------------------------------------------------------------------------------ whole prover
+@pytest.fixture(params=[True, False], ids=["tables", "no-tables"])
+def precompute(request, b200):
+    """run with and without the pre-shifted base tables (b200_params_precompute)"""
+    b200.set_precompute(request.param)
+    yield request.param
+    b200.set_precompute(True)
+
+
 @pytest.mark.parametrize("curve,k", [(0, 5), (1, 5), (0, 8), (1, 8)])
-def test_prover_matches_reference_golden(b200, dev, curve, k):
+def test_prover_matches_reference_golden(b200, dev, precompute, curve, k):
     params, inp, expected = util.golden(curve, k)
     P = b200.Params.from_bytes(curve, params)
+    if precompute:
+        assert P.precompute() > 0
     assert (P.d, P.m) == ((1 << k) - 1, 1 << k)
     got = P.prove(inp)
     assert got == expected
@@ -337,7 +347,7 @@ def test_prover_matches_reference_golden(b200, dev, curve, k):
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-def test_sharded_prover_matches_reference_golden(b200, dev, curve):
+def test_sharded_prover_matches_reference_golden(b200, dev, precompute, curve):
     """MSMs split by point range over `world` ranks (run sequentially on one GPU here) + host combine."""
     params, inp, expected = util.golden(curve, 8)
     P = b200.Params.from_bytes(curve, params)
