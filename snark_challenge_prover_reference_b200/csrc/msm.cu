@@ -98,6 +98,25 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t *__restr
   entries[pos] = (e << 1) | (d < 0 ? 1u : 0u);
 }
 
+// ---- tasks: a bucket's entry list is cut into pieces of at most T entries; one thread sums one piece -------------
+__global__ void msm_ntasks_kernel(const uint32_t *__restrict__ counts, uint32_t nbuckets, uint32_t T,
+                                  uint32_t *__restrict__ ntasks) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nbuckets) ntasks[b] = (counts[b] + T - 1) / T;
+}
+// one thread per bucket writes the descriptors of its tasks: owning bucket and length
+__global__ void msm_task_fill_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ task_off,
+                                     uint32_t nbuckets, uint32_t T, uint32_t *__restrict__ task_bucket,
+                                     uint32_t *__restrict__ task_len) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  uint32_t cnt = counts[b], t = task_off[b];
+  for (uint32_t done = 0; done < cnt; done += T, t++) {
+    task_bucket[t] = b;
+    task_len[t] = cnt - done < T ? cnt - done : T;
+  }
+}
+
 __global__ void iota_kernel(uint32_t *v, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = i;
@@ -153,7 +172,8 @@ MsmWorkspace &msm_workspace() {
 void msm_release_workspace() {
   MsmWorkspace &ws = msm_workspace();
   DevBuf *all[] = {&ws.digits, &ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.order,
-                   &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan};
+                   &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan,
+                   &ws.ntasks, &ws.task_off, &ws.task_bucket, &ws.task_len, &ws.task_len_sorted, &ws.partials};
   for (DevBuf *b : all) b->release();
 }
 
@@ -169,9 +189,8 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   B200_CHECK(ws.counts.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.offsets.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.cursor.reserve(nbuckets * sizeof(uint32_t)));
-  B200_CHECK(ws.order.reserve(nbuckets * sizeof(uint32_t)));
-  B200_CHECK(ws.counts_sorted.reserve(nbuckets * sizeof(uint32_t)));
-  B200_CHECK(ws.iota.reserve(nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.ntasks.reserve(nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.task_off.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.plan.reserve(256 * sizeof(uint32_t)));
   B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.windows.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
   Timer tm;
@@ -192,15 +211,10 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   note_launch();
   g_msm_phase_ms[0] = tm.stop();
 
-  // ---- counting sort: scan, scatter; then bucket order by descending size
+  // ---- counting sort of the entries by bucket: scan + scatter
   tm.start();
-  size_t tmp_bytes = 0, tmp2 = 0;
-  int end_bit = 1;
-  while ((1ull << end_bit) <= (merged ? (size_t)W * n : n)) end_bit++;
+  size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ws.counts.as<uint32_t>(), ws.offsets.as<uint32_t>(), (int)nbuckets);
-  cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp2, ws.counts.as<uint32_t>(), ws.counts_sorted.as<uint32_t>(),
-                                            ws.iota.as<uint32_t>(), ws.order.as<uint32_t>(), (int)nbuckets, 0, end_bit);
-  if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
   B200_CHECK(ws.cub_tmp.reserve(tmp_bytes));
   size_t tb = ws.cub_tmp.bytes;
   B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.p, tb, ws.counts.as<uint32_t>(), ws.offsets.as<uint32_t>(),
@@ -213,12 +227,50 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
     B200_CUDA_CHECK(cudaGetLastError());
     note_launch();
   }
-  iota_kernel<<<grid_for(nbuckets, 256), 256>>>(ws.iota.as<uint32_t>(), (uint32_t)nbuckets);
-  note_launch();
-  tb = ws.cub_tmp.bytes;
-  B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(ws.cub_tmp.p, tb, ws.counts.as<uint32_t>(),
-                                                            ws.counts_sorted.as<uint32_t>(), ws.iota.as<uint32_t>(),
-                                                            ws.order.as<uint32_t>(), (int)nbuckets, 0, end_bit));
+  // ---- tasks: pieces of <= T entries, visited longest-first (equal loop lengths inside a warp). T keeps a few
+  // hundred thousand threads in flight even when there are few buckets (small n, or one merged bucket set), and it
+  // bounds the serial chain of any single thread when the scalar distribution is skewed.
+  {
+    size_t entries_total = (size_t)W * n;
+    uint32_t T = 64;
+    while (T > 8 && entries_total / T < 260000) T >>= 1;
+    plan.task_len = T;
+    msm_ntasks_kernel<<<grid_for(nbuckets, 256), 256>>>(ws.counts.as<uint32_t>(), (uint32_t)nbuckets, T,
+                                                       ws.ntasks.as<uint32_t>());
+    note_launch();
+    tb = ws.cub_tmp.bytes;
+    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.p, tb, ws.ntasks.as<uint32_t>(),
+                                                  ws.task_off.as<uint32_t>(), (int)nbuckets));
+    uint32_t last[2];
+    B200_CUDA_CHECK(cudaMemcpy(&last[0], ws.task_off.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost));
+    B200_CUDA_CHECK(cudaMemcpy(&last[1], ws.ntasks.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost));
+    const size_t ntasks = (size_t)last[0] + last[1];
+    plan.ntasks = ntasks;
+    const size_t cap = ntasks ? ntasks : 1;
+    B200_CHECK(ws.task_bucket.reserve(cap * sizeof(uint32_t)));
+    B200_CHECK(ws.task_len.reserve(cap * sizeof(uint32_t)));
+    B200_CHECK(ws.task_len_sorted.reserve(cap * sizeof(uint32_t)));
+    B200_CHECK(ws.order.reserve(cap * sizeof(uint32_t)));
+    B200_CHECK(ws.iota.reserve(cap * sizeof(uint32_t)));
+    if (ntasks) {
+      msm_task_fill_kernel<<<grid_for(nbuckets, 256), 256>>>(ws.counts.as<uint32_t>(), ws.task_off.as<uint32_t>(),
+                                                            (uint32_t)nbuckets, T, ws.task_bucket.as<uint32_t>(),
+                                                            ws.task_len.as<uint32_t>());
+      note_launch();
+      iota_kernel<<<grid_for(ntasks, 256), 256>>>(ws.iota.as<uint32_t>(), (uint32_t)ntasks);
+      note_launch();
+      int end_bit = 1;
+      while ((1u << end_bit) <= T) end_bit++;
+      size_t need = 0;
+      cub::DeviceRadixSort::SortPairsDescending(nullptr, need, ws.task_len.as<uint32_t>(), ws.task_len_sorted.as<uint32_t>(),
+                                                ws.iota.as<uint32_t>(), ws.order.as<uint32_t>(), (int)ntasks, 0, end_bit);
+      B200_CHECK(ws.cub_tmp.reserve(need));
+      tb = ws.cub_tmp.bytes;
+      B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(ws.cub_tmp.p, tb, ws.task_len.as<uint32_t>(),
+                                                                ws.task_len_sorted.as<uint32_t>(), ws.iota.as<uint32_t>(),
+                                                                ws.order.as<uint32_t>(), (int)ntasks, 0, end_bit));
+    }
+  }
   g_msm_phase_ms[1] = tm.stop();
   return 0;
 }

@@ -11,27 +11,50 @@
 
 namespace b200 {
 
+// One thread sums one task (a piece of <= T entries of one bucket's list) by mixed addition.
 template <class G>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
                                                              const uint32_t *__restrict__ entries,
                                                              const uint32_t *__restrict__ offsets,
-                                                             const uint32_t *__restrict__ counts_sorted,
-                                                             const uint32_t *__restrict__ order, uint32_t nbuckets,
-                                                             Proj<typename G::F> *__restrict__ buckets) {
+                                                             const uint32_t *__restrict__ task_off,
+                                                             const uint32_t *__restrict__ task_bucket,
+                                                             const uint32_t *__restrict__ task_len_sorted,
+                                                             const uint32_t *__restrict__ order, uint32_t ntasks,
+                                                             uint32_t T, Proj<typename G::F> *__restrict__ partials) {
   typedef typename G::F F;
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nbuckets) return;
-  uint32_t b = order[t];
-  uint32_t cnt = counts_sorted[t];
-  uint32_t start = offsets[b];
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntasks) return;
+  const uint32_t t = order[i];
+  const uint32_t b = task_bucket[t];
+  const uint32_t len = task_len_sorted[i];
+  const uint32_t start = offsets[b] + (t - task_off[b]) * T;
   Proj<F> acc;
   proj_set_zero(acc);
-  for (uint32_t k = 0; k < cnt; k++) {
+  for (uint32_t k = 0; k < len; k++) {
     uint32_t e = entries[start + k];
     Affine<F> q = points[e >> 1];
     if (affine_is_zero(q)) continue;
     if (e & 1) F::neg(q.y, q.y);
     proj_madd<G>(acc, q);
+  }
+  partials[t] = acc;
+}
+
+// bucket value = sum of the partial sums of its tasks (usually one: then this is a copy; none: O)
+template <class G>
+__global__ void __launch_bounds__(128) msm_combine_kernel(const Proj<typename G::F> *__restrict__ partials,
+                                                          const uint32_t *__restrict__ task_off,
+                                                          const uint32_t *__restrict__ ntasks, uint32_t nbuckets,
+                                                          Proj<typename G::F> *__restrict__ buckets) {
+  typedef typename G::F F;
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  const uint32_t cnt = ntasks[b], off = task_off[b];
+  Proj<F> acc;
+  proj_set_zero(acc);
+  for (uint32_t s = 0; s < cnt; s++) {
+    Proj<F> cur = partials[off + s];
+    proj_add<G>(acc, acc, cur);
   }
   buckets[b] = acc;
 }
@@ -99,11 +122,20 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
   Timer tm;
 
-  // ---- bucket accumulation
+  // ---- bucket accumulation: one thread per task, then per-bucket combine of the task sums
   tm.start();
-  msm_accumulate_kernel<G><<<grid_for(nbuckets, 128), 128>>>(
-      (const Affine<F> *)d_points, ws.entries.as<uint32_t>(), ws.offsets.as<uint32_t>(),
-      ws.counts_sorted.as<uint32_t>(), ws.order.as<uint32_t>(), (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
+  B200_CHECK(ws.partials.reserve((plan.ntasks ? plan.ntasks : 1) * sizeof(Proj<F>)));
+  if (plan.ntasks) {
+    msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128>>>(
+        (const Affine<F> *)d_points, ws.entries.as<uint32_t>(), ws.offsets.as<uint32_t>(), ws.task_off.as<uint32_t>(),
+        ws.task_bucket.as<uint32_t>(), ws.task_len_sorted.as<uint32_t>(), ws.order.as<uint32_t>(),
+        (uint32_t)plan.ntasks, plan.task_len, ws.partials.as<Proj<F>>());
+    B200_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+  }
+  msm_combine_kernel<G><<<grid_for(nbuckets, 128), 128>>>(ws.partials.as<Proj<F>>(), ws.task_off.as<uint32_t>(),
+                                                         ws.ntasks.as<uint32_t>(), (uint32_t)nbuckets,
+                                                         ws.buckets.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
   g_msm_phase_ms[2] = tm.stop();

@@ -11,6 +11,7 @@ namespace b200 {
 
 struct MsmWorkspace {
   DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b, plan;
+  DevBuf ntasks, task_off, task_bucket, task_len, task_len_sorted, partials;
 };
 MsmWorkspace &msm_workspace();
 
@@ -20,6 +21,8 @@ struct MsmPlan {
   uint32_t nb = 0;              // buckets per window = 2^(c-1)
   size_t nbuckets = 0;          // W * nb, or nb when merged
   std::vector<uint32_t> windows;  // start_bit | width << 16
+  uint32_t task_len = 0;        // T: entries per accumulation task (set by msm_prepare)
+  size_t ntasks = 0;            // number of tasks of this call (set by msm_prepare)
 };
 
 extern double g_msm_phase_ms[5];         // last call: digits, sort, accumulate, reduce, host tail
