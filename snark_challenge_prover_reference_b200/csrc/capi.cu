@@ -459,6 +459,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     size_t lo = (size_t)rank * one, hi = (rank == world - 1) ? J.n : lo + one;
     double a = now_ms();
     std::function<void()> tail;
+    msm_select_slot(jj & 1);  // alternate the two workspaces/streams: reduce(k) overlaps accumulate(k+1)
     if (use_precompute())
       rc_all = msm_table_dispatch_deferred(curve, J.group, J.scalars + lo * 96, p->pre.table[j].p, hi - lo,
                                            p->pre.plan[j], o, tail);
@@ -467,6 +468,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     if (rc_all == 0) tails.push_back(std::async(std::launch::async, tail));
     *J.ms = now_ms() - a;
   }
+  msm_select_slot(0);
   double t_join = now_ms();
   for (auto &f : tails) f.get();
   double join_ms = now_ms() - t_join;

@@ -59,9 +59,10 @@ struct DevBuf {
   T *as() const { return (T *)p; }
 };
 
-struct Timer {  // CUDA-event timer on the default stream
+struct Timer {  // CUDA-event timer on one stream
   cudaEvent_t a, b;
-  Timer() {
+  cudaStream_t st;
+  explicit Timer(cudaStream_t s = 0) : st(s) {
     cudaEventCreate(&a);
     cudaEventCreate(&b);
   }
@@ -69,9 +70,15 @@ struct Timer {  // CUDA-event timer on the default stream
     cudaEventDestroy(a);
     cudaEventDestroy(b);
   }
-  void start() { cudaEventRecord(a, 0); }
+  void start() { cudaEventRecord(a, st); }
+  void stop_async() { cudaEventRecord(b, st); }  // read later with elapsed() after the stream has drained
+  float elapsed() {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+  }
   float stop() {
-    cudaEventRecord(b, 0);
+    cudaEventRecord(b, st);
     cudaEventSynchronize(b);
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);

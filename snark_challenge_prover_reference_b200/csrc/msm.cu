@@ -165,16 +165,44 @@ int msm_make_plan(size_t n, bool merged, MsmPlan &plan) {
   return 0;
 }
 
-MsmWorkspace &msm_workspace() {
-  static thread_local MsmWorkspace ws;
+static thread_local int g_slot = 0;
+void msm_select_slot(int slot) { g_slot = slot & 1; }
+static MsmWorkspace *workspace_slots() {
+  static thread_local MsmWorkspace ws[2];
   return ws;
 }
+MsmWorkspace &msm_workspace() {
+  MsmWorkspace &ws = workspace_slots()[g_slot];
+  if (!ws.stream) cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking);
+  return ws;
+}
+MsmWorkspace::Staging *MsmWorkspace::next_staging(size_t bytes) {
+  Staging &s = ring[ring_pos];
+  ring_pos = (ring_pos + 1) & 3;
+  if (!s.done) {
+    cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    cudaEventCreate(&s.t0);
+    cudaEventCreate(&s.t1);
+  }
+  if (s.bytes < bytes) {
+    if (s.pinned) cudaFreeHost(s.pinned);
+    if (cudaMallocHost(&s.pinned, bytes) != cudaSuccess) {
+      s.pinned = nullptr;
+      s.bytes = 0;
+      return nullptr;
+    }
+    s.bytes = bytes;
+  }
+  return &s;
+}
 void msm_release_workspace() {
-  MsmWorkspace &ws = msm_workspace();
+  for (int s = 0; s < 2; s++) {
+  MsmWorkspace &ws = workspace_slots()[s];
   DevBuf *all[] = {&ws.digits, &ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.order,
                    &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan,
                    &ws.ntasks, &ws.task_off, &ws.task_bucket, &ws.task_len, &ws.task_len_sorted, &ws.partials};
   for (DevBuf *b : all) b->release();
+  }
 }
 
 int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
@@ -184,6 +212,14 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   const int merged = plan.merged ? 1 : 0;
   const size_t nbuckets = plan.nbuckets;
   MsmWorkspace &ws = msm_workspace();
+  cudaStream_t st = ws.stream;
+  {
+    // inputs are produced on the default stream (copies, compute_H, generators): order this MSM after it
+    static thread_local cudaEvent_t fence = nullptr;
+    if (!fence) B200_CUDA_CHECK(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
+    B200_CUDA_CHECK(cudaEventRecord(fence, 0));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(st, fence, 0));
+  }
   B200_CHECK(ws.digits.reserve((size_t)W * n * sizeof(int32_t)));
   B200_CHECK(ws.entries.reserve((size_t)W * n * sizeof(uint32_t)));
   B200_CHECK(ws.counts.reserve(nbuckets * sizeof(uint32_t)));
@@ -192,19 +228,19 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   B200_CHECK(ws.ntasks.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.task_off.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.plan.reserve(256 * sizeof(uint32_t)));
-  B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.windows.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
-  Timer tm;
+  B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.windows.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  Timer tm(st);
 
   // ---- digits + histogram
   tm.start();
-  B200_CUDA_CHECK(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), 0));
-  B200_CUDA_CHECK(cudaMemsetAsync(ws.cursor.p, 0, nbuckets * sizeof(uint32_t), 0));
+  B200_CUDA_CHECK(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), st));
+  B200_CUDA_CHECK(cudaMemsetAsync(ws.cursor.p, 0, nbuckets * sizeof(uint32_t), st));
   if (fr_tag == 0)
-    msm_digits_kernel<PrimeA><<<grid_for(n, 128), 128>>>((const Fp<PrimeA> *)d_scalars, (uint32_t)n, c, W, merged,
+    msm_digits_kernel<PrimeA><<<grid_for(n, 128), 128, 0, st>>>((const Fp<PrimeA> *)d_scalars, (uint32_t)n, c, W, merged,
                                                          ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
                                                          ws.counts.as<uint32_t>());
   else
-    msm_digits_kernel<PrimeB><<<grid_for(n, 128), 128>>>((const Fp<PrimeB> *)d_scalars, (uint32_t)n, c, W, merged,
+    msm_digits_kernel<PrimeB><<<grid_for(n, 128), 128, 0, st>>>((const Fp<PrimeB> *)d_scalars, (uint32_t)n, c, W, merged,
                                                          ws.plan.as<uint32_t>(), ws.digits.as<int32_t>(),
                                                          ws.counts.as<uint32_t>());
   B200_CUDA_CHECK(cudaGetLastError());
@@ -218,10 +254,10 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   B200_CHECK(ws.cub_tmp.reserve(tmp_bytes));
   size_t tb = ws.cub_tmp.bytes;
   B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.p, tb, ws.counts.as<uint32_t>(), ws.offsets.as<uint32_t>(),
-                                                (int)nbuckets));
+                                                (int)nbuckets, st));
   {
     size_t total = (size_t)W * n;
-    msm_scatter_kernel<<<grid_for(total, 256), 256>>>(ws.digits.as<int32_t>(), (uint32_t)n, W, c, merged,
+    msm_scatter_kernel<<<grid_for(total, 256), 256, 0, st>>>(ws.digits.as<int32_t>(), (uint32_t)n, W, c, merged,
                                                       ws.offsets.as<uint32_t>(), ws.cursor.as<uint32_t>(),
                                                       ws.entries.as<uint32_t>());
     B200_CUDA_CHECK(cudaGetLastError());
@@ -235,15 +271,16 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
     uint32_t T = 64;
     while (T > 8 && entries_total / T < 260000) T >>= 1;
     plan.task_len = T;
-    msm_ntasks_kernel<<<grid_for(nbuckets, 256), 256>>>(ws.counts.as<uint32_t>(), (uint32_t)nbuckets, T,
+    msm_ntasks_kernel<<<grid_for(nbuckets, 256), 256, 0, st>>>(ws.counts.as<uint32_t>(), (uint32_t)nbuckets, T,
                                                        ws.ntasks.as<uint32_t>());
     note_launch();
     tb = ws.cub_tmp.bytes;
     B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.p, tb, ws.ntasks.as<uint32_t>(),
-                                                  ws.task_off.as<uint32_t>(), (int)nbuckets));
+                                                  ws.task_off.as<uint32_t>(), (int)nbuckets, st));
     uint32_t last[2];
-    B200_CUDA_CHECK(cudaMemcpy(&last[0], ws.task_off.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost));
-    B200_CUDA_CHECK(cudaMemcpy(&last[1], ws.ntasks.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost));
+    B200_CUDA_CHECK(cudaMemcpyAsync(&last[0], ws.task_off.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(&last[1], ws.ntasks.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
     const size_t ntasks = (size_t)last[0] + last[1];
     plan.ntasks = ntasks;
     const size_t cap = ntasks ? ntasks : 1;
@@ -253,11 +290,11 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
     B200_CHECK(ws.order.reserve(cap * sizeof(uint32_t)));
     B200_CHECK(ws.iota.reserve(cap * sizeof(uint32_t)));
     if (ntasks) {
-      msm_task_fill_kernel<<<grid_for(nbuckets, 256), 256>>>(ws.counts.as<uint32_t>(), ws.task_off.as<uint32_t>(),
+      msm_task_fill_kernel<<<grid_for(nbuckets, 256), 256, 0, st>>>(ws.counts.as<uint32_t>(), ws.task_off.as<uint32_t>(),
                                                             (uint32_t)nbuckets, T, ws.task_bucket.as<uint32_t>(),
                                                             ws.task_len.as<uint32_t>());
       note_launch();
-      iota_kernel<<<grid_for(ntasks, 256), 256>>>(ws.iota.as<uint32_t>(), (uint32_t)ntasks);
+      iota_kernel<<<grid_for(ntasks, 256), 256, 0, st>>>(ws.iota.as<uint32_t>(), (uint32_t)ntasks);
       note_launch();
       int end_bit = 1;
       while ((1u << end_bit) <= T) end_bit++;
@@ -268,7 +305,7 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
       tb = ws.cub_tmp.bytes;
       B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(ws.cub_tmp.p, tb, ws.task_len.as<uint32_t>(),
                                                                 ws.task_len_sorted.as<uint32_t>(), ws.iota.as<uint32_t>(),
-                                                                ws.order.as<uint32_t>(), (int)ntasks, 0, end_bit));
+                                                                ws.order.as<uint32_t>(), (int)ntasks, 0, end_bit, st));
     }
   }
   g_msm_phase_ms[1] = tm.stop();

@@ -108,40 +108,43 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 }
 
 
-// GPU half of one MSM: everything up to the per-window sums, copied to the host (the copy synchronises).
+// GPU half of one MSM. Returns after the accumulation has finished and the (latency-bound) bucket reduction has been
+// ENQUEUED on the workspace's stream; the window sums arrive asynchronously in `stage` (wait on stage->done).
 template <class G>
-int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan,
-                  std::vector<Proj<typename G::F>> &win) {
+int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan, MsmWorkspace::Staging *&stage) {
   typedef typename G::F F;
   typedef typename G::ScalarPrime FrP;
   B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan));
   MsmWorkspace &ws = msm_workspace();
+  cudaStream_t st = ws.stream;
   const int W = plan.merged ? 1 : plan.W;  // number of independent bucket sets to reduce
   const uint32_t nb = plan.nb;
   const size_t nbuckets = plan.nbuckets;
   B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
-  Timer tm;
+  stage = ws.next_staging((size_t)W * sizeof(Proj<F>));
+  if (!stage) return set_error(-5, "msm: pinned staging allocation failed");
+  Timer tm(st);
 
   // ---- bucket accumulation: one thread per task, then per-bucket combine of the task sums
   tm.start();
   B200_CHECK(ws.partials.reserve((plan.ntasks ? plan.ntasks : 1) * sizeof(Proj<F>)));
   if (plan.ntasks) {
-    msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128>>>(
+    msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128, 0, st>>>(
         (const Affine<F> *)d_points, ws.entries.as<uint32_t>(), ws.offsets.as<uint32_t>(), ws.task_off.as<uint32_t>(),
         ws.task_bucket.as<uint32_t>(), ws.task_len_sorted.as<uint32_t>(), ws.order.as<uint32_t>(),
         (uint32_t)plan.ntasks, plan.task_len, ws.partials.as<Proj<F>>());
     B200_CUDA_CHECK(cudaGetLastError());
     note_launch();
   }
-  msm_combine_kernel<G><<<grid_for(nbuckets, 128), 128>>>(ws.partials.as<Proj<F>>(), ws.task_off.as<uint32_t>(),
-                                                         ws.ntasks.as<uint32_t>(), (uint32_t)nbuckets,
-                                                         ws.buckets.as<Proj<F>>());
+  msm_combine_kernel<G><<<grid_for(nbuckets, 128), 128, 0, st>>>(ws.partials.as<Proj<F>>(), ws.task_off.as<uint32_t>(),
+                                                                 ws.ntasks.as<uint32_t>(), (uint32_t)nbuckets,
+                                                                 ws.buckets.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
   g_msm_phase_ms[2] = tm.stop();
 
-  // ---- bucket reduction: chunks of K buckets, then tree sum per window
-  tm.start();
+  // ---- bucket reduction (enqueued, not awaited): chunks of K buckets, then tree sum per bucket set
+  B200_CUDA_CHECK(cudaEventRecord(stage->t0, st));
   // chunk length: long chunks amortise the lo*sum fix-up, short ones keep enough threads in flight (>= ~32 K)
   uint32_t K = 32;
   while (K > 2 && (size_t)W * (nb / K) < 32768) K >>= 1;
@@ -149,15 +152,15 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   uint32_t per = nb / K;
   B200_CHECK(ws.red_a.reserve((size_t)W * per * sizeof(Proj<F>)));
   B200_CHECK(ws.red_b.reserve((size_t)W * ((per + 7) / 8) * sizeof(Proj<F>) + 16));
-  msm_reduce_kernel<G><<<grid_for((size_t)W * per, 128), 128>>>(ws.buckets.as<Proj<F>>(), W, nb, K,
-                                                               ws.red_a.as<Proj<F>>());
+  msm_reduce_kernel<G><<<grid_for((size_t)W * per, 128), 128, 0, st>>>(ws.buckets.as<Proj<F>>(), W, nb, K,
+                                                                       ws.red_a.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
   Proj<F> *cur = ws.red_a.as<Proj<F>>(), *nxt = ws.red_b.as<Proj<F>>();
   while (per > 1) {
     uint32_t R = 8;
     uint32_t per_out = (per + R - 1) / R;
-    msm_sum_kernel<G><<<grid_for((size_t)W * per_out, 128), 128>>>(cur, W, per, R, nxt);
+    msm_sum_kernel<G><<<grid_for((size_t)W * per_out, 128), 128, 0, st>>>(cur, W, per, R, nxt);
     B200_CUDA_CHECK(cudaGetLastError());
     note_launch();
     Proj<F> *t = cur;
@@ -165,10 +168,25 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
     nxt = t;
     per = per_out;
   }
+  B200_CUDA_CHECK(cudaMemcpyAsync(stage->pinned, cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost, st));
+  B200_CUDA_CHECK(cudaEventRecord(stage->t1, st));
+  B200_CUDA_CHECK(cudaEventRecord(stage->done, st));
+  for (int i = 0; i < 3; i++) g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i] += g_msm_phase_ms[i];
+  return 0;
+}
+
+// wait for the window sums of an MSM issued by msm_gpu_phase and fetch them
+template <class G>
+int msm_collect(const MsmPlan &plan, MsmWorkspace::Staging *stage, std::vector<Proj<typename G::F>> &win) {
+  typedef typename G::F F;
+  B200_CUDA_CHECK(cudaEventSynchronize(stage->done));
+  const int W = plan.merged ? 1 : plan.W;
   win.resize(W);
-  B200_CUDA_CHECK(cudaMemcpy(win.data(), cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost));
-  g_msm_phase_ms[3] = tm.stop();
-  for (int i = 0; i < 4; i++) g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i] += g_msm_phase_ms[i];
+  memcpy(win.data(), stage->pinned, (size_t)W * sizeof(Proj<F>));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, stage->t0, stage->t1);
+  g_msm_phase_ms[3] = ms;
+  g_msm_phase_total[F::kDegree == 1 ? 0 : 1][3] += ms;
   return 0;
 }
 
@@ -199,15 +217,18 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
     return 0;
   }
   MsmPlan plan;
+  MsmWorkspace::Staging *stage = nullptr;
   std::vector<Proj<F>> win;
-  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, plan, win));
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, plan, stage));
+  B200_CHECK(msm_collect<G>(plan, stage, win));
   g_msm_phase_ms[4] = msm_host_phase<G>(plan, win, h_out);
   g_msm_phase_total[F::kDegree == 1 ? 0 : 1][4] += g_msm_phase_ms[4];
   return 0;
 }
 
-// Same sum, but the serial host tail is returned as a closure so that the caller can run it on another thread while
-// the next MSM already occupies the GPU (b200_prove does this for its five MSMs).
+// Same sum, but the wait for the bucket reduction and the serial host tail are returned as a closure, so that the
+// caller can run them on another thread while the next MSM already occupies the GPU (b200_prove does this for its five
+// MSMs, alternating the two workspaces/streams).
 template <class G>
 int msm_run_deferred(const void *d_scalars, const void *d_points, size_t n, void *h_out, std::function<void()> &tail) {
   typedef typename G::F F;
@@ -219,12 +240,14 @@ int msm_run_deferred(const void *d_scalars, const void *d_points, size_t n, void
     return 0;
   }
   auto plan = std::make_shared<MsmPlan>();
-  auto win = std::make_shared<std::vector<Proj<F>>>();
-  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, *plan, *win));
-  tail = [plan, win, h_out]() { msm_host_phase<G>(*plan, *win, h_out); };
+  MsmWorkspace::Staging *stage = nullptr;
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, *plan, stage));
+  tail = [plan, stage, h_out]() {
+    std::vector<Proj<F>> win;
+    if (msm_collect<G>(*plan, stage, win) == 0) msm_host_phase<G>(*plan, win, h_out);
+  };
   return 0;
 }
-
 
 // ---- pre-shifted bases ------------------------------------------------------------------------------------------
 // table[j*n + i] = 2^(start_j) * P_i in affine wire format, for the W windows of `plan`. One thread per base: W-1 runs
@@ -310,9 +333,12 @@ int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n,
     return 0;
   }
   auto plan = std::make_shared<MsmPlan>(table_plan);
-  auto win = std::make_shared<std::vector<Proj<F>>>();
-  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, *win));
-  tail = [plan, win, h_out]() { msm_host_phase<G>(*plan, *win, h_out); };
+  MsmWorkspace::Staging *stage = nullptr;
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage));
+  tail = [plan, stage, h_out]() {
+    std::vector<Proj<F>> win;
+    if (msm_collect<G>(*plan, stage, win) == 0) msm_host_phase<G>(*plan, win, h_out);
+  };
   return 0;
 }
 

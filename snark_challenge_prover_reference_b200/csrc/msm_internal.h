@@ -12,8 +12,22 @@ namespace b200 {
 struct MsmWorkspace {
   DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b, plan;
   DevBuf ntasks, task_off, task_bucket, task_len, task_len_sorted, partials;
+  cudaStream_t stream = nullptr;   // every kernel of an MSM that uses this workspace runs on this stream
+  // ring of pinned staging buffers + events for the asynchronous copy of the window sums to the host
+  struct Staging {
+    void *pinned = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t done = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;  // reduce-phase timing
+  } ring[4];
+  int ring_pos = 0;
+  Staging *next_staging(size_t bytes);
 };
+// Two workspaces / streams: b200_prove alternates them so that the latency-bound bucket reduction of one MSM overlaps
+// the throughput-bound accumulation of the next. msm_select_slot() picks the one used by subsequent calls on this
+// host thread (default 0).
 MsmWorkspace &msm_workspace();
+void msm_select_slot(int slot);
 
 struct MsmPlan {
   int c = 0, W = 0;
