@@ -13,7 +13,7 @@ namespace b200 {
 
 // One thread sums one task (a piece of <= T entries of one bucket's list) by mixed addition.
 template <class G>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
+__global__ void __launch_bounds__(128, G::F::kDegree == 2 ? 3 : 1) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
                                                              const uint32_t *__restrict__ entries,
                                                              const uint32_t *__restrict__ offsets,
                                                              const uint32_t *__restrict__ task_off,
@@ -28,16 +28,18 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const Affine<typena
   const uint32_t b = task_bucket[t];
   const uint32_t len = task_len_sorted[i];
   const uint32_t start = offsets[b] + (t - task_off[b]) * T;
-  Proj<F> acc;
-  proj_set_zero(acc);
+  XYZZ<F> acc;
+  xyzz_set_zero(acc);
   for (uint32_t k = 0; k < len; k++) {
     uint32_t e = entries[start + k];
     Affine<F> q = points[e >> 1];
     if (affine_is_zero(q)) continue;
     if (e & 1) F::neg(q.y, q.y);
-    proj_madd<G>(acc, q);
+    xyzz_madd<G>(acc, q);
   }
-  partials[t] = acc;
+  Proj<F> out;
+  xyzz_to_proj(out, acc);
+  partials[t] = out;
 }
 
 // bucket value = sum of the partial sums of its tasks (usually one: then this is a copy; none: O)
