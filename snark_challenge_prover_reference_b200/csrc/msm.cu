@@ -181,6 +181,7 @@ MsmWorkspace::Staging *MsmWorkspace::next_staging(size_t bytes) {
   ring_pos = (ring_pos + 1) & 3;
   if (!s.done) {
     cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    cudaEventCreate(&s.ta);
     cudaEventCreate(&s.t0);
     cudaEventCreate(&s.t1);
   }

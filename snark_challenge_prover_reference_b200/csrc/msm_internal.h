@@ -18,7 +18,7 @@ struct MsmWorkspace {
     void *pinned = nullptr;
     size_t bytes = 0;
     cudaEvent_t done = nullptr;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;  // reduce-phase timing
+    cudaEvent_t ta = nullptr, t0 = nullptr, t1 = nullptr;  // accumulate starts at ta, reduce spans t0..t1
   } ring[4];
   int ring_pos = 0;
   Staging *next_staging(size_t bytes);
