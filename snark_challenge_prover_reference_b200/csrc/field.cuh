@@ -233,10 +233,21 @@ struct alignas(16) Fp {
       x[i] = a[i];
       y[i] = b[i];
     }
+    // Default: interleaved CIOS (1152 IMAD.WIDE). -DB200_MUL_KARATSUBA selects the one-level Karatsuba product +
+    // half-width Montgomery reduction (1008 IMAD.WIDE, ~330 more IADD3 on the ALU pipe). Measured on B200 (round 1):
+    // 12 % fewer multiplier-pipe instructions but the longer carry chains and +16 registers drop the fmaheavy
+    // pipe from 94 % to 84 % busy at 8 warps/SM - no net gain, so it stays an option.
+#if defined(B200_MUL_KARATSUBA)
+    if (P::kTag == 'A')
+      fp_mulk_ptx_A(z, x, y);
+    else
+      fp_mulk_ptx_B(z, x, y);
+#else
     if (P::kTag == 'A')
       fp_mul_ptx_A(z, x, y);
     else
       fp_mul_ptx_B(z, x, y);
+#endif
 #pragma unroll
     for (int i = 0; i < kLimbs; i++) r[i] = z[i];
   }

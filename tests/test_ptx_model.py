@@ -22,11 +22,14 @@ def test_generated_ptx_matches_python_ints():
     rng = random.Random(42)
     for tag, p in M.PRIMES.items():
         mul, add, sub = G.gen_mul_body(p), G.gen_add_body(p), G.gen_sub_body(p)
+        mulk, _ = G.gen_mul_karatsuba_body(p)
         rinv = pow(M.R, -1, p)
-        cases = [(0, 0), (p - 1, p - 1), (1, p - 1), (p - 1, 1), (0, p - 1)]
+        cases = [(0, 0), (p - 1, p - 1), (1, p - 1), (p - 1, 1), (0, p - 1), ((1 << 384) - 1, (1 << 384) - 1),
+                 (p - 1, (1 << 384) - 1), (1 << 752, 1 << 752)]
         cases += [(rng.randrange(p), rng.randrange(p)) for _ in range(60)]
         for a, b in cases:
             assert _run(mul, a, b) == a * b * rinv % p
+            assert _run(mulk, a, b) == a * b * rinv % p
             assert _run(add, a, b) == (a + b) % p
             assert _run(sub, a, b) == (a - b) % p
 
@@ -37,5 +40,7 @@ def test_checked_in_header_is_current():
     text = open(path).read()
     for tag, p in M.PRIMES.items():
         assert G.emit_function("fp_mul_ptx_%s" % tag, G.gen_mul_body(p)) in text
+        kl, nk = G.gen_mul_karatsuba_body(p)
+        assert G.emit_function("fp_mulk_ptx_%s" % tag, kl, nk=nk) in text
         assert G.emit_function("fp_add_ptx_%s" % tag, G.gen_add_body(p)) in text
         assert G.emit_function("fp_sub_ptx_%s" % tag, G.gen_sub_body(p)) in text

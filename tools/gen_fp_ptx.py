@@ -203,7 +203,7 @@ def model_mul(lines, a, b):
 
 
 # --------------------------------------------------------------------------- C++ emission
-def emit_function(name, lines, sqr=False):
+def emit_function(name, lines, sqr=False, nk=0):
     """One asm statement; operands: %0..%23 = r (out), %24..%47 = a, %48..%71 = b."""
     sub = {}
     for j in range(N):
@@ -217,7 +217,8 @@ def emit_function(name, lines, sqr=False):
         args = [sub.get(x, x) for x in args]
         return f"{opc} {', '.join(args)};"
 
-    body = ["{", ".reg .u32 P<24>, Q<24>, t<24>, m, z, brw;", ".reg .pred pr;"] + [tr(l) for l in lines] + ["}"]
+    decl = ".reg .u32 P<24>, Q<24>, t<24>, m, z, brw;" if nk == 0 else ".reg .u32 k<%d>, m, brw;" % nk
+    body = ["{", decl, ".reg .pred pr;"] + [tr(l) for l in lines] + ["}"]
     s = []
     if sqr:
         s.append(f"__device__ __forceinline__ void {name}(uint32_t (&r)[24], const uint32_t (&a)[24]) {{")
@@ -244,6 +245,9 @@ def main():
     for tag, p in PRIMES.items():
         parts.append(emit_function(f"fp_mul_ptx_{tag}", gen_mul_body(p)))
         parts.append("")
+        kl, nk = gen_mul_karatsuba_body(p)
+        parts.append(emit_function(f"fp_mulk_ptx_{tag}", kl, nk=nk))
+        parts.append("")
         parts.append(emit_function(f"fp_add_ptx_{tag}", gen_add_body(p)))
         parts.append("")
         parts.append(emit_function(f"fp_sub_ptx_{tag}", gen_sub_body(p)))
@@ -251,6 +255,185 @@ def main():
     with open(out, "w") as f:
         f.write("\n".join(parts))
     print("wrote", os.path.normpath(out))
+
+
+
+
+# --------------------------------------------------------------------------- Karatsuba variant
+def gen_mul_karatsuba_body(p):
+    """a*b*2^-768 mod p with a one-level Karatsuba product (3 x 12x12 limbs = 432 wide MACs instead of 576) followed
+    by a Montgomery reduction that runs the CIOS row machinery on the LOW half of the product only and adds the high
+    half at the end:  T = a*b (48 limbs);  U = (T_lo + sum_i m_i p 2^(32 i)) / 2^768;  r = U + T_hi  (< 2p).
+    Inputs a0..a23, b0..b23; outputs r0..r23. All intermediate names are PTX virtual registers (the caller declares
+    them with .reg .u32 k<400>)."""
+    pl = to_limbs32(p)
+    inv = _inv32(p)
+    L = []
+    cnt = [0]
+
+    def new(n=1):
+        regs = [f"k{cnt[0] + i}" for i in range(n)]
+        cnt[0] += n
+        return regs if n > 1 else regs[0]
+
+    z = new()
+    L.append(f"mov.u32 {z}, 0;")
+    H = N // 2  # 12
+
+    def mul_half(u, v, hu=H):
+        """full product of two hu-limb numbers -> 2*hu limbs, even/odd accumulation (sppark-style wide multiply)."""
+        n2 = 2 * hu
+        E = [None] * (n2 + 2)  # value at limb position k (even-aligned pairs (0,1),(2,3),...)
+        O = [None] * (n2 + 2)  # odd-aligned pairs (1,2),(3,4),... : O[k] holds limb position k
+        for i in range(hu):
+            for par in (0, 1):  # par 0: u_even * v_i ; par 1: u_odd * v_i
+                idxs = list(range(par, hu, 2))
+                first = idxs[0] + i
+                arr = E if first % 2 == 0 else O
+                started = False
+                for j in idxs:
+                    pos = i + j
+                    lo_init = arr[pos] is None
+                    hi_init = arr[pos + 1] is None
+                    if lo_init:
+                        arr[pos] = new()
+                    if hi_init:
+                        arr[pos + 1] = new()
+                    # low word
+                    if lo_init and not started:
+                        L.append(f"mul.lo.u32 {arr[pos]}, {u[j]}, {v[i]};")
+                        carry_live = False
+                    elif lo_init:
+                        L.append(f"madc.lo.cc.u32 {arr[pos]}, {u[j]}, {v[i]}, {z};")
+                        carry_live = True
+                    elif not started:
+                        L.append(f"mad.lo.cc.u32 {arr[pos]}, {u[j]}, {v[i]}, {arr[pos]};")
+                        carry_live = True
+                    else:
+                        L.append(f"madc.lo.cc.u32 {arr[pos]}, {u[j]}, {v[i]}, {arr[pos]};")
+                        carry_live = True
+                    # high word
+                    addend = z if hi_init else arr[pos + 1]
+                    if carry_live:
+                        L.append(f"madc.hi.cc.u32 {arr[pos+1]}, {u[j]}, {v[i]}, {addend};")
+                    elif hi_init:
+                        L.append(f"mul.hi.u32 {arr[pos+1]}, {u[j]}, {v[i]};")
+                        # no carry defined yet: make the flag well defined for the next madc
+                        L.append(f"add.cc.u32 {arr[pos+1]}, {arr[pos+1]}, 0;")
+                    else:
+                        L.append(f"mad.hi.cc.u32 {arr[pos+1]}, {u[j]}, {v[i]}, {arr[pos+1]};")
+                    started = True
+                # carry out of the chain goes to the next word of the same array
+                top = i + idxs[-1] + 2
+                if top < n2 + 1:
+                    if arr[top] is None:
+                        arr[top] = new()
+                        L.append(f"addc.u32 {arr[top]}, {z}, 0;")
+                    else:
+                        L.append(f"addc.u32 {arr[top]}, {arr[top]}, 0;")
+        # merge: result = E + O
+        res = new(n2)
+        for k in range(n2):
+            ek = E[k] if E[k] is not None else z
+            ok = O[k] if O[k] is not None else z
+            opn = "add.cc.u32" if k == 0 else ("addc.cc.u32" if k < n2 - 1 else "addc.u32")
+            L.append(f"{opn} {res[k]}, {ek}, {ok};")
+        return res
+
+    aL, aH = [f"a{j}" for j in range(H)], [f"a{j}" for j in range(H, N)]
+    bL, bH = [f"b{j}" for j in range(H)], [f"b{j}" for j in range(H, N)]
+    # sa = aL + aH, sb = bL + bH (12 limbs + carry bit as a 0 / 0xffffffff mask)
+    sa, sb = new(H), new(H)
+    ca, cb = new(), new()
+    for (s, lo, hi, c) in ((sa, aL, aH, ca), (sb, bL, bH, cb)):
+        for k in range(H):
+            opn = "add.cc.u32" if k == 0 else "addc.cc.u32"
+            L.append(f"{opn} {s[k]}, {lo[k]}, {hi[k]};")
+        L.append(f"addc.u32 {c}, {z}, 0;")
+        L.append(f"sub.u32 {c}, {z}, {c};")  # 0 -> 0, 1 -> 0xffffffff
+    zm24 = mul_half(sa, sb)
+    # zm (25 limbs) = sa_lo*sb_lo + (ca ? sb_lo : 0)<<384 + (cb ? sa_lo : 0)<<384 + (ca&cb)<<768
+    zm = zm24 + [new()]
+    t = new(H)
+    for k in range(H):
+        L.append(f"and.b32 {t[k]}, {sb[k]}, {ca};")
+    for k in range(H):
+        opn = "add.cc.u32" if k == 0 else "addc.cc.u32"
+        L.append(f"{opn} {zm[H+k]}, {zm[H+k]}, {t[k]};")
+    L.append(f"addc.u32 {zm[2*H]}, {z}, 0;")
+    for k in range(H):
+        L.append(f"and.b32 {t[k]}, {sa[k]}, {cb};")
+    for k in range(H):
+        opn = "add.cc.u32" if k == 0 else "addc.cc.u32"
+        L.append(f"{opn} {zm[H+k]}, {zm[H+k]}, {t[k]};")
+    L.append(f"addc.u32 {zm[2*H]}, {zm[2*H]}, 0;")
+    cc = new()
+    L.append(f"and.b32 {cc}, {ca}, {cb};")
+    L.append(f"and.b32 {cc}, {cc}, 1;")
+    L.append(f"add.u32 {zm[2*H]}, {zm[2*H]}, {cc};")
+    z0 = mul_half(aL, bL)
+    z2 = mul_half(aH, bH)
+    # z1 = zm - z0 - z2 (25 limbs, non-negative)
+    for sub in (z0, z2):
+        for k in range(2 * H):
+            opn = "sub.cc.u32" if k == 0 else "subc.cc.u32"
+            L.append(f"{opn} {zm[k]}, {zm[k]}, {sub[k]};")
+        L.append(f"subc.u32 {zm[2*H]}, {zm[2*H]}, 0;")
+    # T = z0 + z1 << 384 + z2 << 768  (48 limbs): T[0..11] = z0[0..11]; T[12..35] = (z0[12..23] | z2[0..11]) + z1[0..23];
+    # T[36..47] = z2[12..23] + z1[24] + carry
+    T = z0[:H] + [None] * (3 * H)
+    mid = z0[H:] + z2[:H]
+    for k in range(2 * H):
+        opn = "add.cc.u32" if k == 0 else "addc.cc.u32"
+        L.append(f"{opn} {mid[k]}, {mid[k]}, {zm[k]};")
+        T[H + k] = mid[k]
+    for k in range(H):
+        src = zm[2 * H] if k == 0 else z
+        opn = "addc.cc.u32" if k < H - 1 else "addc.u32"
+        L.append(f"{opn} {z2[H+k]}, {z2[H+k]}, {src};")
+        T[3 * H + k] = z2[H + k]
+    # ---- Montgomery reduction of T_lo with the even/odd row machinery; window X (positions 0..23), Y (1..24)
+    X = list(T[:N])
+    Y = new(N)
+    for k in range(N):
+        L.append(f"mov.u32 {Y[k]}, 0;")
+    for i in range(N):
+        if i > 0:
+            Xo, Yo = X, Y
+            X = Yo
+            fresh = new(2)
+            L.append(f"mov.u32 {fresh[0]}, 0;")
+            L.append(f"mov.u32 {fresh[1]}, 0;")
+            Y = Xo[2:] + fresh  # shift down one 64-bit pair: pure renaming
+            L.append(f"add.cc.u32 {X[0]}, {X[0]}, {Xo[1]};")
+        L.append(f"mul.lo.u32 m, {X[0]}, {inv};")
+        for k in range(N // 2):
+            lo = ("mad.lo.cc.u32" if i == 0 else "madc.lo.cc.u32") if k == 0 else "madc.lo.cc.u32"
+            hi = "madc.hi.cc.u32" if k < N // 2 - 1 else "madc.hi.u32"
+            L.append(f"{lo} {Y[2*k]}, m, {pl[2*k+1]}, {Y[2*k]};")
+            L.append(f"{hi} {Y[2*k+1]}, m, {pl[2*k+1]}, {Y[2*k+1]};")
+        for k in range(N // 2):
+            lo = "mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32"
+            L.append(f"{lo} {X[2*k]}, m, {pl[2*k]}, {X[2*k]};")
+            L.append(f"madc.hi.cc.u32 {X[2*k+1]}, m, {pl[2*k]}, {X[2*k+1]};")
+        L.append(f"addc.u32 {Y[N-1]}, {Y[N-1]}, 0;")
+    # U = Y[j] + X[j+1]; r' = U + T_hi
+    for j in range(N):
+        opn = "add.cc.u32" if j == 0 else ("addc.cc.u32" if j < N - 1 else "addc.u32")
+        src = X[j + 1] if j + 1 < N else z
+        L.append(f"{opn} {Y[j]}, {Y[j]}, {src};")
+    for j in range(N):
+        opn = "add.cc.u32" if j == 0 else ("addc.cc.u32" if j < N - 1 else "addc.u32")
+        L.append(f"{opn} {Y[j]}, {Y[j]}, {T[N + j]};")
+    Tm = new(N)
+    for j in range(N):
+        opn = "sub.cc.u32" if j == 0 else "subc.cc.u32"
+        L.append(f"{opn} {Tm[j]}, {Y[j]}, {pl[j]};")
+    L.append(f"subc.u32 brw, {z}, {z};")
+    L.append("setp.ne.u32 pr, brw, 0;")
+    for j in range(N):
+        L.append(f"selp.u32 r{j}, {Y[j]}, {Tm[j]}, pr;")
+    return L, cnt[0]
 
 
 if __name__ == "__main__":
