@@ -231,8 +231,8 @@ class Domain:
         self.h, self.curve, self.m = h, curve, m
 
     def close(self):
-        if self.h and lib is not None:
-            lib().b200_domain_destroy(self.h)
+        if self.h and lib is not None and _lib is not None:
+            _lib.b200_domain_destroy(self.h)
         self.h = None
 
     __del__ = close
@@ -289,9 +289,9 @@ class Params:
         return lib().b200_params_m(self.h)
 
     def close(self):
-        if self.h:
-            lib().b200_params_destroy(self.h)
-            self.h = None
+        if self.h and lib is not None and _lib is not None:
+            _lib.b200_params_destroy(self.h)
+        self.h = None
 
     __del__ = close
 

@@ -428,9 +428,6 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   B200_CUDA_CHECK(cudaMemcpy(p->cb.p, in + (m + 1) * 96 + (d + 1) * 96, (d + 1) * 96, cudaMemcpyDefault));
   B200_CUDA_CHECK(cudaMemcpy(p->cc.p, in + (m + 1) * 96 + 2 * (d + 1) * 96, (d + 1) * 96, cudaMemcpyDefault));
   double t1 = now_ms();
-  B200_CHECK(b200_compute_h(p->dom, p->ca.p, p->cb.p, p->cc.p, p->h.p));
-  B200_CUDA_CHECK(cudaDeviceSynchronize());
-  double t2 = now_ms();
   const int curve = p->curve;
   const size_t g1a = affine_bytes(curve, 1), g2a = affine_bytes(curve, 2);
   const size_t g1p = proj_bytes(curve, 1), g2p = proj_bytes(curve, 2);
@@ -446,20 +443,28 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   };
   // The GPU half of each MSM runs here, back to back; the serial host halves (window combine, 753 doublings each)
   // run on worker threads while the next MSM occupies the GPU.
-  // B2 (G2) goes first: its host tail is the longest and then overlaps with the four G1 MSMs.
+  // Issue order: B2 (G2, the longest), A, B1, L - all driven by w - each on its own stream; then compute_H on the
+  // default stream (it overlaps the MSMs already in flight), then the H MSM, which is fenced on the default stream.
   const size_t outoff[5] = {0, g1p, 2 * g1p, 2 * g1p + g2p, 3 * g1p + g2p};
-  const int order[5] = {2, 0, 1, 3, 4};
+  const int order[5] = {2, 0, 1, 4, 3};
   std::vector<std::future<void>> tails;
   int rc_all = 0;
+  double t2 = t1;
   for (int jj = 0; jj < 5 && rc_all == 0; jj++) {
     const int j = order[jj];
+    if (j == 3) {  // H needs the witness map
+      double a = now_ms();
+      rc_all = b200_compute_h(p->dom, p->ca.p, p->cb.p, p->cc.p, p->h.p);
+      t2 = t1 + (now_ms() - a);
+      if (rc_all) break;
+    }
     unsigned char *o = partials + outoff[j];
     const Job &J = jobs[j];
     size_t one = J.n / (size_t)world;
     size_t lo = (size_t)rank * one, hi = (rank == world - 1) ? J.n : lo + one;
     double a = now_ms();
     std::function<void()> tail;
-    msm_select_slot(jj & 1);  // alternate the two workspaces/streams: reduce(k) overlaps accumulate(k+1)
+    msm_select_slot(jj);
     if (use_precompute())
       rc_all = msm_table_dispatch_deferred(curve, J.group, J.scalars + lo * 96, p->pre.table[j].p, hi - lo,
                                            p->pre.plan[j], o, tail);
@@ -531,7 +536,8 @@ int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_
   std::vector<unsigned char> part(partial_size(p->curve));
   B200_CHECK(prove_partials(p, h_input, input_bytes, 0, 1, part.data(), timings));
   double t1 = now_ms();
-  const unsigned char *r = (const unsigned char *)h_input + input_bytes - 96;
+  unsigned char r[96];  // the input image may live in host or device memory
+  B200_CUDA_CHECK(cudaMemcpy(r, (const unsigned char *)h_input + input_bytes - 96, 96, cudaMemcpyDefault));
   B200_CHECK(b200_prove_combine(p->curve, part.data(), 1, r, h_out, out_bytes));
   if (timings) {
     timings->tail_ms += now_ms() - t1;

@@ -30,8 +30,8 @@ struct Mnt4G2 {
   typedef Fp2<PrimeB, 13> F;
   typedef PrimeA ScalarPrime;
   B200_HD static void mul_by_a(F &r, const F &x) {
-    F::B::template mul_small<26>(r.c0, x.c0);
-    F::B::template mul_small<26>(r.c1, x.c1);
+    F::B::template mul_small_ni<26>(r.c0, x.c0);
+    F::B::template mul_small_ni<26>(r.c1, x.c1);
   }
 };
 struct Mnt6G1 {
@@ -44,9 +44,9 @@ struct Mnt6G2 {
   typedef PrimeB ScalarPrime;
   B200_HD static void mul_by_a(F &r, const F &x) {
     typename F::B t0, t1, t2;
-    F::B::template mul_small<121>(t0, x.c1);
-    F::B::template mul_small<121>(t1, x.c2);
-    F::B::template mul_small<11>(t2, x.c0);
+    F::B::template mul_small_ni<121>(t0, x.c1);
+    F::B::template mul_small_ni<121>(t1, x.c2);
+    F::B::template mul_small_ni<11>(t2, x.c0);
     r.c0 = t0;
     r.c1 = t1;
     r.c2 = t2;

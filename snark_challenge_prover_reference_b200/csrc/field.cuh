@@ -261,6 +261,14 @@ struct alignas(16) Fp {
   }
   B200_HD static B200_INLINE void sqr(Fp &r, const Fp &a) { mul(r, a, a); }
 
+  // out-of-line add / sub / small-constant multiply for the tower fields (keeps Fq2/Fq3 code a short list of calls:
+  // with the ~100-instruction carry chains inlined ~40 times the G2 kernels no longer fit the instruction cache)
+  B200_HD static B200_NOINLINE void add_ni(Fp &r, const Fp &a, const Fp &b) { add(r, a, b); }
+  B200_HD static B200_NOINLINE void sub_ni(Fp &r, const Fp &a, const Fp &b) { sub(r, a, b); }
+  B200_HD static B200_NOINLINE void neg_ni(Fp &r, const Fp &a) { neg(r, a); }
+  template <unsigned K>
+  B200_HD static B200_NOINLINE void mul_small_ni(Fp &r, const Fp &a) { mul_small<K>(r, a); }
+
   // r = k*a for a small compile-time constant k (double-and-add; used for curve a, non-residues 13 / 11)
   template <unsigned K>
   B200_HD static B200_INLINE void mul_small(Fp &r, const Fp &a) {
@@ -330,44 +338,44 @@ struct alignas(16) Fp2 {
   B200_HD static void set_one(Fp2 &r) { B::set_one(r.c0); B::set_zero(r.c1); }
   B200_HD static bool is_zero(const Fp2 &a) { return B::is_zero(a.c0) && B::is_zero(a.c1); }
   B200_HD static bool eq(const Fp2 &a, const Fp2 &b) { return B::eq(a.c0, b.c0) && B::eq(a.c1, b.c1); }
-  B200_HD static B200_NOINLINE void add(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::add(r.c0, a.c0, b.c0); B::add(r.c1, a.c1, b.c1); }
-  B200_HD static B200_NOINLINE void sub(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::sub(r.c0, a.c0, b.c0); B::sub(r.c1, a.c1, b.c1); }
-  B200_HD static B200_NOINLINE void dbl(Fp2 &r, const Fp2 &a) { B::dbl(r.c0, a.c0); B::dbl(r.c1, a.c1); }
-  B200_HD static B200_NOINLINE void neg(Fp2 &r, const Fp2 &a) { B::neg(r.c0, a.c0); B::neg(r.c1, a.c1); }
+  B200_HD static B200_NOINLINE void add(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::add_ni(r.c0, a.c0, b.c0); B::add_ni(r.c1, a.c1, b.c1); }
+  B200_HD static B200_NOINLINE void sub(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::sub_ni(r.c0, a.c0, b.c0); B::sub_ni(r.c1, a.c1, b.c1); }
+  B200_HD static B200_NOINLINE void dbl(Fp2 &r, const Fp2 &a) { B::add_ni(r.c0, a.c0, a.c0); B::add_ni(r.c1, a.c1, a.c1); }
+  B200_HD static B200_NOINLINE void neg(Fp2 &r, const Fp2 &a) { B::neg_ni(r.c0, a.c0); B::neg_ni(r.c1, a.c1); }
   B200_HD static B200_NOINLINE void mul(Fp2 &r, const Fp2 &a, const Fp2 &b) {  // Karatsuba, 3 base multiplications
     B aA, bB, s, t;
     B::mul(aA, a.c0, b.c0);
     B::mul(bB, a.c1, b.c1);
-    B::add(s, a.c0, a.c1);
-    B::add(t, b.c0, b.c1);
+    B::add_ni(s, a.c0, a.c1);
+    B::add_ni(t, b.c0, b.c1);
     B::mul(s, s, t);
-    B::sub(s, s, aA);
-    B::sub(r.c1, s, bB);
-    B::template mul_small<NR>(t, bB);
-    B::add(r.c0, aA, t);
+    B::sub_ni(s, s, aA);
+    B::sub_ni(r.c1, s, bB);
+    B::template mul_small_ni<NR>(t, bB);
+    B::add_ni(r.c0, aA, t);
   }
   B200_HD static B200_NOINLINE void sqr(Fp2 &r, const Fp2 &a) {  // complex squaring, 2 base multiplications
     B ab, s, t;
     B::mul(ab, a.c0, a.c1);
-    B::add(s, a.c0, a.c1);
-    B::template mul_small<NR>(t, a.c1);
-    B::add(t, t, a.c0);
+    B::add_ni(s, a.c0, a.c1);
+    B::template mul_small_ni<NR>(t, a.c1);
+    B::add_ni(t, t, a.c0);
     B::mul(s, s, t);
-    B::sub(s, s, ab);
-    B::template mul_small<NR>(t, ab);
-    B::sub(r.c0, s, t);
-    B::dbl(r.c1, ab);
+    B::sub_ni(s, s, ab);
+    B::template mul_small_ni<NR>(t, ab);
+    B::sub_ni(r.c0, s, t);
+    B::add_ni(r.c1, ab, ab);
   }
   B200_HD static void inv(Fp2 &r, const Fp2 &a) {  // fp2.tcc:128-142
     B t0, t1, t2;
     B::sqr(t0, a.c0);
     B::sqr(t1, a.c1);
-    B::template mul_small<NR>(t1, t1);
-    B::sub(t2, t0, t1);
+    B::template mul_small_ni<NR>(t1, t1);
+    B::sub_ni(t2, t0, t1);
     B::inv(t2, t2);
     B::mul(r.c0, a.c0, t2);
     B::mul(t0, a.c1, t2);
-    B::neg(r.c1, t0);
+    B::neg_ni(r.c1, t0);
   }
 };
 
@@ -387,64 +395,64 @@ struct alignas(16) Fp3 {
     return B::eq(a.c0, b.c0) && B::eq(a.c1, b.c1) && B::eq(a.c2, b.c2);
   }
   B200_HD static B200_NOINLINE void add(Fp3 &r, const Fp3 &a, const Fp3 &b) {
-    B::add(r.c0, a.c0, b.c0); B::add(r.c1, a.c1, b.c1); B::add(r.c2, a.c2, b.c2);
+    B::add_ni(r.c0, a.c0, b.c0); B::add_ni(r.c1, a.c1, b.c1); B::add_ni(r.c2, a.c2, b.c2);
   }
   B200_HD static B200_NOINLINE void sub(Fp3 &r, const Fp3 &a, const Fp3 &b) {
-    B::sub(r.c0, a.c0, b.c0); B::sub(r.c1, a.c1, b.c1); B::sub(r.c2, a.c2, b.c2);
+    B::sub_ni(r.c0, a.c0, b.c0); B::sub_ni(r.c1, a.c1, b.c1); B::sub_ni(r.c2, a.c2, b.c2);
   }
-  B200_HD static B200_NOINLINE void dbl(Fp3 &r, const Fp3 &a) { B::dbl(r.c0, a.c0); B::dbl(r.c1, a.c1); B::dbl(r.c2, a.c2); }
-  B200_HD static B200_NOINLINE void neg(Fp3 &r, const Fp3 &a) { B::neg(r.c0, a.c0); B::neg(r.c1, a.c1); B::neg(r.c2, a.c2); }
+  B200_HD static B200_NOINLINE void dbl(Fp3 &r, const Fp3 &a) { B::add_ni(r.c0, a.c0, a.c0); B::add_ni(r.c1, a.c1, a.c1); B::add_ni(r.c2, a.c2, a.c2); }
+  B200_HD static B200_NOINLINE void neg(Fp3 &r, const Fp3 &a) { B::neg_ni(r.c0, a.c0); B::neg_ni(r.c1, a.c1); B::neg_ni(r.c2, a.c2); }
   B200_HD static B200_NOINLINE void mul(Fp3 &r, const Fp3 &a, const Fp3 &b) {  // Karatsuba, 6 base multiplications
     B aA, bB, cC, s, t, u;
     B::mul(aA, a.c0, b.c0);
     B::mul(bB, a.c1, b.c1);
     B::mul(cC, a.c2, b.c2);
     // c0 = aA + nr*((b+c)(B+C) - bB - cC)
-    B::add(s, a.c1, a.c2);
-    B::add(t, b.c1, b.c2);
+    B::add_ni(s, a.c1, a.c2);
+    B::add_ni(t, b.c1, b.c2);
     B::mul(s, s, t);
-    B::sub(s, s, bB);
-    B::sub(s, s, cC);
-    B::template mul_small<NR>(s, s);
+    B::sub_ni(s, s, bB);
+    B::sub_ni(s, s, cC);
+    B::template mul_small_ni<NR>(s, s);
     // c1 = (a+b)(A+B) - aA - bB + nr*cC
-    B::add(t, a.c0, a.c1);
-    B::add(u, b.c0, b.c1);
+    B::add_ni(t, a.c0, a.c1);
+    B::add_ni(u, b.c0, b.c1);
     B::mul(t, t, u);
-    B::sub(t, t, aA);
-    B::sub(t, t, bB);
-    B::template mul_small<NR>(u, cC);
-    B::add(t, t, u);
+    B::sub_ni(t, t, aA);
+    B::sub_ni(t, t, bB);
+    B::template mul_small_ni<NR>(u, cC);
+    B::add_ni(t, t, u);
     // c2 = (a+c)(A+C) - aA + bB - cC
     B u2, v2;
-    B::add(u2, a.c0, a.c2);
-    B::add(v2, b.c0, b.c2);
+    B::add_ni(u2, a.c0, a.c2);
+    B::add_ni(v2, b.c0, b.c2);
     B::mul(u2, u2, v2);
-    B::sub(u2, u2, aA);
-    B::add(u2, u2, bB);
-    B::sub(r.c2, u2, cC);
-    B::add(r.c0, aA, s);
+    B::sub_ni(u2, u2, aA);
+    B::add_ni(u2, u2, bB);
+    B::sub_ni(r.c2, u2, cC);
+    B::add_ni(r.c0, aA, s);
     r.c1 = t;
   }
   B200_HD static B200_NOINLINE void sqr(Fp3 &r, const Fp3 &a) {  // CH-SQR2: 3 squarings + 2 multiplications
     B s0, s1, s2, s3, s4, t;
     B::sqr(s0, a.c0);
     B::mul(s1, a.c0, a.c1);
-    B::dbl(s1, s1);
-    B::sub(t, a.c0, a.c1);
-    B::add(t, t, a.c2);
+    B::add_ni(s1, s1, s1);
+    B::sub_ni(t, a.c0, a.c1);
+    B::add_ni(t, t, a.c2);
     B::sqr(s2, t);
     B::mul(s3, a.c1, a.c2);
-    B::dbl(s3, s3);
+    B::add_ni(s3, s3, s3);
     B::sqr(s4, a.c2);
     // c0 = s0 + nr*s3 ; c1 = s1 + nr*s4 ; c2 = s1 + s2 + s3 - s0 - s4
-    B::template mul_small<NR>(t, s3);
-    B::add(r.c0, s0, t);
-    B::template mul_small<NR>(t, s4);
-    B::add(r.c1, s1, t);
-    B::add(t, s1, s2);
-    B::add(t, t, s3);
-    B::sub(t, t, s0);
-    B::sub(r.c2, t, s4);
+    B::template mul_small_ni<NR>(t, s3);
+    B::add_ni(r.c0, s0, t);
+    B::template mul_small_ni<NR>(t, s4);
+    B::add_ni(r.c1, s1, t);
+    B::add_ni(t, s1, s2);
+    B::add_ni(t, t, s3);
+    B::sub_ni(t, t, s0);
+    B::sub_ni(r.c2, t, s4);
   }
   B200_HD static void inv(Fp3 &r, const Fp3 &a) {  // fp3.tcc:125-143
     B t0, t1, t2, t3, t4, t5, c0, c1, c2, t6, u;
@@ -454,17 +462,17 @@ struct alignas(16) Fp3 {
     B::mul(t3, a.c0, a.c1);
     B::mul(t4, a.c0, a.c2);
     B::mul(t5, a.c1, a.c2);
-    B::template mul_small<NR>(u, t5);
-    B::sub(c0, t0, u);
-    B::template mul_small<NR>(u, t2);
-    B::sub(c1, u, t3);
-    B::sub(c2, t1, t4);
+    B::template mul_small_ni<NR>(u, t5);
+    B::sub_ni(c0, t0, u);
+    B::template mul_small_ni<NR>(u, t2);
+    B::sub_ni(c1, u, t3);
+    B::sub_ni(c2, t1, t4);
     B::mul(t6, a.c0, c0);
     B::mul(t0, a.c2, c1);
     B::mul(t1, a.c1, c2);
-    B::add(t0, t0, t1);
-    B::template mul_small<NR>(t0, t0);
-    B::add(t6, t6, t0);
+    B::add_ni(t0, t0, t1);
+    B::template mul_small_ni<NR>(t0, t0);
+    B::add_ni(t6, t6, t0);
     B::inv(t6, t6);
     B::mul(r.c0, t6, c0);
     B::mul(r.c1, t6, c1);

@@ -166,9 +166,9 @@ int msm_make_plan(size_t n, bool merged, MsmPlan &plan) {
 }
 
 static thread_local int g_slot = 0;
-void msm_select_slot(int slot) { g_slot = slot & 1; }
+void msm_select_slot(int slot) { g_slot = ((slot % kMsmSlots) + kMsmSlots) % kMsmSlots; }
 static MsmWorkspace *workspace_slots() {
-  static thread_local MsmWorkspace ws[2];
+  static thread_local MsmWorkspace ws[kMsmSlots];
   return ws;
 }
 MsmWorkspace &msm_workspace() {
@@ -197,7 +197,7 @@ MsmWorkspace::Staging *MsmWorkspace::next_staging(size_t bytes) {
   return &s;
 }
 void msm_release_workspace() {
-  for (int s = 0; s < 2; s++) {
+  for (int s = 0; s < kMsmSlots; s++) {
   MsmWorkspace &ws = workspace_slots()[s];
   DevBuf *all[] = {&ws.digits, &ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.order,
                    &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan,

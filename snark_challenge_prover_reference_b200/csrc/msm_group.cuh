@@ -152,14 +152,16 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   if (K > nb) K = nb;
   uint32_t per = nb / K;
   B200_CHECK(ws.red_a.reserve((size_t)W * per * sizeof(Proj<F>)));
-  B200_CHECK(ws.red_b.reserve((size_t)W * ((per + 7) / 8) * sizeof(Proj<F>) + 16));
+  B200_CHECK(ws.red_b.reserve((size_t)W * ((per + 1) / 2) * sizeof(Proj<F>) + 16));
   msm_reduce_kernel<G><<<grid_for((size_t)W * per, 128), 128, 0, st>>>(ws.buckets.as<Proj<F>>(), W, nb, K,
                                                                        ws.red_a.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
   Proj<F> *cur = ws.red_a.as<Proj<F>>(), *nxt = ws.red_b.as<Proj<F>>();
   while (per > 1) {
-    uint32_t R = 8;
+    // radix of the tree sum: 8 while a level still fills the GPU, 2 below that (every level then costs one
+    // point addition of latency instead of eight)
+    uint32_t R = ((size_t)W * per > 262144) ? 8 : 2;
     uint32_t per_out = (per + R - 1) / R;
     msm_sum_kernel<G><<<grid_for((size_t)W * per_out, 128), 128, 0, st>>>(cur, W, per, R, nxt);
     B200_CUDA_CHECK(cudaGetLastError());

@@ -23,9 +23,10 @@ struct MsmWorkspace {
   int ring_pos = 0;
   Staging *next_staging(size_t bytes);
 };
-// Two workspaces / streams: b200_prove alternates them so that the latency-bound bucket reduction of one MSM overlaps
-// the throughput-bound accumulation of the next. msm_select_slot() picks the one used by subsequent calls on this
-// host thread (default 0).
+// One workspace + stream per MSM of a proof: b200_prove issues its five MSMs on five streams so that the latency-bound
+// phases of one (counting sort, bucket reduction) overlap the throughput-bound accumulation of the others.
+// msm_select_slot() picks the one used by subsequent calls on this host thread (default 0).
+constexpr int kMsmSlots = 5;
 MsmWorkspace &msm_workspace();
 void msm_select_slot(int slot);
 
