@@ -197,22 +197,62 @@ struct alignas(16) Fp {
 #endif
 
   // ---------------------------------------------------------------- dispatch
+#if defined(__CUDACC__)
+  // out-of-line device add / sub (operands by pointer, like the multiply): callers then hold no limbs in registers
+  // across field operations, which keeps the big point-arithmetic kernels at ~128 registers (16 warps/SM).
+  static __device__ __noinline__ void add_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) {
+      x[i] = a[i];
+      y[i] = b[i];
+    }
+    if (P::kTag == 'A')
+      fp_add_ptx_A(z, x, y);
+    else
+      fp_add_ptx_B(z, x, y);
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) r[i] = z[i];
+  }
+  static __device__ __noinline__ void sub_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) {
+      x[i] = a[i];
+      y[i] = b[i];
+    }
+    if (P::kTag == 'A')
+      fp_sub_ptx_A(z, x, y);
+    else
+      fp_sub_ptx_B(z, x, y);
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) r[i] = z[i];
+  }
+#endif
   B200_HD static B200_INLINE void add(Fp &r, const Fp &a, const Fp &b) {
 #if defined(__CUDA_ARCH__)
+#if defined(B200_FP_ADD_INLINE)
     if (P::kTag == 'A')
       fp_add_ptx_A(r.l, a.l, b.l);
     else
       fp_add_ptx_B(r.l, a.l, b.l);
+#else
+    add_dev(r.l, a.l, b.l);
+#endif
 #else
     host_add(r, a, b);
 #endif
   }
   B200_HD static B200_INLINE void sub(Fp &r, const Fp &a, const Fp &b) {
 #if defined(__CUDA_ARCH__)
+#if defined(B200_FP_ADD_INLINE)
     if (P::kTag == 'A')
       fp_sub_ptx_A(r.l, a.l, b.l);
     else
       fp_sub_ptx_B(r.l, a.l, b.l);
+#else
+    sub_dev(r.l, a.l, b.l);
+#endif
 #else
     host_sub(r, a, b);
 #endif
