@@ -105,6 +105,10 @@ int b200_params_destroy(b200_params *p);
 int b200_params_precompute(b200_params *p, int rank, int world);
 double b200_params_precompute_ms(const b200_params *p);
 int b200_set_precompute(int on);
+/* sum_i scalars[i] * query[i] over one whole query of the key (which: 0 A, 1 B1, 2 B2 (G2), 3 L, 4 H); uses the
+ * pre-shifted base table when precomputation is enabled and n is the query's length. Result: projective, host memory.
+ * B::multiexp_G1 / B::multiexp_G2 on vectors obtained from B::params_* bind to this. */
+int b200_params_msm(b200_params *p, int which, const void *d_scalars, size_t n, void *h_out_proj);
 size_t b200_params_d(const b200_params *p);
 size_t b200_params_m(const b200_params *p);
 const void *b200_params_query(const b200_params *p, int which); /* 0 A, 1 B1, 2 B2, 3 L, 4 H (device pointers) */

@@ -98,6 +98,7 @@ _SIGNATURES = {
     "b200_params_precompute": (_i, [_vp, _i, _i]),
     "b200_params_precompute_ms": (ctypes.c_double, [_vp]),
     "b200_set_precompute": (_i, [_i]),
+    "b200_params_msm": (_i, [_vp, _i, _vp, _sz, _vp]),
     "b200_params_d": (_sz, [_vp]),
     "b200_params_m": (_sz, [_vp]),
     "b200_params_query": (_vp, [_vp, _i]),
@@ -299,6 +300,12 @@ class Params:
         """build the pre-shifted base tables for this rank's slice (key-only preprocessing); returns seconds"""
         check(lib().b200_params_precompute(self.h, rank, world))
         return lib().b200_params_precompute_ms(self.h) / 1e3
+
+    def msm(self, which, d_scalars, n):
+        """MSM over one whole query (0 A, 1 B1, 2 B2, 3 L, 4 H) -> projective point bytes"""
+        out = ctypes.create_string_buffer(proj_bytes(self.curve, 2 if which == 2 else 1))
+        check(lib().b200_params_msm(self.h, which, _ptr(d_scalars), n, ctypes.addressof(out)))
+        return out.raw
 
     def prove(self, input_image, timings=False):
         """One whole proof from a HOST input image; returns the proof bytes (A | B | C, wire format)."""

@@ -413,6 +413,27 @@ int b200_set_precompute(int on) {
   return 0;
 }
 
+// MSM of one whole query of a resident key: uses the pre-shifted base table when one exists for (rank 0, world 1)
+// and n is the query's length, else the table-free path. This is what B::multiexp_G1/G2 call, so the reference's own
+// driver gets the table speed-up too.
+int b200_params_msm(b200_params *p, int which, const void *d_scalars, size_t n, void *h_out) {
+  B200_CHECK(require_device());
+  if (which < 0 || which > 4) return set_error(-1, "bad query index %d", which);
+  const size_t ns[5] = {p->m + 1, p->m + 1, p->m + 1, p->m - 1, p->d};  // A, B1, B2, L, H
+  const int job_of_query[5] = {0, 1, 2, 4, 3};
+  const int group = which == 2 ? 2 : 1;
+  if (use_precompute() && n == ns[which]) {
+    B200_CHECK(b200_params_precompute(p, 0, 1));
+    const int j = job_of_query[which];
+    std::function<void()> tail;
+    msm_select_slot(0);
+    B200_CHECK(msm_table_dispatch_deferred(p->curve, group, d_scalars, p->pre.table[j].p, n, p->pre.plan[j], h_out, tail));
+    tail();
+    return 0;
+  }
+  return msm_dispatch(p->curve, group, d_scalars, p->q[which], n, h_out);
+}
+
 // Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
 // multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
 static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, int rank, int world,

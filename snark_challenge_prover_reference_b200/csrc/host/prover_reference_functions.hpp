@@ -30,10 +30,12 @@ public:
   struct vector_G1 {
     std::shared_ptr<b200_host::params_box> owner;
     const void *data;  // device pointer to affine wire-format points
+    int query;         // which query of the key this is (0 A, 1 B1, 3 L, 4 H)
   };
   struct vector_G2 {
     std::shared_ptr<b200_host::params_box> owner;
     const void *data;
+    int query;         // 2 = B2
   };
   struct field {
     unsigned char bytes[96];  // Fr, Montgomery form
