@@ -98,6 +98,13 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t *__restr
   entries[pos] = (e << 1) | (d < 0 ? 1u : 0u);
 }
 
+// ---- folding of task sums for skewed inputs (a bucket with more than kFoldWidth task sums) ----------------------
+__global__ void msm_fold_counts_kernel(const uint32_t *__restrict__ cnt_in, uint32_t nbuckets, uint32_t width,
+                                       uint32_t *__restrict__ cnt_out) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nbuckets) cnt_out[b] = (cnt_in[b] + width - 1) / width;
+}
+
 // ---- tasks: a bucket's entry list is cut into pieces of at most T entries; one thread sums one piece -------------
 __global__ void msm_ntasks_kernel(const uint32_t *__restrict__ counts, uint32_t nbuckets, uint32_t T,
                                   uint32_t *__restrict__ ntasks) {
@@ -201,7 +208,8 @@ void msm_release_workspace() {
   MsmWorkspace &ws = workspace_slots()[s];
   DevBuf *all[] = {&ws.digits, &ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.order,
                    &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan,
-                   &ws.ntasks, &ws.task_off, &ws.task_bucket, &ws.task_len, &ws.task_len_sorted, &ws.partials};
+                   &ws.ntasks, &ws.task_off, &ws.task_bucket, &ws.task_len, &ws.task_len_sorted, &ws.partials,
+                   &ws.scalar_out, &ws.fold_cnt, &ws.fold_off, &ws.fold_bucket, &ws.fold_partials};
   for (DevBuf *b : all) b->release();
   }
 }
@@ -229,6 +237,7 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   B200_CHECK(ws.ntasks.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.task_off.reserve(nbuckets * sizeof(uint32_t)));
   B200_CHECK(ws.plan.reserve(256 * sizeof(uint32_t)));
+  B200_CHECK(ws.scalar_out.reserve(64));
   B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.windows.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   Timer tm(st);
 
@@ -278,12 +287,22 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
     tb = ws.cub_tmp.bytes;
     B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.p, tb, ws.ntasks.as<uint32_t>(),
                                                   ws.task_off.as<uint32_t>(), (int)nbuckets, st));
-    uint32_t last[2];
+    uint32_t last[3];
+    {
+      size_t need = 0;
+      cub::DeviceReduce::Max(nullptr, need, ws.ntasks.as<uint32_t>(), ws.scalar_out.as<uint32_t>(), (int)nbuckets, st);
+      B200_CHECK(ws.cub_tmp.reserve(need));
+      tb = ws.cub_tmp.bytes;
+      B200_CUDA_CHECK(cub::DeviceReduce::Max(ws.cub_tmp.p, tb, ws.ntasks.as<uint32_t>(), ws.scalar_out.as<uint32_t>(),
+                                             (int)nbuckets, st));
+    }
     B200_CUDA_CHECK(cudaMemcpyAsync(&last[0], ws.task_off.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(&last[1], ws.ntasks.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(&last[2], ws.scalar_out.as<uint32_t>(), 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
     const size_t ntasks = (size_t)last[0] + last[1];
     plan.ntasks = ntasks;
+    plan.max_tasks_per_bucket = last[2];
     const size_t cap = ntasks ? ntasks : 1;
     B200_CHECK(ws.task_bucket.reserve(cap * sizeof(uint32_t)));
     B200_CHECK(ws.task_len.reserve(cap * sizeof(uint32_t)));
@@ -310,6 +329,28 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
     }
   }
   g_msm_phase_ms[1] = tm.stop();
+  return 0;
+}
+
+// bookkeeping of one fold level (group-independent): cnt_out = ceil(cnt_in / width), off_out = exclusive scan,
+// returns the total number of groups (synchronises the stream; only reached for skewed scalar distributions)
+int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, uint32_t *cnt_out, uint32_t *off_out,
+                   size_t &total_out) {
+  MsmWorkspace &ws = msm_workspace();
+  cudaStream_t st = ws.stream;
+  msm_fold_counts_kernel<<<grid_for(nbuckets, 256), 256, 0, st>>>(cnt_in, nbuckets, width, cnt_out);
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, cnt_out, off_out, (int)nbuckets, st);
+  B200_CHECK(ws.cub_tmp.reserve(need));
+  size_t tb = ws.cub_tmp.bytes;
+  B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.p, tb, cnt_out, off_out, (int)nbuckets, st));
+  uint32_t last[2];
+  B200_CUDA_CHECK(cudaMemcpyAsync(&last[0], off_out + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
+  B200_CUDA_CHECK(cudaMemcpyAsync(&last[1], cnt_out + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
+  B200_CUDA_CHECK(cudaStreamSynchronize(st));
+  total_out = (size_t)last[0] + last[1];
   return 0;
 }
 

@@ -42,6 +42,34 @@ __global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : (G::F::kDegree =
   partials[t] = out;
 }
 
+// One fold level: the sums of one bucket are added in groups of `width`; thread i looks at sum i of the input list and
+// works only if it is the first of its group. Keeps the per-bucket combine short when millions of scalars are equal.
+template <class G>
+__global__ void __launch_bounds__(128) msm_fold_kernel(const Proj<typename G::F> *__restrict__ in,
+                                                       const uint32_t *__restrict__ bucket_in,
+                                                       const uint32_t *__restrict__ off_in,
+                                                       const uint32_t *__restrict__ cnt_in, uint32_t total_in,
+                                                       uint32_t width, const uint32_t *__restrict__ off_out,
+                                                       Proj<typename G::F> *__restrict__ out,
+                                                       uint32_t *__restrict__ bucket_out) {
+  typedef typename G::F F;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_in) return;
+  const uint32_t b = bucket_in[i];
+  const uint32_t s = i - off_in[b];
+  if (s % width != 0) return;
+  const uint32_t cnt = cnt_in[b];
+  const uint32_t len = cnt - s < width ? cnt - s : width;
+  Proj<F> acc = in[i];
+  for (uint32_t k = 1; k < len; k++) {
+    Proj<F> cur = in[i + k];
+    proj_add<G>(acc, acc, cur);
+  }
+  const uint32_t o = off_out[b] + s / width;
+  out[o] = acc;
+  bucket_out[o] = b;
+}
+
 // bucket value = sum of the partial sums of its tasks (usually one: then this is a copy; none: O)
 template <class G>
 __global__ void __launch_bounds__(128) msm_combine_kernel(const Proj<typename G::F> *__restrict__ partials,
@@ -138,8 +166,41 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
     B200_CUDA_CHECK(cudaGetLastError());
     note_launch();
   }
-  msm_combine_kernel<G><<<grid_for(nbuckets, 128), 128, 0, st>>>(ws.partials.as<Proj<F>>(), ws.task_off.as<uint32_t>(),
-                                                                 ws.ntasks.as<uint32_t>(), (uint32_t)nbuckets,
+  // skewed scalars: fold the task sums of heavy buckets in parallel until no bucket has more than kFoldWidth of them
+  const Proj<F> *sums = ws.partials.as<Proj<F>>();
+  const uint32_t *sum_bucket = ws.task_bucket.as<uint32_t>(), *sum_off = ws.task_off.as<uint32_t>(),
+                 *sum_cnt = ws.ntasks.as<uint32_t>();
+  {
+    size_t total = plan.ntasks;
+    uint32_t maxc = plan.max_tasks_per_bucket;
+    int half = 0;
+    if (maxc > kFoldWidth) {
+      const size_t cap = total / kFoldWidth + nbuckets + 1;  // upper bound on the first level's output
+      B200_CHECK(ws.fold_cnt.reserve(2 * nbuckets * sizeof(uint32_t)));
+      B200_CHECK(ws.fold_off.reserve(2 * nbuckets * sizeof(uint32_t)));
+      B200_CHECK(ws.fold_bucket.reserve(2 * cap * sizeof(uint32_t)));
+      B200_CHECK(ws.fold_partials.reserve(2 * cap * sizeof(Proj<F>)));
+      while (maxc > kFoldWidth) {
+        uint32_t *cnt_out = ws.fold_cnt.as<uint32_t>() + half * nbuckets, *off_out = ws.fold_off.as<uint32_t>() + half * nbuckets;
+        uint32_t *bucket_out = ws.fold_bucket.as<uint32_t>() + half * cap;
+        Proj<F> *out = ws.fold_partials.as<Proj<F>>() + half * cap;
+        size_t total_out = 0;
+        B200_CHECK(msm_fold_level(sum_cnt, (uint32_t)nbuckets, kFoldWidth, cnt_out, off_out, total_out));
+        msm_fold_kernel<G><<<grid_for(total, 128), 128, 0, st>>>(sums, sum_bucket, sum_off, sum_cnt, (uint32_t)total,
+                                                                 kFoldWidth, off_out, out, bucket_out);
+        B200_CUDA_CHECK(cudaGetLastError());
+        note_launch();
+        sums = out;
+        sum_bucket = bucket_out;
+        sum_off = off_out;
+        sum_cnt = cnt_out;
+        total = total_out;
+        maxc = (maxc + kFoldWidth - 1) / kFoldWidth;
+        half ^= 1;
+      }
+    }
+  }
+  msm_combine_kernel<G><<<grid_for(nbuckets, 128), 128, 0, st>>>(sums, sum_off, sum_cnt, (uint32_t)nbuckets,
                                                                  ws.buckets.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();

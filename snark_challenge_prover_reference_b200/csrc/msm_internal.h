@@ -12,6 +12,7 @@ namespace b200 {
 struct MsmWorkspace {
   DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b, plan;
   DevBuf ntasks, task_off, task_bucket, task_len, task_len_sorted, partials;
+  DevBuf scalar_out, fold_cnt, fold_off, fold_bucket, fold_partials;  // fold_* hold two ping-pong halves
   cudaStream_t stream = nullptr;   // every kernel of an MSM that uses this workspace runs on this stream
   // ring of pinned staging buffers + events for the asynchronous copy of the window sums to the host
   struct Staging {
@@ -38,6 +39,7 @@ struct MsmPlan {
   std::vector<uint32_t> windows;  // start_bit | width << 16
   uint32_t task_len = 0;        // T: entries per accumulation task (set by msm_prepare)
   size_t ntasks = 0;            // number of tasks of this call (set by msm_prepare)
+  uint32_t max_tasks_per_bucket = 0;  // largest number of task sums any bucket has (set by msm_prepare)
 };
 
 extern double g_msm_phase_ms[5];         // last call: digits, sort, accumulate, reduce, host tail
@@ -48,6 +50,9 @@ extern double g_msm_phase_total[2][5];   // accumulated, [0] G1 calls, [1] G2 ca
 // plan.W == 0 on entry: choose a per-window plan for n. Otherwise the caller's plan (e.g. the one a table was built for).
 int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan);
 int msm_make_plan(size_t n, bool merged, MsmPlan &plan);
+constexpr uint32_t kFoldWidth = 32;  // a bucket with more task sums than this is folded in parallel first
+int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, uint32_t *cnt_out, uint32_t *off_out,
+                   size_t &total_out);
 // pre-shifted base tables (merged buckets), see msm_group.cuh
 int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n, MsmPlan &plan, DevBuf &table);
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,

@@ -223,6 +223,26 @@ def test_msm_degenerate_scalars(b200, oracle, dev):
         assert b200.g_to_affine(curve, 1, b200.msm(curve, 1, pts, pts, 0)) == bytes(ab)
 
 
+def test_msm_skewed_scalars_fold_path(b200, oracle, dev):
+    """All scalars equal: every window puts all n points into ONE bucket, i.e. thousands of task sums per bucket, which
+    exercises the parallel folding of task sums (two levels at n = 2^14). msm(1,...,1) is checked against the oracle
+    (which adds the n points directly, multiexp.tcc:468-479) and msm(s,...,s) against s * msm(1,...,1)."""
+    import torch
+    for curve, group, n in ((0, 1, 1 << 14), (1, 2, 1 << 12)):
+        c = util.curve_obj(curve)
+        ab = b200.affine_bytes(curve, group)
+        pts = torch.empty(n * ab, dtype=torch.uint8, device=dev)
+        b200.check(b200.lib().b200_gen_points(curve, group, pts.data_ptr(), n, 11))
+        one = util.fe_bytes(M.to_mont(1, c.r))
+        s_val = random.Random(99 + curve).randrange(2, c.r)
+        s = util.fe_bytes(M.to_mont(s_val, c.r))
+        sum_ones = b200.msm(curve, group, b200.to_device(one * n), pts, n)
+        sum_s = b200.msm(curve, group, b200.to_device(s * n), pts, n)
+        assert b200.g_to_affine(curve, group, sum_ones) == util.orc_msm_affine(oracle, curve, group, one * n,
+                                                                              b200.from_device(pts), n)
+        assert b200.g_to_affine(curve, group, sum_s) == b200.g_to_affine(curve, group, b200.g_scale(curve, group, s, sum_ones))
+
+
 def test_msm_linearity_large(b200, dev):
     """n = 2^15 (beyond what the oracle does in seconds): msm(s,P) + msm(t,P) == msm(s+t,P), and the same sum from
     two different window widths."""
