@@ -306,44 +306,89 @@ def b200_arm(args):
     h2d = sum(h.numel() for h in host_inputs)
     d2h = sum(pbytes)
 
-    # roofline of the dominant kernel: msm_accumulate_kernel<G1> (4 of the 5 MSMs of each proof); IMAD-pipe bound.
-    # launches per step: 4 (MNT4753 G1) + 4 (MNT6753 G1); algorithmic MAC32 per launch = 620928 * points of that launch
-    n4, n6 = (1 << args.log2_mnt4) // world, (1 << args.log2_mnt6) // world
-    g1_launches = 8 * args.steps
-    g1_mac = args.steps * 4 * MAC32_PER_POINT["g1"] * (n4 + n6)
-    acc_ms_g1 = phases["g1"]["accumulate"]
+    # Roofline of the dominant kernel, msm_accumulate_kernel<G1> (4 of the 5 MSMs of each proof). Inside a proof the
+    # five MSMs run concurrently on five streams, so per-kernel event times overlap; the kernel is therefore timed
+    # here in isolation (same key, same scalars, one MSM at a time through b200_params_msm, CUDA events around the
+    # accumulation launches on the MSM's stream). Bound: the INT32 multiplier (IMAD.WIDE / fmaheavy) pipe.
     imad = pkg.imad_peak()
     peak = max(imad["mad_wide_mac32_per_s"], imad["carry_chain_mac32_per_s"])
-    achieved = g1_mac / (acc_ms_g1 / 1e3) if acc_ms_g1 > 0 else 0.0
-    roofline = {"bound": "imad (INT32 multiply pipe; neither HBM nor tensor bound, SURVEY.md 8d)",
+    iso = {"g1": [], "g2": []}
+    plans = {}
+    if world == 1:
+        for i, (curve, k) in enumerate(shapes):
+            m = 1 << k
+            d_w = dev_inputs[i]
+            for which, n in ((0, m + 1), (1, m + 1), (3, m - 1), (4, m - 1), (2, m + 1)):
+                keys[i].msm(which, d_w, n)  # warm
+                keys[i].msm(which, d_w, n)
+                ph = pkg.msm_phase_ms()
+                iso["g2" if which == 2 else "g1"].append((curve, n, ph["accumulate"], ph["reduce"]))
+                plans[(curve, which == 2)] = pkg.msm_last_plan()
+    else:
+        # sharded run: per-kernel event times of rank 0 inside the timed region (the five MSMs of a proof overlap on
+        # five streams, so these over-state the kernel time; the isolated measurement is the N=1 line's)
+        for i, (curve, k) in enumerate(shapes):
+            n = (1 << k) // world
+            for _ in range(4):
+                iso["g1"].append((curve, n, phases["g1"]["accumulate"] / (8 * args.steps), phases["g1"]["reduce"] / (8 * args.steps)))
+            iso["g2"].append((curve, n, phases["g2"]["accumulate"] / (2 * args.steps), phases["g2"]["reduce"] / (2 * args.steps)))
+    g1_mac = sum(MAC32_PER_POINT["g1"] * n for _, n, _, _ in iso["g1"])
+    acc_ms_g1 = sum(t for _, _, t, _ in iso["g1"])
+    achieved = g1_mac / (acc_ms_g1 / 1e3)
+    g1_big = [t for c, _, t, _ in iso["g1"] if c == 0]
+    roofline = {"bound": "imad (INT32 multiplier pipe; neither HBM nor tensor bound, SURVEY.md 8d)",
                 "kernel": "msm_accumulate_kernel<G1>", "achieved": achieved / 1e12, "peak": peak / 1e12,
-                "unit": "TMAC32/s", "frac": achieved / peak if peak else None, "traffic": None,
-                "launches": g1_launches, "avg_launch_ms": acc_ms_g1 / g1_launches,
+                "unit": "TMAC32/s", "frac": achieved / peak if peak else None,
+                "frac_issued": (sum(plans[(c, False)]["windows"] * 10 * 1152 * n for c, n, _, _ in iso["g1"]) / (acc_ms_g1 / 1e3) / peak
+                                if plans else None),
+                "issued_note": "IMAD.WIDE actually issued per point = windows x 10 multiplications x 1152, over the same time",
+                "windows": {("MNT4753" if c == 0 else "MNT6753") + ("_g2" if g2 else "_g1"): v for (c, g2), v in plans.items()},
+                "traffic": 7.3e9 + 6.3e9, "traffic_note": "dram read+write bytes of one 2^20-point launch, ncu --set full (profiles/)",
+                "launches": len(iso["g1"]), "avg_launch_ms": statistics.mean(g1_big) if g1_big else None,
                 "peak_source": "measured live by b200_imad_peak (IMAD.WIDE carry-chain microbenchmark on all SMs)",
-                "share_of_step": acc_ms_g1 / ms_dev,
-                "note": "achieved uses SURVEY 8d's algorithmic 620928 MAC32/point (48 windows); with the pre-shifted "
-                        "base tables the kernel really runs 36-42 windows, so frac > 1 means fewer windows, not a "
-                        "faster pipe: ncu shows the fmaheavy pipe ~94% busy (profiles/)"}
-    g2_mac = args.steps * (MAC32_PER_POINT["g2_fq2"] * n4 + MAC32_PER_POINT["g2_fq3"] * n6)
-    acc_ms_g2 = phases["g2"]["accumulate"]
-    roofline_g2 = {"kernel": "msm_accumulate_kernel<G2>", "achieved": g2_mac / (acc_ms_g2 / 1e3) / 1e12 if acc_ms_g2 else None,
-                   "peak": peak / 1e12, "unit": "TMAC32/s",
-                   "frac": (g2_mac / (acc_ms_g2 / 1e3)) / peak if acc_ms_g2 and peak else None,
-                   "share_of_step": acc_ms_g2 / ms_dev}
+                "timing": "kernel timed alone with CUDA events on its stream (inside a proof 5 MSMs overlap)",
+                "note": "achieved uses SURVEY 8d's algorithmic 620928 MAC32/point (48 windows x 11 mul x 1176); with the "
+                        "pre-shifted base tables and XYZZ additions the kernel issues 36-42 windows x 10 mul, so frac > 1 "
+                        "means less work per point, not a faster pipe: ncu shows the fmaheavy pipe 84-94 % busy (profiles/)"}
+    g2_mac = sum((MAC32_PER_POINT["g2_fq2"] if c == 0 else MAC32_PER_POINT["g2_fq3"]) * n for c, n, _, _ in iso["g2"])
+    acc_ms_g2 = sum(t for _, _, t, _ in iso["g2"])
+    roofline_g2 = {"kernel": "msm_accumulate_kernel<G2>", "achieved": g2_mac / (acc_ms_g2 / 1e3) / 1e12,
+                   "peak": peak / 1e12, "unit": "TMAC32/s", "frac": (g2_mac / (acc_ms_g2 / 1e3)) / peak if peak else None,
+                   "launch_ms": [round(t, 2) for _, _, t, _ in iso["g2"]]}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # compute_H timed alone (inside a proof it is enqueued asynchronously under the MSMs): CUDA events on the default
+    # stream, which is the stream ntt.cu launches on
+    ch_ms = 0.0
+    for i, (curve, k) in enumerate(shapes):
+        m = 1 << k
+        dom = pkg.Domain(curve, m)
+        bufs = [dev_inputs[i][:m].clone() for _ in range(3)]
+        out = torch.empty((m + 1) * FE, dtype=torch.uint8, device=dev)
+        dom.compute_h(*bufs, out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            dom.compute_h(*bufs, out)
+        e1.record()
+        torch.cuda.synchronize()
+        ch_ms += e0.elapsed_time(e1)
+        dom.close()
     # compute_H: 7 NTTs of m elements + pointwise ops; algorithmic HBM bytes 7*192*m + 4*96*m
-    ch_ms = sum(t["compute_h_ms"] for t in tms_dev if True)
     ch_bytes = args.steps * sum((7 * 192 + 4 * 96) * (1 << k) for _, k in shapes)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline_ntt = {"bound": "hbm", "kernel": "ntt_pass_kernel (compute_H: 7 NTT + pointwise)",
                     "achieved": ch_bytes / (ch_ms / 1e3) / 1e9 if ch_ms else None, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (ch_bytes / (ch_ms / 1e3) / 1e9) / hbm_peak if ch_ms else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
-                    "note": "753-bit butterflies are IMAD-bound (588 MAC32 per 96 B element-stage), see DESIGN.md"}
+                    "ms_per_step": ch_ms / args.steps,
+                    "imad_frac": (args.steps * sum((7 * 588 * k + 4 * 1176) * (1 << k) for _, k in shapes) / (ch_ms / 1e3)) / peak if ch_ms else None,
+                    "note": "753-bit butterflies are IMAD-bound (588 MAC32 per 96 B element-stage, 61 MAC32/byte): imad_frac is "
+                            "the fraction of the measured IMAD.WIDE peak, the binding roofline; see DESIGN.md 4.3"}
 
     per_curve = {}
     for i, (curve, k) in enumerate(shapes):
@@ -368,8 +413,11 @@ def b200_arm(args):
             "roofline_ntt": roofline_ntt, "proof_latency_s": {n: v["latency_s"] for n, v in per_curve.items()},
             "per_curve": per_curve,
             "msm_points_per_s": {
-                "g1": 4 * args.steps * (n4 + n6) * world / (sum(phases["g1"].values()) / 1e3) if sum(phases["g1"].values()) else None,
-                "g2": args.steps * (n4 + n6) * world / (sum(phases["g2"].values()) / 1e3) if sum(phases["g2"].values()) else None},
+                "note": "one MSM alone on one GPU, accumulate + reduce phases, points of this rank's slice",
+                "g1_2^%d" % args.log2_mnt4: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g1"] if c == 0), default=None),
+                "g2_fq2_2^%d" % args.log2_mnt4: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g2"] if c == 0), default=None),
+                "g1_2^%d" % args.log2_mnt6: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g1"] if c == 1), default=None),
+                "g2_fq3_2^%d" % args.log2_mnt6: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g2"] if c == 1), default=None)},
             "msm_phase_ms_per_step": {g: {k: v / args.steps for k, v in ph.items()} for g, ph in phases.items()},
             "imad_peak": imad}
     if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REF_DIR, "main")):

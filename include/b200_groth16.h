@@ -146,6 +146,8 @@ unsigned long long b200_launch_count(void);
 /* accumulated MSM phase times (ms) since the last reset: out10 = G1 {digits, sort, accumulate, reduce, host tail},
  * then the same five for G2 calls */
 int b200_msm_phase_totals(double *out10, int reset);
+/* window width c, number of windows W and task length T of the most recently prepared MSM */
+int b200_msm_last_plan(int *out3);
 /* time of the last MSM phases (ms): 0 digits, 1 sort, 2 accumulate, 3 reduce, 4 host tail */
 int b200_msm_last_phase_ms(double *out5);
 

@@ -81,6 +81,7 @@ _SIGNATURES = {
     "b200_msm_g2": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_msm_set_window": (_i, [_i]),
     "b200_msm_last_phase_ms": (_i, [ctypes.POINTER(ctypes.c_double)]),
+    "b200_msm_last_plan": (_i, [ctypes.POINTER(ctypes.c_int)]),
     "b200_msm_phase_totals": (_i, [ctypes.POINTER(ctypes.c_double), _i]),
     "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200_g1_add": (_i, [_i, _vp, _vp, _vp]),
@@ -208,6 +209,12 @@ def msm_phase_ms():
     arr = (ctypes.c_double * 5)()
     check(lib().b200_msm_last_phase_ms(arr))
     return dict(zip(("digits", "sort", "accumulate", "reduce", "host_tail"), list(arr)))
+
+
+def msm_last_plan():
+    arr = (ctypes.c_int * 3)()
+    check(lib().b200_msm_last_plan(arr))
+    return {"c": arr[0], "windows": arr[1], "task_len": arr[2]}
 
 
 def msm_phase_totals(reset=False):

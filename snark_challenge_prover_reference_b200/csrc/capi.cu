@@ -258,6 +258,10 @@ int b200_msm_phase_totals(double *out5, int reset) {
   msm_phase_totals(out5, reset);
   return 0;
 }
+int b200_msm_last_plan(int *out3) {
+  msm_last_plan(out3);
+  return 0;
+}
 int b200_msm_last_phase_ms(double *out5) {
   msm_last_phase_ms(out5);
   return 0;
@@ -444,10 +448,9 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   if (world < 1 || rank < 0 || rank >= world) return set_error(-1, "bad rank/world %d/%d", rank, world);
   const char *in = (const char *)h_input;
   double t0 = now_ms();
+  // w first (it drives four of the five MSMs); ca/cb/cc follow asynchronously on the default stream right before
+  // compute_H, under the MSMs that are already running (truly asynchronous when the image is in pinned memory)
   B200_CUDA_CHECK(cudaMemcpy(p->w.p, in, (m + 1) * 96, cudaMemcpyDefault));
-  B200_CUDA_CHECK(cudaMemcpy(p->ca.p, in + (m + 1) * 96, (d + 1) * 96, cudaMemcpyDefault));
-  B200_CUDA_CHECK(cudaMemcpy(p->cb.p, in + (m + 1) * 96 + (d + 1) * 96, (d + 1) * 96, cudaMemcpyDefault));
-  B200_CUDA_CHECK(cudaMemcpy(p->cc.p, in + (m + 1) * 96 + 2 * (d + 1) * 96, (d + 1) * 96, cudaMemcpyDefault));
   double t1 = now_ms();
   const int curve = p->curve;
   const size_t g1a = affine_bytes(curve, 1), g2a = affine_bytes(curve, 2);
@@ -475,6 +478,10 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     const int j = order[jj];
     if (j == 3) {  // H needs the witness map
       double a = now_ms();
+      const char *abc = in + (m + 1) * 96;
+      B200_CUDA_CHECK(cudaMemcpyAsync(p->ca.p, abc, (d + 1) * 96, cudaMemcpyDefault, 0));
+      B200_CUDA_CHECK(cudaMemcpyAsync(p->cb.p, abc + (d + 1) * 96, (d + 1) * 96, cudaMemcpyDefault, 0));
+      B200_CUDA_CHECK(cudaMemcpyAsync(p->cc.p, abc + 2 * (d + 1) * 96, (d + 1) * 96, cudaMemcpyDefault, 0));
       rc_all = b200_compute_h(p->dom, p->ca.p, p->cb.p, p->cc.p, p->h.p);
       t2 = t1 + (now_ms() - a);
       if (rc_all) break;
@@ -486,9 +493,12 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     double a = now_ms();
     std::function<void()> tail;
     msm_select_slot(jj);
+    // A and B1 (slots 1, 2) run over the same scalars and window plan as B2 (slot 0): they reuse its digits, counting
+    // sort and task list
+    const int share = (jj == 1 || jj == 2) && p->pre.plan[j].c == p->pre.plan[2].c ? 0 : -1;
     if (use_precompute())
       rc_all = msm_table_dispatch_deferred(curve, J.group, J.scalars + lo * 96, p->pre.table[j].p, hi - lo,
-                                           p->pre.plan[j], o, tail);
+                                           p->pre.plan[j], o, tail, share);
     else
       rc_all = msm_dispatch_deferred(curve, J.group, J.scalars + lo * 96, J.points + lo * J.stride, hi - lo, o, tail);
     if (rc_all == 0) tails.push_back(std::async(std::launch::async, tail));

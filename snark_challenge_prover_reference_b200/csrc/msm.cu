@@ -36,6 +36,10 @@ void msm_phase_totals(double *out10, int reset) {
       if (reset) g_msm_phase_total[g][i] = 0;
     }
 }
+static int g_last_plan[3] = {0, 0, 0};
+void msm_last_plan(int *out3) {
+  for (int i = 0; i < 3; i++) out3[i] = g_last_plan[i];
+}
 void msm_last_phase_ms(double *out5) {
   for (int i = 0; i < 5; i++) out5[i] = g_msm_phase_ms[i];
 }
@@ -178,11 +182,16 @@ static MsmWorkspace *workspace_slots() {
   static thread_local MsmWorkspace ws[kMsmSlots];
   return ws;
 }
-MsmWorkspace &msm_workspace() {
-  MsmWorkspace &ws = workspace_slots()[g_slot];
-  if (!ws.stream) cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking);
+MsmWorkspace &msm_workspace_slot(int slot) {
+  MsmWorkspace &ws = workspace_slots()[slot];
+  if (!ws.stream) {
+    cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ws.prep_done, cudaEventDisableTiming);
+    ws.prepared = new MsmPlan();
+  }
   return ws;
 }
+MsmWorkspace &msm_workspace() { return msm_workspace_slot(g_slot); }
 MsmWorkspace::Staging *MsmWorkspace::next_staging(size_t bytes) {
   Staging &s = ring[ring_pos];
   ring_pos = (ring_pos + 1) & 3;
@@ -329,6 +338,11 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
     }
   }
   g_msm_phase_ms[1] = tm.stop();
+  *ws.prepared = plan;
+  g_last_plan[0] = plan.c;
+  g_last_plan[1] = plan.W;
+  g_last_plan[2] = (int)plan.task_len;
+  B200_CUDA_CHECK(cudaEventRecord(ws.prep_done, st));
   return 0;
 }
 
@@ -375,7 +389,7 @@ int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const voi
 
 #define B200_DECL_G(name)                                                                                   \
   int msm_precompute_##name(const void *, size_t, MsmPlan &, DevBuf &);                                     \
-  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, std::function<void()> &);
+  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, std::function<void()> &, int);
 B200_DECL_G(mnt4g1) B200_DECL_G(mnt4g2) B200_DECL_G(mnt6g1) B200_DECL_G(mnt6g2)
 #undef B200_DECL_G
 
@@ -387,11 +401,11 @@ int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
-                                const MsmPlan &plan, void *h_out, std::function<void()> &tail) {
-  if (curve == 0 && group == 1) return msm_run_table_deferred_mnt4g1(d_scalars, d_table, n, plan, h_out, tail);
-  if (curve == 0 && group == 2) return msm_run_table_deferred_mnt4g2(d_scalars, d_table, n, plan, h_out, tail);
-  if (curve == 1 && group == 1) return msm_run_table_deferred_mnt6g1(d_scalars, d_table, n, plan, h_out, tail);
-  if (curve == 1 && group == 2) return msm_run_table_deferred_mnt6g2(d_scalars, d_table, n, plan, h_out, tail);
+                                const MsmPlan &plan, void *h_out, std::function<void()> &tail, int share_slot) {
+  if (curve == 0 && group == 1) return msm_run_table_deferred_mnt4g1(d_scalars, d_table, n, plan, h_out, tail, share_slot);
+  if (curve == 0 && group == 2) return msm_run_table_deferred_mnt4g2(d_scalars, d_table, n, plan, h_out, tail, share_slot);
+  if (curve == 1 && group == 1) return msm_run_table_deferred_mnt6g1(d_scalars, d_table, n, plan, h_out, tail, share_slot);
+  if (curve == 1 && group == 2) return msm_run_table_deferred_mnt6g2(d_scalars, d_table, n, plan, h_out, tail, share_slot);
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 

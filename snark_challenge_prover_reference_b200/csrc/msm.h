@@ -10,6 +10,8 @@ int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const voi
                           std::function<void()> &tail);
 void msm_set_window(int c);
 void msm_last_phase_ms(double *out5);
+// window width c, number of windows W and task length T of the most recently prepared MSM
+void msm_last_plan(int *out3);
 // accumulated phase times since the last reset: out10 = G1 {digits, sort, accumulate, reduce, host}, then G2
 void msm_phase_totals(double *out10, int reset);
 void msm_release_workspace();

@@ -140,13 +140,24 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 
 // GPU half of one MSM. Returns after the accumulation has finished and the (latency-bound) bucket reduction has been
 // ENQUEUED on the workspace's stream; the window sums arrive asynchronously in `stage` (wait on stage->done).
+// share_slot >= 0: reuse the scalar-side preparation (digits, sort, tasks) that workspace `share_slot` made for the SAME
+// scalars and window plan instead of repeating it (this MSM then only waits for that slot's prep_done event).
 template <class G>
-int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan, MsmWorkspace::Staging *&stage) {
+int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan, MsmWorkspace::Staging *&stage,
+                  int share_slot = -1) {
   typedef typename G::F F;
   typedef typename G::ScalarPrime FrP;
-  B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan));
   MsmWorkspace &ws = msm_workspace();
   cudaStream_t st = ws.stream;
+  MsmWorkspace *prep_ws = &ws;
+  if (share_slot >= 0) {
+    prep_ws = &msm_workspace_slot(share_slot);
+    plan = *prep_ws->prepared;
+    B200_CUDA_CHECK(cudaStreamWaitEvent(st, prep_ws->prep_done, 0));
+  } else {
+    B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan));
+  }
+  MsmWorkspace &pw = *prep_ws;  // owner of entries / offsets / task arrays
   const int W = plan.merged ? 1 : plan.W;  // number of independent bucket sets to reduce
   const uint32_t nb = plan.nb;
   const size_t nbuckets = plan.nbuckets;
@@ -160,16 +171,16 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   B200_CHECK(ws.partials.reserve((plan.ntasks ? plan.ntasks : 1) * sizeof(Proj<F>)));
   if (plan.ntasks) {
     msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128, 0, st>>>(
-        (const Affine<F> *)d_points, ws.entries.as<uint32_t>(), ws.offsets.as<uint32_t>(), ws.task_off.as<uint32_t>(),
-        ws.task_bucket.as<uint32_t>(), ws.task_len_sorted.as<uint32_t>(), ws.order.as<uint32_t>(),
+        (const Affine<F> *)d_points, pw.entries.as<uint32_t>(), pw.offsets.as<uint32_t>(), pw.task_off.as<uint32_t>(),
+        pw.task_bucket.as<uint32_t>(), pw.task_len_sorted.as<uint32_t>(), pw.order.as<uint32_t>(),
         (uint32_t)plan.ntasks, plan.task_len, ws.partials.as<Proj<F>>());
     B200_CUDA_CHECK(cudaGetLastError());
     note_launch();
   }
   // skewed scalars: fold the task sums of heavy buckets in parallel until no bucket has more than kFoldWidth of them
   const Proj<F> *sums = ws.partials.as<Proj<F>>();
-  const uint32_t *sum_bucket = ws.task_bucket.as<uint32_t>(), *sum_off = ws.task_off.as<uint32_t>(),
-                 *sum_cnt = ws.ntasks.as<uint32_t>();
+  const uint32_t *sum_bucket = pw.task_bucket.as<uint32_t>(), *sum_off = pw.task_off.as<uint32_t>(),
+                 *sum_cnt = pw.ntasks.as<uint32_t>();
   {
     size_t total = plan.ntasks;
     uint32_t maxc = plan.max_tasks_per_bucket;
@@ -390,7 +401,7 @@ int msm_precompute(const void *d_points, size_t n, MsmPlan &plan, DevBuf &table)
 // MSM over a table built by msm_precompute (plan must be the table's plan).
 template <class G>
 int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n, const MsmPlan &table_plan, void *h_out,
-                           std::function<void()> &tail) {
+                           std::function<void()> &tail, int share_slot) {
   typedef typename G::F F;
   if (n == 0) {
     Proj<F> zero;
@@ -401,7 +412,7 @@ int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n,
   }
   auto plan = std::make_shared<MsmPlan>(table_plan);
   MsmWorkspace::Staging *stage = nullptr;
-  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage));
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage, share_slot));
   tail = [plan, stage, h_out]() {
     std::vector<Proj<F>> win;
     if (msm_collect<G>(*plan, stage, win) == 0) msm_host_phase<G>(*plan, win, h_out);

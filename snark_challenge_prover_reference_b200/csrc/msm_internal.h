@@ -9,6 +9,7 @@
 
 namespace b200 {
 
+struct MsmPlan;
 struct MsmWorkspace {
   DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b, plan;
   DevBuf ntasks, task_off, task_bucket, task_len, task_len_sorted, partials;
@@ -23,12 +24,17 @@ struct MsmWorkspace {
   } ring[4];
   int ring_pos = 0;
   Staging *next_staging(size_t bytes);
+  // sharing of the scalar-side preparation (digits, counting sort, tasks) between MSMs over the SAME scalars and the
+  // same window plan (A, B1 and B2 of a proof all use w): the producer records prep_done, consumers wait on it
+  cudaEvent_t prep_done = nullptr;
+  MsmPlan *prepared = nullptr;  // plan as completed by msm_prepare (ntasks, task_len, ...)
 };
 // One workspace + stream per MSM of a proof: b200_prove issues its five MSMs on five streams so that the latency-bound
 // phases of one (counting sort, bucket reduction) overlap the throughput-bound accumulation of the others.
 // msm_select_slot() picks the one used by subsequent calls on this host thread (default 0).
 constexpr int kMsmSlots = 5;
 MsmWorkspace &msm_workspace();
+MsmWorkspace &msm_workspace_slot(int slot);
 void msm_select_slot(int slot);
 
 struct MsmPlan {
@@ -56,6 +62,6 @@ int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, ui
 // pre-shifted base tables (merged buckets), see msm_group.cuh
 int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n, MsmPlan &plan, DevBuf &table);
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
-                                const MsmPlan &plan, void *h_out, std::function<void()> &tail);
+                                const MsmPlan &plan, void *h_out, std::function<void()> &tail, int share_slot = -1);
 
 }  // namespace b200
