@@ -343,7 +343,10 @@ def b200_arm(args):
                                 if plans else None),
                 "issued_note": "IMAD.WIDE actually issued per point = windows x 10 multiplications x 1152, over the same time",
                 "windows": {("MNT4753" if c == 0 else "MNT6753") + ("_g2" if g2 else "_g1"): v for (c, g2), v in plans.items()},
-                "traffic": 7.3e9 + 6.3e9, "traffic_note": "dram read+write bytes of one 2^20-point launch, ncu --set full (profiles/)",
+                "traffic": 15.06e9 + 15.63e9,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-point launch, ncu --set full "
+                                "(profiles/prof_accumulate_g1_tables_r01_raw.csv); algorithmic: 36 windows x 2^20 x 192 B = 7.2 GB "
+                                "of table reads, the rest is per-thread stack traffic; 0.6 TB/s, far below the HBM roofline",
                 "launches": len(iso["g1"]), "avg_launch_ms": statistics.mean(g1_big) if g1_big else None,
                 "peak_source": "measured live by b200_imad_peak (IMAD.WIDE carry-chain microbenchmark on all SMs)",
                 "timing": "kernel timed alone with CUDA events on its stream (inside a proof 5 MSMs overlap)",
