@@ -63,7 +63,7 @@ PKG="$HERE/../snark_challenge_prover_reference_b200"
 if [ -f "$PKG/libb200groth16.so" ]; then
   if [ ! -x "$OUT/piecewise_b200" ] || [ "$PKG/libb200groth16.so" -nt "$OUT/piecewise_b200" ]; then
     g++ -std=c++14 -O2 -w -I"$PKG/csrc/host" -I"$HERE/../include" -I"$OUT/stub" \
-       -x c++ "$R/cuda_prover_piecewise.cu" -x c++ "$PKG/csrc/host/prover_reference_functions.cpp" -x none \
+       -x c++ "$R/cuda_prover_piecewise.cu" -x c++ "$PKG/csrc/host/b200_bundle.cpp" -x none \
        -L"$PKG" -lb200groth16 -Wl,-rpath,"$PKG" -Wl,-rpath,'$ORIGIN/../../snark_challenge_prover_reference_b200' \
        -o "$OUT/piecewise_b200"
   fi

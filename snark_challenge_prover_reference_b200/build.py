@@ -73,8 +73,8 @@ def build_driver():
     bindir = os.path.join(HERE, "bin")
     os.makedirs(bindir, exist_ok=True)
     exe = os.path.join(bindir, "cuda_prover_piecewise")
-    srcs = [os.path.join(host, "prover_reference_functions.cpp"), os.path.join(host, "cuda_prover_piecewise.cpp")]
-    deps = srcs + [os.path.join(host, "prover_reference_functions.hpp"), LIB]
+    srcs = [os.path.join(host, "b200_bundle.cpp"), os.path.join(host, "prover_main.cpp")]
+    deps = srcs + [os.path.join(host, "b200_bundle.hpp"), os.path.join(host, "prover_reference_functions.hpp"), LIB]
     if _newer(exe, deps):
         return exe
     cmd = ["/usr/bin/g++", "-std=c++14", "-O2", "-I", host, "-I", os.path.join(ROOT, "include")] + srcs + [

@@ -4,7 +4,7 @@
 //
 // Error behaviour: the reference returns void / pointers and never reports failure (unchecked fopen/fread,
 // SURVEY.md 8b). Here any failing C-ABI call or short file aborts with a message on stderr - there is no CPU fallback.
-#include "prover_reference_functions.hpp"
+#include "b200_bundle.hpp"
 
 #include <cstdio>
 #include <cstdlib>

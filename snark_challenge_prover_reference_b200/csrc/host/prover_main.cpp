@@ -8,7 +8,7 @@
 #include <cstdio>
 #include <string>
 
-#include "prover_reference_functions.hpp"
+#include "b200_bundle.hpp"
 
 typedef std::chrono::steady_clock clk;
 static double since_ms(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }

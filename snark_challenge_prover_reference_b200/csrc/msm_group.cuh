@@ -13,7 +13,7 @@ namespace b200 {
 
 // One thread sums one task (a piece of <= T entries of one bucket's list) by mixed addition.
 template <class G>
-__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : (G::F::kDegree == 2 ? 3 : 1)) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
+__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : (G::F::kDegree == 2 ? 4 : 1)) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
                                                              const uint32_t *__restrict__ entries,
                                                              const uint32_t *__restrict__ offsets,
                                                              const uint32_t *__restrict__ task_off,
