@@ -40,6 +40,7 @@ struct DevBuf {
     cudaError_t e = cudaMalloc(&p, n);
     if (e != cudaSuccess) {
       p = nullptr;
+      cudaGetLastError();  // clear the (non-sticky) error so that other users of the context are not affected
       return set_error(-100 - (int)e, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
     }
     bytes = n;

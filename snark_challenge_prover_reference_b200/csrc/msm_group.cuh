@@ -322,7 +322,7 @@ int msm_run_deferred(const void *d_scalars, const void *d_points, size_t n, void
   B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, *plan, stage));
   tail = [plan, stage, h_out]() {
     std::vector<Proj<F>> win;
-    if (msm_collect<G>(*plan, stage, win) == 0) msm_host_phase<G>(*plan, win, h_out);
+    if (msm_collect<G>(*plan, stage, win) == 0) g_msm_phase_ms[4] = msm_host_phase<G>(*plan, win, h_out);
   };
   return 0;
 }
@@ -415,7 +415,7 @@ int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n,
   B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage, share_slot));
   tail = [plan, stage, h_out]() {
     std::vector<Proj<F>> win;
-    if (msm_collect<G>(*plan, stage, win) == 0) msm_host_phase<G>(*plan, win, h_out);
+    if (msm_collect<G>(*plan, stage, win) == 0) g_msm_phase_ms[4] = msm_host_phase<G>(*plan, win, h_out);
   };
   return 0;
 }
