@@ -76,6 +76,9 @@ int b200_msm_g1(int curve, const void *d_scalars, const void *d_points, size_t n
 int b200_msm_g2(int curve, const void *d_scalars, const void *d_points, size_t n, void *h_out_proj);
 /* tuning hook: force the Pippenger window width (0 = automatic) */
 int b200_msm_set_window(int c);
+/* Bucket accumulation of every following MSM: 0 = XYZZ mixed additions (default), 1 = batched affine additions
+ * with simultaneous inversion. Same results bit for bit; the environment variable B200_BATCH_AFFINE=1 selects 1. */
+int b200_msm_set_batch_affine(int on);
 
 /* ---- O(1) group / field helpers on HOST buffers (serial tail of the prover) --------------------------------- */
 int b200_g1_add(int curve, const void *h_p, const void *h_q, void *h_out);          /* B::G1_add   (:163-168) */

@@ -80,6 +80,7 @@ _SIGNATURES = {
     "b200_msm_g1": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_msm_g2": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_msm_set_window": (_i, [_i]),
+    "b200_msm_set_batch_affine": (_i, [_i]),
     "b200_msm_last_phase_ms": (_i, [ctypes.POINTER(ctypes.c_double)]),
     "b200_msm_last_plan": (_i, [ctypes.POINTER(ctypes.c_int)]),
     "b200_msm_phase_totals": (_i, [ctypes.POINTER(ctypes.c_double), _i]),
@@ -346,6 +347,11 @@ def prove_combine(curve, partials_all, world, r_fr):
     check(lib().b200_prove_combine(curve, ctypes.addressof(pb), world, ctypes.addressof(rb), ctypes.addressof(out),
                                    ctypes.byref(n)))
     return out.raw[:n.value]
+
+
+def set_batch_affine(on):
+    """Select the bucket accumulation of the MSMs: batched affine additions (True) or XYZZ mixed additions."""
+    check(lib().b200_msm_set_batch_affine(1 if on else 0))
 
 
 def set_precompute(on):

@@ -39,7 +39,7 @@ def _compile(src, verbose):
     path = os.path.join(CSRC, src)
     if _newer(obj, [path] + _headers()):
         return obj, ""
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+    cmd = [NVCC] + FLAGS + os.environ.get("B200_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout[-4000:], r.stderr[-8000:]))

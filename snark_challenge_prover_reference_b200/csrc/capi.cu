@@ -249,6 +249,10 @@ int b200_msm_g2(int curve, const void *d_scalars, const void *d_points, size_t n
   B200_CHECK(require_device());
   return msm_dispatch(curve, 2, d_scalars, d_points, n, h_out);
 }
+int b200_msm_set_batch_affine(int on) {
+  msm_set_batch_affine(on);
+  return 0;
+}
 int b200_msm_set_window(int c) {
   msm_set_window(c);
   return 0;

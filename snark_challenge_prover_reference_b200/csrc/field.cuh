@@ -116,15 +116,12 @@ struct alignas(16) Fp {
   static inline __attribute__((always_inline)) void host_mac_row(unsigned long long *t, const unsigned long long *a,
                                                                  unsigned long long b) {
     unsigned long long lo[12], hi[12];
-#pragma GCC unroll 12
     for (int j = 0; j < 12; j++) lo[j] = _mulx_u64(a[j], b, &hi[j]);
     unsigned char c = 0;
-#pragma GCC unroll 12
     for (int j = 0; j < 12; j++) c = _addcarry_u64(c, t[j], lo[j], &t[j]);
     c = _addcarry_u64(c, t[12], 0, &t[12]);
     t[13] += c;
     c = 0;
-#pragma GCC unroll 12
     for (int j = 0; j < 12; j++) c = _addcarry_u64(c, t[j + 1], hi[j], &t[j + 1]);
     t[13] += c;
   }
@@ -143,7 +140,6 @@ struct alignas(16) Fp {
     for (int i = 0; i < 12; i++) {
       host_mac_row(t, av, ld64(b, i));
       host_mac_row(t, pv, t[0] * inv64);
-#pragma GCC unroll 13
       for (int j = 0; j < 13; j++) t[j] = t[j + 1];
       t[13] = 0;
     }
@@ -356,12 +352,101 @@ struct alignas(16) Fp {
     }
     r = acc;
   }
+  // r = a^-1 by a right-shift binary extended gcd that needs only add / sub / shift / select on 24 limbs - on the GPU it
+  // runs on the ALU pipe, which the multiplier-bound kernels leave ~90 % idle, instead of ~1130 multiplications on the
+  // IMAD pipe. Branch-free per iteration (all lanes of a warp stay converged); at most 2*753 iterations.
+  //   u = x, v = p, A = 1, C = 0 with A*x = u, C*x = v (mod p); while u != 0:
+  //     if u odd: (if u < v swap (u,A) <-> (v,C));  u -= v;  A = A - C mod p;     u >>= 1;  A = A/2 mod p
+  //   => v = 1 and C = x^-1 (plain integer inverse of the Montgomery residue x = a*R, i.e. a^-1 * R^-1);
+  //   one Montgomery multiplication by R^3 brings it back to a^-1 * R (the reference does the same, fp.tcc:677-683).
+  B200_HD static void inv_binary(Fp &r, const Fp &a) {
+    uint32_t u[kLimbs], v[kLimbs], A[kLimbs], C[kLimbs];
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) {
+      u[i] = a.l[i];
+      v[i] = P::p(i);
+      A[i] = 0;
+      C[i] = 0;
+    }
+    A[0] = 1;
+    for (int iter = 0; iter < 2 * 753; iter++) {
+      uint32_t nz = 0;
+#pragma unroll
+      for (int i = 0; i < kLimbs; i++) nz |= u[i];
+      if (nz == 0) break;  // per-thread exit: lanes that finish early simply idle until the warp's slowest lane is done
+      const uint32_t odd = 0u - (u[0] & 1u);  // all-ones when u is odd
+      // d = u - v (borrow -> lt), e = A - C (borrow -> bl)
+      uint32_t d[kLimbs], e[kLimbs];
+      uint32_t brw = 0, brw2 = 0;
+#pragma unroll
+      for (int i = 0; i < kLimbs; i++) {
+        uint64_t t = (uint64_t)u[i] - v[i] - brw;
+        d[i] = (uint32_t)t;
+        brw = (uint32_t)(t >> 32) & 1u;
+        uint64_t t2 = (uint64_t)A[i] - C[i] - brw2;
+        e[i] = (uint32_t)t2;
+        brw2 = (uint32_t)(t2 >> 32) & 1u;
+      }
+      const uint32_t lt = 0u - brw;          // u < v
+      const uint32_t swap = odd & lt;
+      // new v = swap ? u : v ; new C = swap ? A : C
+      // new u = odd ? (lt ? -d : d) : u ; new A = odd ? (lt ? (C - A mod p) : (A - C mod p)) : A
+      //   A - C mod p = e + (bl ? p : 0) ;  C - A mod p = -e + (bl ? 0 : p)
+      const uint32_t bl = 0u - brw2;
+      const uint32_t addp = lt ? ~bl : bl;   // all-ones when p must be added
+      uint32_t cn = lt & 1u, ce = lt & 1u;   // +1 of the two's-complement negation
+      uint32_t cp = 0;
+#pragma unroll
+      for (int i = 0; i < kLimbs; i++) {
+        uint64_t nd = (uint64_t)(d[i] ^ lt) + cn;  // lt ? -d : d
+        cn = (uint32_t)(nd >> 32);
+        uint64_t ne = (uint64_t)(e[i] ^ lt) + ce;  // lt ? -e : e
+        ce = (uint32_t)(ne >> 32);
+        uint64_t na = (uint64_t)(uint32_t)ne + (P::p(i) & addp) + cp;
+        cp = (uint32_t)(na >> 32);
+        const uint32_t ui = u[i], ai = A[i];
+        u[i] = (ui & ~odd) | ((uint32_t)nd & odd);
+        A[i] = (ai & ~odd) | ((uint32_t)na & odd);
+        v[i] = (v[i] & ~swap) | (ui & swap);
+        C[i] = (C[i] & ~swap) | (ai & swap);
+      }
+      // u >>= 1 ; A = (A + (A odd ? p : 0)) >> 1   (A + p < 2^754 fits)
+      const uint32_t aodd = 0u - (A[0] & 1u);
+      uint32_t c2 = 0;
+      uint32_t t[kLimbs];
+#pragma unroll
+      for (int i = 0; i < kLimbs; i++) {
+        uint64_t s2 = (uint64_t)A[i] + (P::p(i) & aodd) + c2;
+        t[i] = (uint32_t)s2;
+        c2 = (uint32_t)(s2 >> 32);
+      }
+#pragma unroll
+      for (int i = 0; i < kLimbs; i++) {
+        const uint32_t un = i + 1 < kLimbs ? u[i + 1] : 0u;
+        const uint32_t tn = i + 1 < kLimbs ? t[i + 1] : c2;
+        u[i] = (u[i] >> 1) | (un << 31);
+        A[i] = (t[i] >> 1) | (tn << 31);
+      }
+    }
+    // C may equal p (== 0 mod p) only if the inverse were 0: impossible for a != 0. Bring back to Montgomery form.
+    Fp ci, r3;
+#pragma unroll
+    for (int i = 0; i < kLimbs; i++) {
+      ci.l[i] = C[i];
+      r3.l[i] = P::r3(i);
+    }
+    mul(r, ci, r3);
+  }
   // r = a^-1 (Fermat, a^(p-2)); a != 0. The reference uses an extended gcd (fp.tcc:641-685); the inverse is unique.
   B200_HD static void inv(Fp &r, const Fp &a) {
+#if defined(__CUDA_ARCH__)
+    inv_binary(r, a);
+#else
     uint32_t e[kLimbs];
     for (int i = 0; i < kLimbs; i++) e[i] = P::p(i);
     e[0] -= 2;  // p is odd and p mod 2^32 >= 3, no borrow
     pow_words(r, a, e, kLimbs);
+#endif
   }
 };
 
@@ -382,6 +467,7 @@ struct alignas(16) Fp2 {
   B200_HD static B200_NOINLINE void sub(Fp2 &r, const Fp2 &a, const Fp2 &b) { B::sub_ni(r.c0, a.c0, b.c0); B::sub_ni(r.c1, a.c1, b.c1); }
   B200_HD static B200_NOINLINE void dbl(Fp2 &r, const Fp2 &a) { B::add_ni(r.c0, a.c0, a.c0); B::add_ni(r.c1, a.c1, a.c1); }
   B200_HD static B200_NOINLINE void neg(Fp2 &r, const Fp2 &a) { B::neg_ni(r.c0, a.c0); B::neg_ni(r.c1, a.c1); }
+  B200_HD static B200_INLINE void neg_ni(Fp2 &r, const Fp2 &a) { neg(r, a); }
   B200_HD static B200_NOINLINE void mul(Fp2 &r, const Fp2 &a, const Fp2 &b) {  // Karatsuba, 3 base multiplications
     B aA, bB, s, t;
     B::mul(aA, a.c0, b.c0);
@@ -442,6 +528,7 @@ struct alignas(16) Fp3 {
   }
   B200_HD static B200_NOINLINE void dbl(Fp3 &r, const Fp3 &a) { B::add_ni(r.c0, a.c0, a.c0); B::add_ni(r.c1, a.c1, a.c1); B::add_ni(r.c2, a.c2, a.c2); }
   B200_HD static B200_NOINLINE void neg(Fp3 &r, const Fp3 &a) { B::neg_ni(r.c0, a.c0); B::neg_ni(r.c1, a.c1); B::neg_ni(r.c2, a.c2); }
+  B200_HD static B200_INLINE void neg_ni(Fp3 &r, const Fp3 &a) { neg(r, a); }
   B200_HD static B200_NOINLINE void mul(Fp3 &r, const Fp3 &a, const Fp3 &b) {  // Karatsuba, 6 base multiplications
     B aA, bB, cC, s, t, u;
     B::mul(aA, a.c0, b.c0);

@@ -17,6 +17,7 @@
 // infinity in the bases (y == 0 on the wire) are skipped; P+P and P+(-P) inside a bucket take the same branches as
 // the reference's mixed_add (curve.cuh).
 #include <cub/cub.cuh>
+#include <cstdlib>
 #include <functional>
 #include "common.cuh"
 #include "field.cuh"
@@ -28,6 +29,16 @@ namespace b200 {
 double g_msm_phase_ms[5] = {0, 0, 0, 0, 0};
 double g_msm_phase_total[2][5];
 static int g_forced_window = 0;
+// B200_BATCH_AFFINE=1: bucket accumulation by rounds of batched affine additions (experimental, see msm_group.cuh)
+static int g_batch_affine = -1;  // -1: take B200_BATCH_AFFINE from the environment on first use
+bool msm_use_batch_affine() {
+  if (g_batch_affine < 0) {
+    const char *e = getenv("B200_BATCH_AFFINE");
+    g_batch_affine = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_batch_affine == 1;
+}
+void msm_set_batch_affine(int on) { g_batch_affine = on ? 1 : 0; }
 void msm_set_window(int c) { g_forced_window = c; }
 void msm_phase_totals(double *out10, int reset) {
   for (int g = 0; g < 2; g++)
@@ -218,7 +229,8 @@ void msm_release_workspace() {
   DevBuf *all[] = {&ws.digits, &ws.counts, &ws.offsets, &ws.cursor, &ws.entries, &ws.order,
                    &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan,
                    &ws.ntasks, &ws.task_off, &ws.task_bucket, &ws.task_len, &ws.task_len_sorted, &ws.partials,
-                   &ws.scalar_out, &ws.fold_cnt, &ws.fold_off, &ws.fold_bucket, &ws.fold_partials};
+                   &ws.scalar_out, &ws.fold_cnt, &ws.fold_off, &ws.fold_bucket, &ws.fold_partials,
+                   &ws.aff_cnt, &ws.aff_off, &ws.aff_totals, &ws.aff_pts[0], &ws.aff_pts[1], &ws.aff_scratch};
   for (DevBuf *b : all) b->release();
   }
 }
@@ -307,8 +319,19 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(&last[0], ws.task_off.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaMemcpyAsync(&last[1], ws.ntasks.as<uint32_t>() + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
+    {
+      size_t need = 0;
+      cub::DeviceReduce::Max(nullptr, need, ws.counts.as<uint32_t>(), ws.scalar_out.as<uint32_t>() + 1, (int)nbuckets, st);
+      B200_CHECK(ws.cub_tmp.reserve(need));
+      tb = ws.cub_tmp.bytes;
+      B200_CUDA_CHECK(cub::DeviceReduce::Max(ws.cub_tmp.p, tb, ws.counts.as<uint32_t>(), ws.scalar_out.as<uint32_t>() + 1,
+                                             (int)nbuckets, st));
+    }
+    uint32_t maxcount = 0;
     B200_CUDA_CHECK(cudaMemcpyAsync(&last[2], ws.scalar_out.as<uint32_t>(), 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(&maxcount, ws.scalar_out.as<uint32_t>() + 1, 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    plan.max_count = maxcount;
     const size_t ntasks = (size_t)last[0] + last[1];
     plan.ntasks = ntasks;
     plan.max_tasks_per_bucket = last[2];
@@ -365,6 +388,42 @@ int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, ui
   B200_CUDA_CHECK(cudaMemcpyAsync(&last[1], cnt_out + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
   B200_CUDA_CHECK(cudaStreamSynchronize(st));
   total_out = (size_t)last[0] + last[1];
+  return 0;
+}
+
+// Batch-affine accumulation bookkeeping: level 0 = the bucket counts/offsets of the counting sort; level r+1 halves every
+// list (ceil). All levels are computed up front so that the round kernels can be enqueued without host round trips.
+int msm_affine_levels(const uint32_t *counts, const uint32_t *offsets, uint32_t nbuckets, uint32_t max_count,
+                      std::vector<size_t> &totals) {
+  MsmWorkspace &ws = msm_workspace();
+  cudaStream_t st = ws.stream;
+  int rounds = 0;
+  for (uint32_t c = max_count; c > 1; c = (c + 1) / 2) rounds++;
+  totals.assign(rounds + 1, 0);
+  B200_CHECK(ws.aff_cnt.reserve((size_t)(rounds + 1) * nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.aff_off.reserve((size_t)(rounds + 1) * nbuckets * sizeof(uint32_t)));
+  B200_CHECK(ws.aff_totals.reserve((size_t)(rounds + 1) * 2 * sizeof(uint32_t)));
+  uint32_t *cnt = ws.aff_cnt.as<uint32_t>(), *off = ws.aff_off.as<uint32_t>();
+  B200_CUDA_CHECK(cudaMemcpyAsync(cnt, counts, (size_t)nbuckets * 4, cudaMemcpyDeviceToDevice, st));
+  B200_CUDA_CHECK(cudaMemcpyAsync(off, offsets, (size_t)nbuckets * 4, cudaMemcpyDeviceToDevice, st));
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, cnt, off, (int)nbuckets, st);
+  B200_CHECK(ws.cub_tmp.reserve(need));
+  for (int r = 1; r <= rounds; r++) {
+    uint32_t *ci = cnt + (size_t)(r - 1) * nbuckets, *co = cnt + (size_t)r * nbuckets, *oo = off + (size_t)r * nbuckets;
+    msm_fold_counts_kernel<<<grid_for(nbuckets, 256), 256, 0, st>>>(ci, nbuckets, 2, co);
+    B200_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    size_t tb = ws.cub_tmp.bytes;
+    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp.p, tb, co, oo, (int)nbuckets, st));
+  }
+  std::vector<uint32_t> last(2 * (rounds + 1));
+  for (int r = 0; r <= rounds; r++) {
+    B200_CUDA_CHECK(cudaMemcpyAsync(&last[2 * r], off + (size_t)r * nbuckets + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(&last[2 * r + 1], cnt + (size_t)r * nbuckets + (nbuckets - 1), 4, cudaMemcpyDeviceToHost, st));
+  }
+  B200_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int r = 0; r <= rounds; r++) totals[r] = (size_t)last[2 * r] + last[2 * r + 1];
   return 0;
 }
 

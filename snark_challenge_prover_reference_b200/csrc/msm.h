@@ -9,6 +9,8 @@ int msm_dispatch(int curve, int group, const void *d_scalars, const void *d_poin
 int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out,
                           std::function<void()> &tail);
 void msm_set_window(int c);
+// bucket accumulation: 0 = XYZZ mixed additions per task (default), 1 = rounds of batched affine additions
+void msm_set_batch_affine(int on);
 void msm_last_phase_ms(double *out5);
 // window width c, number of windows W and task length T of the most recently prepared MSM
 void msm_last_plan(int *out3);

@@ -89,6 +89,170 @@ __global__ void __launch_bounds__(128) msm_combine_kernel(const Proj<typename G:
   buckets[b] = acc;
 }
 
+// ---- batch-affine bucket accumulation (B200_BATCH_AFFINE=1) ------------------------------------------------------
+// Every bucket's list is summed as a balanced tree: a round adds adjacent pairs of every list (an odd leftover is
+// carried over), ceil(log2(longest list)) rounds in all. All additions of a round are independent, so they are done
+// in AFFINE coordinates with Montgomery's simultaneous-inversion trick: one thread takes M consecutive outputs of the
+// round, multiplies their denominators together, inverts ONCE (binary gcd on the ALU pipe, Fp::inv_binary) and
+// unwinds. Cost per addition: 3 multiplications for the shared inversion + 3 for (lambda, x3, y3) = 6 instead of the 10
+// of the XYZZ mixed addition. Special cases are classified per pair: O + Q, P + O, P + P (tangent: denominator 2y,
+// numerator 3x^2 + a), P + (-P) = O. Points are kept in wire format ((0,0) = O).
+template <class F>
+struct AffineSource {
+  const Affine<F> *table;    // round 0: pre-shifted bases or plain bases, indexed through `entries`
+  const uint32_t *entries;   // round 0: index << 1 | negate ; nullptr in later rounds
+  const Affine<F> *pts;      // later rounds: output of the previous round
+};
+template <class F>
+__device__ __forceinline__ void affine_fetch(const AffineSource<F> &src, uint32_t idx, Affine<F> &p) {
+  if (src.entries) {
+    const uint32_t e = src.entries[idx];
+    p = src.table[e >> 1];
+    if ((e & 1u) && !F::is_zero(p.y)) F::neg_ni(p.y, p.y);
+  } else {
+    p = src.pts[idx];
+  }
+}
+// classification of one output of a round: 0 copy first operand, 1 copy second, 2 result O, 3 chord, 4 tangent
+template <class F>
+__device__ __forceinline__ int affine_classify(const Affine<F> &p1, const Affine<F> &p2, bool has_second, F &den) {
+  if (!has_second) return 0;
+  if (F::is_zero(p1.y)) return 1;
+  if (F::is_zero(p2.y)) return 0;
+  if (F::eq(p1.x, p2.x)) {
+    if (!F::eq(p1.y, p2.y)) return 2;
+    F::dbl(den, p1.y);
+    return 4;
+  }
+  F::sub(den, p2.x, p1.x);
+  return 3;
+}
+
+template <class G>
+__global__ void __launch_bounds__(128) msm_affine_round_kernel(AffineSource<typename G::F> src,
+                                                               const uint32_t *__restrict__ off_in,
+                                                               const uint32_t *__restrict__ cnt_in,
+                                                               const uint32_t *__restrict__ off_out, uint32_t nbuckets,
+                                                               uint32_t total_out, uint32_t M,
+                                                               Affine<typename G::F> *__restrict__ pts_out,
+                                                               typename G::F *__restrict__ scratch) {
+  typedef typename G::F F;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t j0 = t * M;
+  if (j0 >= total_out) return;
+  const uint32_t jn = j0 + M < total_out ? j0 + M : total_out;
+  F *pre = scratch + (size_t)t * M;
+  // bucket of output j0: last b with off_out[b] <= j0 (empty buckets share the offset of the next non-empty one)
+  uint32_t lo = 0, hi = nbuckets;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (off_out[mid] <= j0) lo = mid;
+    else hi = mid;
+  }
+  uint32_t b = lo, i = j0 - off_out[lo];
+  const uint32_t b0 = b, i0 = i;
+  // NOTE: a variant of the backward loop that kept the per-output inverse in its own temporary (dinv = inv * prefix;
+  // lambda = num * dinv) was miscompiled by nvcc 12.9 for the MNT6753-G1 instantiation: the PTX passed the SAME stack
+  // slot for dinv and num. The ordering below needs no such temporary (tests run every MSM case in both accumulation modes).
+  F run, den, inv, one, acoef, lam, num;
+  Affine<F> p1, p2, out;
+  F::set_one(run);
+  // ---- forward: running product of the denominators
+  for (uint32_t j = j0; j < jn; j++) {
+    while (i >= (cnt_in[b] + 1) / 2) {
+      b++;
+      i = 0;
+    }
+    const uint32_t c = cnt_in[b], base = off_in[b] + 2 * i;
+    affine_fetch(src, base, p1);
+    const bool second = 2 * i + 1 < c;
+    if (second) affine_fetch(src, base + 1, p2);
+    const int kind = affine_classify(p1, p2, second, den);
+#ifdef B200_AFF_TRACE
+    printf("pre-mul run=%08x p1y=%08x p2y=%08x den=%08x\n", ((const uint32_t *)&run)[0], ((const uint32_t *)&p1.y)[0], ((const uint32_t *)&p2.y)[0], ((const uint32_t *)&den)[0]);
+#endif
+    if (kind >= 3) F::mul(run, run, den);
+#ifdef B200_AFF_TRACE
+    printf("fwd j=%u b=%u i=%u c=%u kind=%d den=%08x run=%08x\n", j, b, i, c, kind, ((const uint32_t *)&den)[0], ((const uint32_t *)&run)[0]);
+#endif
+    pre[j - j0] = run;
+    i++;
+  }
+  F::inv(inv, run);
+#ifdef B200_AFF_TRACE
+  printf("inv=%08x\n", ((const uint32_t *)&inv)[0]);
+#endif
+  // ---- backward: unwind the product, finish every addition
+  F::set_one(one);
+  G::mul_by_a(acoef, one);
+  // position of the last output handled by this thread
+  for (uint32_t j = jn; j-- > j0;) {
+    if (i == 0) {
+      do {
+        b--;
+      } while ((cnt_in[b] + 1) / 2 == 0);
+      i = (cnt_in[b] + 1) / 2;
+    }
+    i--;
+    const uint32_t c = cnt_in[b], base = off_in[b] + 2 * i;
+    affine_fetch(src, base, p1);
+    const bool second = 2 * i + 1 < c;
+    if (second) affine_fetch(src, base + 1, p2);
+    const int kind = affine_classify(p1, p2, second, den);
+    if (kind == 0) {
+      out = p1;
+    } else if (kind == 1) {
+      out = p2;
+    } else if (kind == 2) {
+      F::set_zero(out.x);
+      F::set_zero(out.y);
+    } else {
+      // lambda = num * (inv * prefix) ; then drop this denominator from the running inverse
+      if (kind == 3) {
+        F::sub(num, p2.y, p1.y);
+      } else {
+        F::sqr(num, p1.x);
+        F::add(lam, num, num);
+        F::add(num, lam, num);
+        F::add(num, num, acoef);  // 3 x^2 + a
+        p2.x = p1.x;
+      }
+      F::mul(num, num, inv);
+      F::mul(lam, num, j > j0 ? pre[j - j0 - 1] : one);
+      F::mul(inv, inv, den);
+      F::sqr(out.x, lam);
+      F::sub(out.x, out.x, p1.x);
+      F::sub(out.x, out.x, p2.x);
+      F::sub(num, p1.x, out.x);
+      F::mul(num, lam, num);
+      F::sub(out.y, num, p1.y);
+    }
+    pts_out[off_out[b] + i] = out;
+  }
+  (void)b0;
+  (void)i0;
+}
+
+// bucket[b] = the single remaining point of list b (or O), converted to the projective form the reduction uses
+template <class G>
+__global__ void __launch_bounds__(128) msm_affine_finish_kernel(AffineSource<typename G::F> src,
+                                                                const uint32_t *__restrict__ off_in,
+                                                                const uint32_t *__restrict__ cnt_in, uint32_t nbuckets,
+                                                                Proj<typename G::F> *__restrict__ buckets) {
+  typedef typename G::F F;
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbuckets) return;
+  Proj<F> out;
+  if (cnt_in[b] == 0) {
+    proj_set_zero(out);
+  } else {
+    Affine<F> p;
+    affine_fetch(src, off_in[b], p);
+    proj_from_affine(out, p);
+  }
+  buckets[b] = out;
+}
+
 // One thread reduces K consecutive buckets of one window: sum_{v in (lo, lo+K]} v * B_v  (bucket value v = index+1)
 template <class G>
 __global__ void __launch_bounds__(128) msm_reduce_kernel(const Proj<typename G::F> *__restrict__ buckets, int W,
@@ -165,9 +329,58 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   stage = ws.next_staging((size_t)W * sizeof(Proj<F>));
   if (!stage) return set_error(-5, "msm: pinned staging allocation failed");
 
+  B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
+  if (msm_use_batch_affine()) {
+    // ---- bucket accumulation by rounds of batched affine additions
+    std::vector<size_t> totals;
+    B200_CHECK(msm_affine_levels(pw.counts.as<uint32_t>(), pw.offsets.as<uint32_t>(), (uint32_t)nbuckets, plan.max_count, totals));
+    const int rounds = (int)totals.size() - 1;
+    const uint32_t *cnt = ws.aff_cnt.as<uint32_t>(), *off = ws.aff_off.as<uint32_t>();
+    AffineSource<F> src{(const Affine<F> *)d_points, pw.entries.as<uint32_t>(), nullptr};
+    for (int r = 1; r <= rounds; r++) {
+      const size_t total_out = totals[r];
+      if (total_out == 0) break;
+      // one full wave of resident threads per round: M = outputs per thread (>= 24 so that the shared inversion,
+      // ~60 multiplications' worth of ALU work, stays a small part of the 6 multiplications per addition)
+      static int wave = 0;
+      if (!wave) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_affine_round_kernel<G>, 128, 0);
+        wave = (per_sm > 0 ? per_sm : 1) * sms * 128;
+      }
+      uint32_t M = (uint32_t)((total_out + wave - 1) / wave);
+      M = M < 24 ? 24 : M;
+      const size_t nthreads = (total_out + M - 1) / M;
+      DevBuf &outbuf = ws.aff_pts[r & 1];
+      B200_CHECK(outbuf.reserve(total_out * sizeof(Affine<F>)));
+      B200_CHECK(ws.aff_scratch.reserve(nthreads * M * sizeof(F)));
+      msm_affine_round_kernel<G><<<grid_for(nthreads, 128), 128, 0, st>>>(
+          src, off + (size_t)(r - 1) * nbuckets, cnt + (size_t)(r - 1) * nbuckets, off + (size_t)r * nbuckets,
+          (uint32_t)nbuckets, (uint32_t)total_out, M, outbuf.as<Affine<F>>(), ws.aff_scratch.as<F>());
+      B200_CUDA_CHECK(cudaGetLastError());
+      note_launch();
+      src = AffineSource<F>{nullptr, nullptr, outbuf.as<Affine<F>>()};
+    }
+    msm_affine_finish_kernel<G><<<grid_for(nbuckets, 128), 128, 0, st>>>(
+        src, off + (size_t)rounds * nbuckets, cnt + (size_t)rounds * nbuckets, (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
+    B200_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    if (getenv("B200_AFF_DEBUG")) {
+      std::vector<Proj<F>> hb(nbuckets);
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hb.data(), ws.buckets.p, nbuckets * sizeof(Proj<F>), cudaMemcpyDeviceToHost);
+      for (size_t b = 0; b < nbuckets && b < 8; b++) {
+        const uint32_t *w = (const uint32_t *)&hb[b];
+        printf("bucket %zu:", b);
+        for (size_t k = 0; k < sizeof(Proj<F>) / 4; k++) printf("%s%08x", k % 24 == 0 ? "\n  " : "", w[k / 24 * 24 + 23 - k % 24]);
+        printf("\n");
+      }
+    }
+  } else {
   // ---- bucket accumulation: one thread per task, then per-bucket combine of the task sums. Nothing below waits
   // on the host: the caller may already prepare the next MSM on the other stream.
-  B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
   B200_CHECK(ws.partials.reserve((plan.ntasks ? plan.ntasks : 1) * sizeof(Proj<F>)));
   if (plan.ntasks) {
     msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128, 0, st>>>(
@@ -215,6 +428,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
                                                                  ws.buckets.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
+  }
 
   // ---- bucket reduction (enqueued, not awaited): chunks of K buckets, then tree sum per bucket set
   B200_CUDA_CHECK(cudaEventRecord(stage->t0, st));

@@ -14,6 +14,7 @@ struct MsmWorkspace {
   DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b, plan;
   DevBuf ntasks, task_off, task_bucket, task_len, task_len_sorted, partials;
   DevBuf scalar_out, fold_cnt, fold_off, fold_bucket, fold_partials;  // fold_* hold two ping-pong halves
+  DevBuf aff_cnt, aff_off, aff_totals, aff_pts[2], aff_scratch;        // batch-affine accumulation (msm_affine_*)
   cudaStream_t stream = nullptr;   // every kernel of an MSM that uses this workspace runs on this stream
   // ring of pinned staging buffers + events for the asynchronous copy of the window sums to the host
   struct Staging {
@@ -46,6 +47,7 @@ struct MsmPlan {
   uint32_t task_len = 0;        // T: entries per accumulation task (set by msm_prepare)
   size_t ntasks = 0;            // number of tasks of this call (set by msm_prepare)
   uint32_t max_tasks_per_bucket = 0;  // largest number of task sums any bucket has (set by msm_prepare)
+  uint32_t max_count = 0;             // largest bucket (set by msm_prepare)
 };
 
 extern double g_msm_phase_ms[5];         // last call: digits, sort, accumulate, reduce, host tail
@@ -56,6 +58,9 @@ extern double g_msm_phase_total[2][5];   // accumulated, [0] G1 calls, [1] G2 ca
 // plan.W == 0 on entry: choose a per-window plan for n. Otherwise the caller's plan (e.g. the one a table was built for).
 int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan);
 int msm_make_plan(size_t n, bool merged, MsmPlan &plan);
+int msm_affine_levels(const uint32_t *counts, const uint32_t *offsets, uint32_t nbuckets, uint32_t max_count,
+                      std::vector<size_t> &totals);
+bool msm_use_batch_affine();
 constexpr uint32_t kFoldWidth = 32;  // a bucket with more task sums than this is folded in parallel first
 int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, uint32_t *cnt_out, uint32_t *off_out,
                    size_t &total_out);

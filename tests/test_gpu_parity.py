@@ -188,25 +188,33 @@ def _msm_case(b200, oracle, dev, curve, group, n, seed, special=True, window=0):
     assert got == exp, (curve, group, n, window)
 
 
+@pytest.fixture(params=[0, 1], ids=["xyzz", "batch-affine"])
+def accum(request, b200):
+    """Run the test under both bucket-accumulation modes of the MSM (the results must be identical bit for bit)."""
+    b200.set_batch_affine(request.param)
+    yield request.param
+    b200.set_batch_affine(0)
+
+
 @pytest.mark.parametrize("curve", [0, 1])
 @pytest.mark.parametrize("n", [1, 2, 3, 17, 256, 1000])
-def test_msm_g1_vs_oracle(b200, oracle, dev, curve, n):
+def test_msm_g1_vs_oracle(b200, oracle, dev, curve, n, accum):
     _msm_case(b200, oracle, dev, curve, 1, n, 4000 + n + curve)
 
 
 @pytest.mark.parametrize("curve", [0, 1])
 @pytest.mark.parametrize("n", [1, 5, 64, 300])
-def test_msm_g2_vs_oracle(b200, oracle, dev, curve, n):
+def test_msm_g2_vs_oracle(b200, oracle, dev, curve, n, accum):
     _msm_case(b200, oracle, dev, curve, 2, n, 5000 + n + curve)
 
 
 @pytest.mark.parametrize("window", [3, 8, 13, 16])
-def test_msm_window_widths(b200, oracle, dev, window):
+def test_msm_window_widths(b200, oracle, dev, window, accum):
     _msm_case(b200, oracle, dev, 0, 1, 200, 6000 + window, window=window)
     _msm_case(b200, oracle, dev, 1, 2, 40, 6100 + window, window=window)
 
 
-def test_msm_degenerate_scalars(b200, oracle, dev):
+def test_msm_degenerate_scalars(b200, oracle, dev, accum):
     import torch
     for curve in (0, 1):
         c = util.curve_obj(curve)
@@ -223,7 +231,7 @@ def test_msm_degenerate_scalars(b200, oracle, dev):
         assert b200.g_to_affine(curve, 1, b200.msm(curve, 1, pts, pts, 0)) == bytes(ab)
 
 
-def test_msm_skewed_scalars_fold_path(b200, oracle, dev):
+def test_msm_skewed_scalars_fold_path(b200, oracle, dev, accum):
     """All scalars equal: every window puts all n points into ONE bucket, i.e. thousands of task sums per bucket, which
     exercises the parallel folding of task sums (two levels at n = 2^14). msm(1,...,1) is checked against the oracle
     (which adds the n points directly, multiexp.tcc:468-479) and msm(s,...,s) against s * msm(1,...,1)."""
@@ -243,7 +251,7 @@ def test_msm_skewed_scalars_fold_path(b200, oracle, dev):
         assert b200.g_to_affine(curve, group, sum_s) == b200.g_to_affine(curve, group, b200.g_scale(curve, group, s, sum_ones))
 
 
-def test_msm_linearity_large(b200, dev):
+def test_msm_linearity_large(b200, dev, accum):
     """n = 2^15 (beyond what the oracle does in seconds): msm(s,P) + msm(t,P) == msm(s+t,P), and the same sum from
     two different window widths."""
     import torch
@@ -353,7 +361,7 @@ def precompute(request, b200):
 
 
 @pytest.mark.parametrize("curve,k", [(0, 5), (1, 5), (0, 8), (1, 8)])
-def test_prover_matches_reference_golden(b200, dev, precompute, curve, k):
+def test_prover_matches_reference_golden(b200, dev, precompute, curve, k, accum):
     params, inp, expected = util.golden(curve, k)
     P = b200.Params.from_bytes(curve, params)
     if precompute:
@@ -367,7 +375,7 @@ def test_prover_matches_reference_golden(b200, dev, precompute, curve, k):
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-def test_sharded_prover_matches_reference_golden(b200, dev, precompute, curve):
+def test_sharded_prover_matches_reference_golden(b200, dev, precompute, curve, accum):
     """MSMs split by point range over `world` ranks (run sequentially on one GPU here) + host combine."""
     params, inp, expected = util.golden(curve, 8)
     P = b200.Params.from_bytes(curve, params)
