@@ -196,33 +196,42 @@ struct alignas(16) Fp {
 #if defined(__CUDACC__)
   // out-of-line device add / sub (operands by pointer, like the multiply): callers then hold no limbs in registers
   // across field operations, which keeps the big point-arithmetic kernels at ~128 registers (16 warps/SM).
+  // every Fp object is 16-byte aligned (alignas(16), 96-byte stride in arrays): move operands as 6 x 128 bits
+  static __device__ __forceinline__ void load_limbs(uint32_t (&x)[kLimbs], const uint32_t *a) {
+    const uint4 *a4 = reinterpret_cast<const uint4 *>(a);
+#pragma unroll
+    for (int k = 0; k < kLimbs / 4; k++) {
+      const uint4 v = a4[k];
+      x[4 * k] = v.x;
+      x[4 * k + 1] = v.y;
+      x[4 * k + 2] = v.z;
+      x[4 * k + 3] = v.w;
+    }
+  }
+  static __device__ __forceinline__ void store_limbs(uint32_t *r, const uint32_t (&z)[kLimbs]) {
+    uint4 *r4 = reinterpret_cast<uint4 *>(r);
+#pragma unroll
+    for (int k = 0; k < kLimbs / 4; k++) r4[k] = make_uint4(z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
+  }
   static __device__ __noinline__ void add_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
     uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
-#pragma unroll
-    for (int i = 0; i < kLimbs; i++) {
-      x[i] = a[i];
-      y[i] = b[i];
-    }
+    load_limbs(x, a);
+    load_limbs(y, b);
     if (P::kTag == 'A')
       fp_add_ptx_A(z, x, y);
     else
       fp_add_ptx_B(z, x, y);
-#pragma unroll
-    for (int i = 0; i < kLimbs; i++) r[i] = z[i];
+    store_limbs(r, z);
   }
   static __device__ __noinline__ void sub_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
     uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
-#pragma unroll
-    for (int i = 0; i < kLimbs; i++) {
-      x[i] = a[i];
-      y[i] = b[i];
-    }
+    load_limbs(x, a);
+    load_limbs(y, b);
     if (P::kTag == 'A')
       fp_sub_ptx_A(z, x, y);
     else
       fp_sub_ptx_B(z, x, y);
-#pragma unroll
-    for (int i = 0; i < kLimbs; i++) r[i] = z[i];
+    store_limbs(r, z);
   }
 #endif
   B200_HD static B200_INLINE void add(Fp &r, const Fp &a, const Fp &b) {
@@ -264,11 +273,8 @@ struct alignas(16) Fp {
   // inside the body. One copy per modulus per module keeps the instruction footprint inside the 32 KB L1.5 I-cache.
   static __device__ __noinline__ void mul_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
     uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
-#pragma unroll
-    for (int i = 0; i < kLimbs; i++) {
-      x[i] = a[i];
-      y[i] = b[i];
-    }
+    load_limbs(x, a);
+    load_limbs(y, b);
     // Default: interleaved CIOS (1152 IMAD.WIDE). -DB200_MUL_KARATSUBA selects the one-level Karatsuba product +
     // half-width Montgomery reduction (1008 IMAD.WIDE, ~330 more IADD3 on the ALU pipe). Measured on B200 (round 1):
     // 12 % fewer multiplier-pipe instructions but the longer carry chains and +16 registers drop the fmaheavy
@@ -284,8 +290,7 @@ struct alignas(16) Fp {
     else
       fp_mul_ptx_B(z, x, y);
 #endif
-#pragma unroll
-    for (int i = 0; i < kLimbs; i++) r[i] = z[i];
+    store_limbs(r, z);
   }
 #endif
   B200_HD static B200_INLINE void mul(Fp &r, const Fp &a, const Fp &b) {

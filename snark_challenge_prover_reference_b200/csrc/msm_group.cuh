@@ -97,45 +97,85 @@ __global__ void __launch_bounds__(128) msm_combine_kernel(const Proj<typename G:
 // unwinds. Cost per addition: 3 multiplications for the shared inversion + 3 for (lambda, x3, y3) = 6 instead of the 10
 // of the XYZZ mixed addition. Special cases are classified per pair: O + Q, P + O, P + P (tangent: denominator 2y,
 // numerator 3x^2 + a), P + (-P) = O. Points are kept in wire format ((0,0) = O).
+#ifndef B200_AFF_BLOCKS
+#define B200_AFF_BLOCKS 1
+#endif
 template <class F>
 struct AffineSource {
   const Affine<F> *table;    // round 0: pre-shifted bases or plain bases, indexed through `entries`
   const uint32_t *entries;   // round 0: index << 1 | negate ; nullptr in later rounds
   const Affine<F> *pts;      // later rounds: output of the previous round
 };
+// streaming (evict-first) copies: the points, the prefix products and the round outputs pass through once, the L1/L2
+// capacity is needed for the threads' stack frames (the operands of every field operation live there)
+template <class T>
+__device__ __forceinline__ void load_streaming(T &dst, const T *src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  uint4 *d = reinterpret_cast<uint4 *>(&dst);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 16); k++) d[k] = __ldcs(s + k);
+}
+template <class T>
+__device__ __forceinline__ void store_streaming(T *dst, const T &src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  const uint4 *s = reinterpret_cast<const uint4 *>(&src);
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 16); k++) __stcs(d + k, s[k]);
+}
+// One operand of a round: the point stays in GLOBAL memory (the field routines take generic pointers, so nothing is
+// copied to the stack) and a first-round entry's negation is carried as a flag. Every case below is arranged so
+// that no y coordinate ever has to be negated up front:
+//   same flags     : lambda = (y2 - y1)/(x2 - x1), y3 = lambda (x1 - x3) - y1   - the sum of the stored points
+//   different flags: lambda = (y1 + y2)/(x2 - x1), y3 = lambda (x3 - x1) - y1   - P1 - P2 of the stored points
+// and the result is negated (y3 := y1 - ...) when the FIRST operand carried the flag.
 template <class F>
-__device__ __forceinline__ void affine_fetch(const AffineSource<F> &src, uint32_t idx, Affine<F> &p) {
+struct AffineOperand {
+  const Affine<F> *p;
+  uint32_t neg;
+};
+template <class F>
+__device__ __forceinline__ AffineOperand<F> affine_operand(const AffineSource<F> &src, uint32_t idx) {
   if (src.entries) {
     const uint32_t e = src.entries[idx];
-    p = src.table[e >> 1];
-    if ((e & 1u) && !F::is_zero(p.y)) F::neg_ni(p.y, p.y);
-  } else {
-    p = src.pts[idx];
+    return AffineOperand<F>{src.table + (e >> 1), e & 1u};
   }
+  return AffineOperand<F>{src.pts + idx, 0u};
 }
-// classification of one output of a round: 0 copy first operand, 1 copy second, 2 result O, 3 chord, 4 tangent
+// classification of one output of a round: 0 copy first operand, 1 copy second, 2 result O, 3 chord, 4 tangent;
+// den = the denominator of lambda for kinds 3 and 4
 template <class F>
-__device__ __forceinline__ int affine_classify(const Affine<F> &p1, const Affine<F> &p2, bool has_second, F &den) {
+__device__ __forceinline__ int affine_classify(const AffineOperand<F> &a, const AffineOperand<F> &b, bool has_second,
+                                               F &den) {
   if (!has_second) return 0;
-  if (F::is_zero(p1.y)) return 1;
-  if (F::is_zero(p2.y)) return 0;
-  if (F::eq(p1.x, p2.x)) {
-    if (!F::eq(p1.y, p2.y)) return 2;
-    F::dbl(den, p1.y);
+  if (F::is_zero(a.p->y)) return 1;
+  if (F::is_zero(b.p->y)) return 0;
+  if (F::eq(a.p->x, b.p->x)) {
+    const bool same_point = F::eq(a.p->y, b.p->y) == (a.neg == b.neg);
+    if (!same_point) return 2;
+    F::dbl(den, a.p->y);
     return 4;
   }
-  F::sub(den, p2.x, p1.x);
+  F::sub(den, b.p->x, a.p->x);
   return 3;
+}
+template <class F>
+__device__ __forceinline__ void affine_copy(Affine<F> *dst, const AffineOperand<F> &a) {
+  Affine<F> t;
+  load_streaming(t, a.p);
+  if (a.neg && !F::is_zero(t.y)) F::neg_ni(t.y, t.y);
+  store_streaming(dst, t);
 }
 
 template <class G>
-__global__ void __launch_bounds__(128) msm_affine_round_kernel(AffineSource<typename G::F> src,
+__global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(AffineSource<typename G::F> src,
                                                                const uint32_t *__restrict__ off_in,
                                                                const uint32_t *__restrict__ cnt_in,
                                                                const uint32_t *__restrict__ off_out, uint32_t nbuckets,
                                                                uint32_t total_out, uint32_t M,
-                                                               Affine<typename G::F> *__restrict__ pts_out,
-                                                               typename G::F *__restrict__ scratch) {
+                                                               Affine<typename G::F> *pts_out,
+                                                               typename G::F *scratch) {
   typedef typename G::F F;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t j0 = t * M;
@@ -150,13 +190,12 @@ __global__ void __launch_bounds__(128) msm_affine_round_kernel(AffineSource<type
     else hi = mid;
   }
   uint32_t b = lo, i = j0 - off_out[lo];
-  const uint32_t b0 = b, i0 = i;
   // NOTE: a variant of the backward loop that kept the per-output inverse in its own temporary (dinv = inv * prefix;
   // lambda = num * dinv) was miscompiled by nvcc 12.9 for the MNT6753-G1 instantiation: the PTX passed the SAME stack
-  // slot for dinv and num. The ordering below needs no such temporary (tests run every MSM case in both accumulation modes).
-  F run, den, inv, one, acoef, lam, num;
-  Affine<F> p1, p2, out;
-  F::set_one(run);
+  // slot for dinv and num. The ordering below needs no such temporary (tests run every MSM case in both accumulation
+  // modes).
+  F inv, den, lam, num, x3;  // the only field elements on the stack; inv holds the running product first
+  F::set_one(inv);
   // ---- forward: running product of the denominators
   for (uint32_t j = j0; j < jn; j++) {
     while (i >= (cnt_in[b] + 1) / 2) {
@@ -164,28 +203,16 @@ __global__ void __launch_bounds__(128) msm_affine_round_kernel(AffineSource<type
       i = 0;
     }
     const uint32_t c = cnt_in[b], base = off_in[b] + 2 * i;
-    affine_fetch(src, base, p1);
     const bool second = 2 * i + 1 < c;
-    if (second) affine_fetch(src, base + 1, p2);
-    const int kind = affine_classify(p1, p2, second, den);
-#ifdef B200_AFF_TRACE
-    printf("pre-mul run=%08x p1y=%08x p2y=%08x den=%08x\n", ((const uint32_t *)&run)[0], ((const uint32_t *)&p1.y)[0], ((const uint32_t *)&p2.y)[0], ((const uint32_t *)&den)[0]);
-#endif
-    if (kind >= 3) F::mul(run, run, den);
-#ifdef B200_AFF_TRACE
-    printf("fwd j=%u b=%u i=%u c=%u kind=%d den=%08x run=%08x\n", j, b, i, c, kind, ((const uint32_t *)&den)[0], ((const uint32_t *)&run)[0]);
-#endif
-    pre[j - j0] = run;
+    const AffineOperand<F> q1 = affine_operand(src, base);
+    const AffineOperand<F> q2 = second ? affine_operand(src, base + 1) : q1;
+    const int kind = affine_classify(q1, q2, second, den);
+    if (kind >= 3) F::mul(inv, inv, den);
+    store_streaming(pre + (j - j0), inv);
     i++;
   }
-  F::inv(inv, run);
-#ifdef B200_AFF_TRACE
-  printf("inv=%08x\n", ((const uint32_t *)&inv)[0]);
-#endif
+  F::inv(inv, inv);
   // ---- backward: unwind the product, finish every addition
-  F::set_one(one);
-  G::mul_by_a(acoef, one);
-  // position of the last output handled by this thread
   for (uint32_t j = jn; j-- > j0;) {
     if (i == 0) {
       do {
@@ -195,42 +222,48 @@ __global__ void __launch_bounds__(128) msm_affine_round_kernel(AffineSource<type
     }
     i--;
     const uint32_t c = cnt_in[b], base = off_in[b] + 2 * i;
-    affine_fetch(src, base, p1);
     const bool second = 2 * i + 1 < c;
-    if (second) affine_fetch(src, base + 1, p2);
-    const int kind = affine_classify(p1, p2, second, den);
+    const AffineOperand<F> q1 = affine_operand(src, base);
+    const AffineOperand<F> q2 = second ? affine_operand(src, base + 1) : q1;
+    const int kind = affine_classify(q1, q2, second, den);
+    Affine<F> *out = pts_out + (off_out[b] + i);
     if (kind == 0) {
-      out = p1;
+      affine_copy(out, q1);
     } else if (kind == 1) {
-      out = p2;
+      affine_copy(out, q2);
     } else if (kind == 2) {
-      F::set_zero(out.x);
-      F::set_zero(out.y);
+      F::set_zero(x3);
+      store_streaming(&out->x, x3);
+      store_streaming(&out->y, x3);
     } else {
-      // lambda = num * (inv * prefix) ; then drop this denominator from the running inverse
+      const bool same = kind == 4 || q1.neg == q2.neg;
       if (kind == 3) {
-        F::sub(num, p2.y, p1.y);
+        if (same) F::sub(num, q2.p->y, q1.p->y);
+        else F::add(num, q1.p->y, q2.p->y);
       } else {
-        F::sqr(num, p1.x);
+        F::sqr(num, q1.p->x);
         F::add(lam, num, num);
         F::add(num, lam, num);
-        F::add(num, num, acoef);  // 3 x^2 + a
-        p2.x = p1.x;
+        F::set_one(lam);
+        G::mul_by_a(lam, lam);
+        F::add(num, num, lam);  // 3 x^2 + a
       }
+      // lambda = num * (inv * prefix) ; then drop this denominator from the running inverse
       F::mul(num, num, inv);
-      F::mul(lam, num, j > j0 ? pre[j - j0 - 1] : one);
+      if (j > j0) F::mul(lam, num, pre[j - j0 - 1]);
+      else lam = num;
       F::mul(inv, inv, den);
-      F::sqr(out.x, lam);
-      F::sub(out.x, out.x, p1.x);
-      F::sub(out.x, out.x, p2.x);
-      F::sub(num, p1.x, out.x);
+      F::sqr(x3, lam);
+      F::sub(x3, x3, q1.p->x);
+      F::sub(x3, x3, q2.p->x);
+      if (same) F::sub(num, q1.p->x, x3);
+      else F::sub(num, x3, q1.p->x);
       F::mul(num, lam, num);
-      F::sub(out.y, num, p1.y);
+      if (q1.neg) F::sub(out->y, q1.p->y, num);
+      else F::sub(out->y, num, q1.p->y);
+      store_streaming(&out->x, x3);
     }
-    pts_out[off_out[b] + i] = out;
   }
-  (void)b0;
-  (void)i0;
 }
 
 // bucket[b] = the single remaining point of list b (or O), converted to the projective form the reduction uses
@@ -247,7 +280,9 @@ __global__ void __launch_bounds__(128) msm_affine_finish_kernel(AffineSource<typ
     proj_set_zero(out);
   } else {
     Affine<F> p;
-    affine_fetch(src, off_in[b], p);
+    const AffineOperand<F> q = affine_operand(src, off_in[b]);
+    load_streaming(p, q.p);
+    if (q.neg && !F::is_zero(p.y)) F::neg_ni(p.y, p.y);
     proj_from_affine(out, p);
   }
   buckets[b] = out;
