@@ -133,6 +133,23 @@ int b200_prove_partial(b200_params *p, const void *h_input, size_t input_bytes, 
 int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
                        size_t *out_bytes);
 
+/* Several proofs in flight on the current device: job 0 runs on the calling thread, every further job on a
+ * persistent worker thread with its own streams and workspaces, so a small proof (MNT6753, 2^15 constraints) runs
+ * underneath a large one (MNT4753, 2^20). world <= 1: a finished proof in h_out (as b200_prove); world > 1: this
+ * rank's partial sums (as b200_prove_partial). At most 8 jobs; the keys must be distinct objects. Replaces running
+ * the reference driver once per curve (cuda_prover_piecewise.cu:100-121). */
+typedef struct {
+  b200_params *key;
+  const void *h_input;
+  size_t input_bytes;
+  void *h_out;
+  size_t out_bytes; /* set by the call */
+  int rank, world;
+  int status; /* set by the call: 0 or the job's error code */
+  b200_prove_timings timings;
+} b200_proof_job;
+int b200_prove_batch(b200_proof_job *jobs, int count);
+
 /* ---- test / bench hooks: element-wise application of the device primitives the kernels are built from ------- */
 /* op: 0 add 1 sub 2 mul 3 sqr 4 from_mont 5 to_mont 6 inv ; tag: 0 = modulus A, 1 = modulus B */
 int b200_dev_fp_op(int tag, int op, const void *d_a, const void *d_b, void *d_r, size_t n);

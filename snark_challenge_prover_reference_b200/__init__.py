@@ -48,6 +48,13 @@ class ProveTimings(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ProofJob(ctypes.Structure):
+    """b200_proof_job of include/b200_groth16.h"""
+    _fields_ = [("key", ctypes.c_void_p), ("h_input", ctypes.c_void_p), ("input_bytes", ctypes.c_size_t),
+                ("h_out", ctypes.c_void_p), ("out_bytes", ctypes.c_size_t), ("rank", ctypes.c_int),
+                ("world", ctypes.c_int), ("status", ctypes.c_int), ("timings", ProveTimings)]
+
+
 _lib = None
 
 _vp, _sz, _i, _u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
@@ -79,6 +86,7 @@ _SIGNATURES = {
     "b200_compute_h": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_msm_g1": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_msm_g2": (_i, [_i, _vp, _vp, _sz, _vp]),
+    "b200_prove_batch": (_i, [_vp, _i]),
     "b200_msm_set_window": (_i, [_i]),
     "b200_msm_set_batch_affine": (_i, [_i]),
     "b200_msm_last_phase_ms": (_i, [ctypes.POINTER(ctypes.c_double)]),
@@ -347,6 +355,25 @@ def prove_combine(curve, partials_all, world, r_fr):
     check(lib().b200_prove_combine(curve, ctypes.addressof(pb), world, ctypes.addressof(rb), ctypes.addressof(out),
                                    ctypes.byref(n)))
     return out.raw[:n.value]
+
+
+def prove_batch(jobs, timings=False):
+    """Several proofs in flight at once on the current device (b200_prove_batch). jobs: sequence of
+    (Params, host_input_image) for whole proofs or (Params, host_input_image, rank, world) for one rank's partial
+    sums. Returns the list of proof (or partial-sum) byte strings, in job order."""
+    arr = (ProofJob * len(jobs))()
+    outs = []
+    for a, job in zip(arr, jobs):
+        key, image = job[0], job[1]
+        rank, world = (job[2], job[3]) if len(job) > 2 else (0, 1)
+        out = ctypes.create_string_buffer(max(proof_bytes(key.curve), partial_bytes(key.curve)))
+        outs.append(out)
+        a.key = key.h.value if hasattr(key.h, "value") else key.h
+        a.h_input, a.input_bytes = _ptr(image), _len(image)
+        a.h_out, a.rank, a.world = ctypes.addressof(out), rank, world
+    check(lib().b200_prove_batch(ctypes.addressof(arr), len(jobs)))
+    res = [o.raw[:a.out_bytes] for o, a in zip(outs, arr)]
+    return (res, [a.timings.as_dict() for a in arr]) if timings else res
 
 
 def set_batch_affine(on):

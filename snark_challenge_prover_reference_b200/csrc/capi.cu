@@ -2,7 +2,10 @@
 // prover tail, the device-resident proving key and the whole-proof entry points.
 #include <chrono>
 #include <functional>
+#include <condition_variable>
 #include <future>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include "../../include/b200_groth16.h"
@@ -28,8 +31,8 @@ int set_error(int code, const char *fmt, ...) {
   return code;
 }
 
-unsigned long long &launch_counter() {
-  static unsigned long long n = 0;
+std::atomic<unsigned long long> &launch_counter() {
+  static std::atomic<unsigned long long> n{0};
   return n;
 }
 
@@ -578,6 +581,87 @@ int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_
     timings->tail_ms += now_ms() - t1;
     timings->total_ms = now_ms() - t0;
   }
+  return 0;
+}
+
+// ---- several proofs in flight at once -------------------------------------------------------------------------------
+// A persistent host thread per extra job: the MSM workspaces and streams are thread_local, so a worker keeps its
+// own set for the life of the process and its proof runs beside the caller's on the same GPU. The MNT6753 proof
+// (2^15 constraints, latency-bound kernels) disappears under the MNT4753 one (2^20, multiplier-bound).
+namespace {
+class ProofWorker {
+ public:
+  ProofWorker() { std::thread([this] { loop(); }).detach(); }
+  void submit(std::function<void()> job) {
+    std::lock_guard<std::mutex> g(mu_);
+    job_ = std::move(job);
+    busy_ = true;
+    cv_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> g(mu_);
+    cv_.wait(g, [this] { return !busy_; });
+  }
+
+ private:
+  void loop() {
+    msm_thread_high_priority(true);
+    for (;;) {
+      std::function<void()> job;
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return busy_ && job_; });
+        job = std::move(job_);
+        job_ = nullptr;
+      }
+      job();
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        busy_ = false;
+      }
+      cv_.notify_all();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::function<void()> job_;
+  bool busy_ = false;
+};
+
+int run_proof_job(b200_proof_job *j) {
+  if (!j->key || !j->h_input || !j->h_out) return set_error(-1, "proof job: null key, input or output");
+  if (j->world > 1)
+    return b200_prove_partial(j->key, j->h_input, j->input_bytes, j->rank, j->world, j->h_out, &j->out_bytes,
+                              &j->timings);
+  return b200_prove(j->key, j->h_input, j->input_bytes, j->h_out, &j->out_bytes, &j->timings);
+}
+}  // namespace
+
+int b200_prove_batch(b200_proof_job *jobs, int count) {
+  B200_CHECK(require_device());
+  constexpr int kMaxJobs = 8;
+  if (!jobs || count < 1 || count > kMaxJobs) return set_error(-1, "prove_batch: count %d not in [1, %d]", count, kMaxJobs);
+  static std::mutex pool_mu;
+  static ProofWorker *pool[kMaxJobs] = {nullptr};  // leaked on purpose: the threads outlive static destruction
+  std::lock_guard<std::mutex> g(pool_mu);          // one batch at a time
+  int dev = 0;
+  B200_CUDA_CHECK(cudaGetDevice(&dev));
+  std::string errs[kMaxJobs];
+  for (int i = 1; i < count; i++) {
+    if (!pool[i]) pool[i] = new ProofWorker();
+    b200_proof_job *j = &jobs[i];
+    std::string *err = &errs[i];
+    pool[i]->submit([j, err, dev] {
+      cudaError_t e = cudaSetDevice(dev);
+      j->status = e == cudaSuccess ? run_proof_job(j) : set_error(-2, "cudaSetDevice: %s", cudaGetErrorString(e));
+      if (j->status) *err = last_error();
+    });
+  }
+  jobs[0].status = run_proof_job(&jobs[0]);
+  if (jobs[0].status) errs[0] = last_error();
+  for (int i = 1; i < count; i++) pool[i]->wait();
+  for (int i = 0; i < count; i++)
+    if (jobs[i].status) return set_error(jobs[i].status, "proof job %d: %s", i, errs[i].c_str());
   return 0;
 }
 

@@ -1,5 +1,6 @@
 // Shared host-side plumbing for the CUDA translation units: error reporting and small RAII helpers.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -88,8 +89,8 @@ struct Timer {  // CUDA-event timer on one stream
 };
 
 // number of kernels this library launched (bench.py reports it as gpu_launches)
-unsigned long long &launch_counter();
-static inline void note_launch(unsigned n = 1) { launch_counter() += n; }
+std::atomic<unsigned long long> &launch_counter();
+static inline void note_launch(unsigned n = 1) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 

@@ -187,6 +187,8 @@ int msm_make_plan(size_t n, bool merged, MsmPlan &plan) {
   return 0;
 }
 
+static thread_local bool g_high_priority = false;
+void msm_thread_high_priority(bool on) { g_high_priority = on; }
 static thread_local int g_slot = 0;
 void msm_select_slot(int slot) { g_slot = ((slot % kMsmSlots) + kMsmSlots) % kMsmSlots; }
 static MsmWorkspace *workspace_slots() {
@@ -196,7 +198,11 @@ static MsmWorkspace *workspace_slots() {
 MsmWorkspace &msm_workspace_slot(int slot) {
   MsmWorkspace &ws = workspace_slots()[slot];
   if (!ws.stream) {
-    cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking);
+    // streams of a worker thread of b200_prove_batch (the smaller proofs) outrank the caller's: their short kernels
+    // slot in as soon as an SM frees up instead of queueing behind the large proof's grids
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, g_high_priority ? greatest : least);
     cudaEventCreateWithFlags(&ws.prep_done, cudaEventDisableTiming);
     ws.prepared = new MsmPlan();
   }

@@ -9,6 +9,8 @@ int msm_dispatch(int curve, int group, const void *d_scalars, const void *d_poin
 int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out,
                           std::function<void()> &tail);
 void msm_set_window(int c);
+// MSM streams created by the calling thread from now on get the highest priority (worker threads of prove_batch)
+void msm_thread_high_priority(bool on);
 // bucket accumulation: 0 = XYZZ mixed additions per task (default), 1 = rounds of batched affine additions
 void msm_set_batch_affine(int on);
 void msm_last_phase_ms(double *out5);

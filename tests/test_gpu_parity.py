@@ -383,3 +383,31 @@ def test_sharded_prover_matches_reference_golden(b200, dev, precompute, curve, a
         parts = b"".join(P.prove_partial(inp, r, world)[0] for r in range(world))
         assert b200.prove_combine(curve, parts, world, inp[-FE:]) == expected
     P.close()
+
+
+def test_concurrent_proofs_match_reference_golden(b200, dev):
+    """b200_prove_batch: the MNT4753 and MNT6753 proofs (and two sizes of each) in flight at the same time, several
+    batches in a row on the same persistent worker threads; then the sharded variant of the same call."""
+    cases = [(0, 8), (1, 8), (0, 5), (1, 5)]
+    keys, inputs, expected = [], [], []
+    for curve, k in cases:
+        params, inp, exp = util.golden(curve, k)
+        keys.append(b200.Params.from_bytes(curve, params))
+        inputs.append(inp)
+        expected.append(exp)
+    for _ in range(3):
+        got = b200.prove_batch(list(zip(keys, inputs)))
+        assert got == expected
+    got, tms = b200.prove_batch(list(zip(keys[:2], inputs[:2])), timings=True)
+    assert got == expected[:2] and all(t["total_ms"] > 0 for t in tms)
+    world = 2
+    parts = [b200.prove_batch([(keys[0], inputs[0], r, world), (keys[1], inputs[1], r, world)]) for r in range(world)]
+    for j in (0, 1):
+        allp = b"".join(parts[r][j] for r in range(world))
+        assert b200.prove_combine(cases[j][0], allp, world, inputs[j][-FE:]) == expected[j]
+    # a failing job is reported with its index and does not wedge the workers
+    with pytest.raises(b200.B200Error, match="proof job 1"):
+        b200.prove_batch([(keys[0], inputs[0]), (keys[1], inputs[1][:-FE])])
+    assert b200.prove_batch(list(zip(keys[:2], inputs[:2]))) == expected[:2]
+    for P in keys:
+        P.close()
