@@ -321,7 +321,7 @@ def b200_arm(args):
     # accumulation launches on the MSM's stream). Bound: the INT32 multiplier (IMAD.WIDE / fmaheavy) pipe.
     imad = pkg.imad_peak()
     peak = max(imad["mad_wide_mac32_per_s"], imad["carry_chain_mac32_per_s"])
-    iso = {"g1": [], "g2": []}
+    iso = {"g1": [], "g2": [], "a_merged": []}
     plans = {}
     if world == 1:
         for i, (curve, k) in enumerate(shapes):
@@ -331,7 +331,10 @@ def b200_arm(args):
                 keys[i].msm(which, d_w, n)  # warm
                 keys[i].msm(which, d_w, n)
                 ph = pkg.msm_phase_ms()
-                iso["g2" if which == 2 else "g1"].append((curve, n, ph["accumulate"], ph["reduce"]))
+                # the A query is kept out of the roofline: the scalars of its m/2 equal bases are merged at run time
+                # (DESIGN.md 4.2), so it accumulates half as many points as it is credited with
+                iso["g2" if which == 2 else ("a_merged" if which == 0 else "g1")].append(
+                    (curve, n, ph["accumulate"], ph["reduce"]))
                 plans[(curve, which == 2)] = pkg.msm_last_plan()
     else:
         # sharded run: per-kernel event times of rank 0 inside the timed region (the five MSMs of a proof overlap on
@@ -357,6 +360,7 @@ def b200_arm(args):
                                 "(profiles/prof_accumulate_g1_tables_r01_raw.csv); algorithmic: 36 windows x 2^20 x 192 B = 7.2 GB "
                                 "of table reads, the rest is per-thread stack traffic; 0.6 TB/s, far below the HBM roofline",
                 "launches": len(iso["g1"]), "avg_launch_ms": statistics.mean(g1_big) if g1_big else None,
+                "a_query_equal_bases_merged_ms": [round(t, 2) for _, _, t, _ in iso["a_merged"]],
                 "peak_source": "measured live by b200_imad_peak (IMAD.WIDE carry-chain microbenchmark on all SMs)",
                 "timing": "kernel timed alone with CUDA events on its stream (inside a proof 5 MSMs overlap)",
                 "note": "achieved uses SURVEY 8d's algorithmic 620928 MAC32/point (48 windows x 11 mul x 1176); with the "

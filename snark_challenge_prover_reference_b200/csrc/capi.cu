@@ -1,5 +1,6 @@
 // extern "C" layer declared in include/b200_groth16.h: runtime plumbing, the O(1) host-side group operations of the
 // prover tail, the device-resident proving key and the whole-proof entry points.
+#include <algorithm>
 #include <chrono>
 #include <functional>
 #include <condition_variable>
@@ -129,6 +130,7 @@ struct Precomputed {
   int rank = -1, world = -1;
   DevBuf table[5];
   MsmPlan plan[5];
+  MsmDedup dedup[5];  // equal bases inside this rank's slice of each G1 query (job order A, B1, B2, H, L)
   double build_ms = 0;
 };
 
@@ -149,6 +151,76 @@ static bool use_precompute() {
     g_use_precompute = (e && e[0] == '0') ? 0 : 1;
   }
   return g_use_precompute != 0;
+}
+
+// Equal bases of one G1 point range (key-load time, host): 64-bit hash of the 192 wire bytes, sort, confirm with memcmp.
+// Only worth a separate scalar pass when a sizeable part of the range folds away (the A query: m/2 of m+1 bases);
+// a stray duplicate pair (B1, B2) is left to the P+P branch of the bucket accumulation.
+static int find_equal_bases(const void *d_points, size_t n, size_t point_bytes, MsmDedup &dd) {
+  dd.reset();
+  if (n < 8) return 0;
+  std::vector<unsigned char> pts(n * point_bytes);
+  B200_CUDA_CHECK(cudaMemcpy(pts.data(), d_points, pts.size(), cudaMemcpyDeviceToHost));
+  std::vector<std::pair<uint64_t, uint32_t>> keyed;
+  keyed.reserve(n);
+  for (size_t i = 0; i < n; i++) {
+    const unsigned char *q = pts.data() + i * point_bytes;
+    bool inf = true;  // y == 0 encodes O: skipped by the kernels anyway
+    for (size_t k = point_bytes / 2; k < point_bytes && inf; k++) inf = q[k] == 0;
+    if (inf) continue;
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t k = 0; k < point_bytes; k += 8) {
+      uint64_t w;
+      memcpy(&w, q + k, 8);
+      h = (h ^ w) * 0x100000001b3ull;
+      h ^= h >> 29;
+    }
+    keyed.emplace_back(h, (uint32_t)i);
+  }
+  std::sort(keyed.begin(), keyed.end());
+  std::vector<uint32_t> members, segments, groups;
+  size_t merged = 0;
+  for (size_t a = 0; a < keyed.size();) {
+    size_t b = a + 1;
+    while (b < keyed.size() && keyed[b].first == keyed[a].first) b++;
+    if (b - a >= 2) {
+      // members of the run that really equal its first element (a hash collision just stays unmerged)
+      const unsigned char *rep = pts.data() + (size_t)keyed[a].second * point_bytes;
+      const size_t first = members.size();
+      members.push_back(keyed[a].second);
+      for (size_t k = a + 1; k < b; k++)
+        if (memcmp(rep, pts.data() + (size_t)keyed[k].second * point_bytes, point_bytes) == 0)
+          members.push_back(keyed[k].second);
+      const size_t len = members.size() - first;
+      if (len < 2) {
+        members.resize(first);
+      } else {
+        const uint32_t g = (uint32_t)(groups.size() / 3), seg0 = (uint32_t)(segments.size() / 3);
+        for (size_t o = 0; o < len; o += kDedupSegment) {
+          segments.push_back((uint32_t)(first + o));
+          segments.push_back((uint32_t)std::min<size_t>(kDedupSegment, len - o));
+          segments.push_back(g);
+        }
+        groups.push_back(keyed[a].second);
+        groups.push_back(seg0);
+        groups.push_back((uint32_t)(segments.size() / 3) - seg0);
+        merged += len - 1;
+      }
+    }
+    a = b;
+  }
+  if (merged < std::max<size_t>(4, n / 32)) return 0;
+  dd.nsegments = (uint32_t)(segments.size() / 3);
+  dd.ngroups = (uint32_t)(groups.size() / 3);
+  B200_CHECK(dd.members.reserve(members.size() * 4));
+  B200_CHECK(dd.segments.reserve(segments.size() * 4));
+  B200_CHECK(dd.groups.reserve(groups.size() * 4));
+  B200_CHECK(dd.segment_sums.reserve((size_t)dd.nsegments * 96));
+  B200_CUDA_CHECK(cudaMemcpy(dd.members.p, members.data(), members.size() * 4, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpy(dd.segments.p, segments.data(), segments.size() * 4, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpy(dd.groups.p, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice));
+  dd.merged = merged;
+  return 0;
 }
 
 extern "C" {
@@ -412,6 +484,8 @@ int b200_params_precompute(b200_params *p, int rank, int world) {
     const char *pts = (const char *)p->q[qi] + lo * affine_bytes(p->curve, group);
     p->pre.plan[j] = MsmPlan();
     if (hi > lo) B200_CHECK(msm_precompute_dispatch(p->curve, group, pts, hi - lo, p->pre.plan[j], p->pre.table[j]));
+    p->pre.dedup[j].reset();
+    if (hi > lo && group == 1) B200_CHECK(find_equal_bases(pts, hi - lo, affine_bytes(p->curve, 1), p->pre.dedup[j]));
   }
   p->pre.rank = rank;
   p->pre.world = world;
@@ -438,7 +512,8 @@ int b200_params_msm(b200_params *p, int which, const void *d_scalars, size_t n, 
     const int j = job_of_query[which];
     std::function<void()> tail;
     msm_select_slot(0);
-    B200_CHECK(msm_table_dispatch_deferred(p->curve, group, d_scalars, p->pre.table[j].p, n, p->pre.plan[j], h_out, tail));
+    B200_CHECK(msm_table_dispatch_deferred(p->curve, group, d_scalars, p->pre.table[j].p, n, p->pre.plan[j], h_out, tail,
+                                           -1, &p->pre.dedup[j]));
     tail();
     return 0;
   }
@@ -502,10 +577,12 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     msm_select_slot(jj);
     // A and B1 (slots 1, 2) run over the same scalars and window plan as B2 (slot 0): they reuse its digits, counting
     // sort and task list
-    const int share = (jj == 1 || jj == 2) && p->pre.plan[j].c == p->pre.plan[2].c ? 0 : -1;
+    // (not when this query's equal bases are merged: its scalars then differ from w)
+    const bool merges = use_precompute() && p->pre.dedup[j].merged > 0;
+    const int share = (jj == 1 || jj == 2) && !merges && p->pre.plan[j].c == p->pre.plan[2].c ? 0 : -1;
     if (use_precompute())
       rc_all = msm_table_dispatch_deferred(curve, J.group, J.scalars + lo * 96, p->pre.table[j].p, hi - lo,
-                                           p->pre.plan[j], o, tail, share);
+                                           p->pre.plan[j], o, tail, share, &p->pre.dedup[j]);
     else
       rc_all = msm_dispatch_deferred(curve, J.group, J.scalars + lo * 96, J.points + lo * J.stride, hi - lo, o, tail);
     if (rc_all == 0) tails.push_back(std::async(std::launch::async, tail));

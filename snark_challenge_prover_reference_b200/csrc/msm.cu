@@ -94,6 +94,73 @@ __global__ void __launch_bounds__(128) msm_digits_kernel(const Fp<FrP> *__restri
   }
 }
 
+// Equal-base merging, step 1: one block per segment of a group adds the members' scalars (Montgomery form, so the sum
+// is just the field sum) and zeroes them in the working copy; step 2: one block per group adds the segment sums and
+// stores the total as the representative's scalar.
+template <class FrP>
+__global__ void __launch_bounds__(128) msm_dedup_segment_kernel(const Fp<FrP> *__restrict__ scalars,
+                                                                const uint32_t *__restrict__ members,
+                                                                const uint32_t *__restrict__ segments,
+                                                                Fp<FrP> *__restrict__ merged,
+                                                                Fp<FrP> *__restrict__ segment_sums) {
+  typedef Fp<FrP> F;
+  __shared__ F part[128];
+  const uint32_t first = segments[3 * blockIdx.x], len = segments[3 * blockIdx.x + 1];
+  F acc, zero;
+  F::set_zero(acc);
+  F::set_zero(zero);
+  for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) {
+    const uint32_t i = members[first + k];
+    F s = scalars[i];
+    F::add(acc, acc, s);
+    merged[i] = zero;
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t w = blockDim.x / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) F::add(part[threadIdx.x], part[threadIdx.x], part[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) segment_sums[blockIdx.x] = part[0];
+}
+template <class FrP>
+__global__ void __launch_bounds__(128) msm_dedup_group_kernel(const uint32_t *__restrict__ groups,
+                                                              const Fp<FrP> *__restrict__ segment_sums,
+                                                              Fp<FrP> *__restrict__ merged) {
+  typedef Fp<FrP> F;
+  __shared__ F part[128];
+  const uint32_t rep = groups[3 * blockIdx.x], first = groups[3 * blockIdx.x + 1], cnt = groups[3 * blockIdx.x + 2];
+  F acc;
+  F::set_zero(acc);
+  for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
+    F s = segment_sums[first + k];
+    F::add(acc, acc, s);
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t w = blockDim.x / 2; w > 0; w >>= 1) {
+    if (threadIdx.x < w) F::add(part[threadIdx.x], part[threadIdx.x], part[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) merged[rep] = part[0];
+}
+template <class FrP>
+static int msm_dedup_scalars(const void *d_scalars, size_t n, const MsmDedup &dd, MsmWorkspace &ws) {
+  typedef Fp<FrP> F;
+  cudaStream_t st = ws.stream;
+  B200_CHECK(ws.merged_scalars.reserve(n * sizeof(F)));
+  B200_CUDA_CHECK(cudaMemcpyAsync(ws.merged_scalars.p, d_scalars, n * sizeof(F), cudaMemcpyDeviceToDevice, st));
+  msm_dedup_segment_kernel<FrP><<<dd.nsegments, 128, 0, st>>>((const F *)d_scalars, dd.members.as<uint32_t>(),
+                                                            dd.segments.as<uint32_t>(), ws.merged_scalars.as<F>(),
+                                                            dd.segment_sums.as<F>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  msm_dedup_group_kernel<FrP><<<dd.ngroups, 128, 0, st>>>(dd.groups.as<uint32_t>(), dd.segment_sums.as<F>(),
+                                                        ws.merged_scalars.as<F>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch(2);
+  return 0;
+}
+
 // merged == 0: bucket space is (window, |digit|), an entry is a point index into the n bases.
 // merged == 1: all windows share one bucket set, an entry is j*n + i, an index into the table of pre-shifted bases
 //              2^(start_j) * P_i (see msm_precompute_kernel).
@@ -236,12 +303,13 @@ void msm_release_workspace() {
                    &ws.counts_sorted, &ws.iota, &ws.cub_tmp, &ws.buckets, &ws.red_a, &ws.red_b, &ws.plan,
                    &ws.ntasks, &ws.task_off, &ws.task_bucket, &ws.task_len, &ws.task_len_sorted, &ws.partials,
                    &ws.scalar_out, &ws.fold_cnt, &ws.fold_off, &ws.fold_bucket, &ws.fold_partials,
-                   &ws.aff_cnt, &ws.aff_off, &ws.aff_totals, &ws.aff_pts[0], &ws.aff_pts[1], &ws.aff_scratch};
+                   &ws.aff_cnt, &ws.aff_off, &ws.aff_totals, &ws.aff_pts[0], &ws.aff_pts[1], &ws.aff_scratch,
+                   &ws.merged_scalars};
   for (DevBuf *b : all) b->release();
   }
 }
 
-int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
+int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan, const MsmDedup *dedup) {
   if (n >= (1ull << 30)) return set_error(-2, "msm: n=%zu too large", n);
   if (plan.W == 0) B200_CHECK(msm_make_plan(n, false, plan));  // caller did not fix a plan: per-window buckets
   const int c = plan.c, W = plan.W;
@@ -268,8 +336,13 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan) {
   B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.windows.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   Timer tm(st);
 
-  // ---- digits + histogram
+  // ---- digits + histogram (after folding the scalars of equal bases into one representative each)
   tm.start();
+  if (dedup && dedup->merged) {
+    if (fr_tag == 0) B200_CHECK(msm_dedup_scalars<PrimeA>(d_scalars, n, *dedup, ws));
+    else B200_CHECK(msm_dedup_scalars<PrimeB>(d_scalars, n, *dedup, ws));
+    d_scalars = ws.merged_scalars.p;
+  }
   B200_CUDA_CHECK(cudaMemsetAsync(ws.counts.p, 0, nbuckets * sizeof(uint32_t), st));
   B200_CUDA_CHECK(cudaMemsetAsync(ws.cursor.p, 0, nbuckets * sizeof(uint32_t), st));
   if (fr_tag == 0)
@@ -454,7 +527,7 @@ int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const voi
 
 #define B200_DECL_G(name)                                                                                   \
   int msm_precompute_##name(const void *, size_t, MsmPlan &, DevBuf &);                                     \
-  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, std::function<void()> &, int);
+  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, std::function<void()> &, int, const MsmDedup *);
 B200_DECL_G(mnt4g1) B200_DECL_G(mnt4g2) B200_DECL_G(mnt6g1) B200_DECL_G(mnt6g2)
 #undef B200_DECL_G
 
@@ -466,11 +539,12 @@ int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
-                                const MsmPlan &plan, void *h_out, std::function<void()> &tail, int share_slot) {
-  if (curve == 0 && group == 1) return msm_run_table_deferred_mnt4g1(d_scalars, d_table, n, plan, h_out, tail, share_slot);
-  if (curve == 0 && group == 2) return msm_run_table_deferred_mnt4g2(d_scalars, d_table, n, plan, h_out, tail, share_slot);
-  if (curve == 1 && group == 1) return msm_run_table_deferred_mnt6g1(d_scalars, d_table, n, plan, h_out, tail, share_slot);
-  if (curve == 1 && group == 2) return msm_run_table_deferred_mnt6g2(d_scalars, d_table, n, plan, h_out, tail, share_slot);
+                                const MsmPlan &plan, void *h_out, std::function<void()> &tail, int share_slot,
+                                const MsmDedup *dedup) {
+  if (curve == 0 && group == 1) return msm_run_table_deferred_mnt4g1(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
+  if (curve == 0 && group == 2) return msm_run_table_deferred_mnt4g2(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
+  if (curve == 1 && group == 1) return msm_run_table_deferred_mnt6g1(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
+  if (curve == 1 && group == 2) return msm_run_table_deferred_mnt6g2(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 

@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 // scalars and window plan instead of repeating it (this MSM then only waits for that slot's prep_done event).
 template <class G>
 int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan, MsmWorkspace::Staging *&stage,
-                  int share_slot = -1) {
+                  int share_slot = -1, const MsmDedup *dedup = nullptr) {
   typedef typename G::F F;
   typedef typename G::ScalarPrime FrP;
   MsmWorkspace &ws = msm_workspace();
@@ -354,7 +354,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
     plan = *prep_ws->prepared;
     B200_CUDA_CHECK(cudaStreamWaitEvent(st, prep_ws->prep_done, 0));
   } else {
-    B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan));
+    B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan, dedup));
   }
   MsmWorkspace &pw = *prep_ws;  // owner of entries / offsets / task arrays
   const int W = plan.merged ? 1 : plan.W;  // number of independent bucket sets to reduce
@@ -650,7 +650,7 @@ int msm_precompute(const void *d_points, size_t n, MsmPlan &plan, DevBuf &table)
 // MSM over a table built by msm_precompute (plan must be the table's plan).
 template <class G>
 int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n, const MsmPlan &table_plan, void *h_out,
-                           std::function<void()> &tail, int share_slot) {
+                           std::function<void()> &tail, int share_slot, const MsmDedup *dedup) {
   typedef typename G::F F;
   if (n == 0) {
     Proj<F> zero;
@@ -661,7 +661,7 @@ int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n,
   }
   auto plan = std::make_shared<MsmPlan>(table_plan);
   MsmWorkspace::Staging *stage = nullptr;
-  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage, share_slot));
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage, share_slot, dedup));
   tail = [plan, stage, h_out]() {
     std::vector<Proj<F>> win;
     if (msm_collect<G>(*plan, stage, win) == 0) g_msm_phase_ms[4] = msm_host_phase<G>(*plan, win, h_out);

@@ -10,11 +10,34 @@
 namespace b200 {
 
 struct MsmPlan;
+// Equal bases inside one MSM's point range, found once per key (b200_params_precompute). sum s_i P = (sum s_i) P for the
+// members of a group (G1 has prime order r, so the scalar sum may be reduced mod r), hence before the digits are
+// extracted the members' scalars are added into the representative's and zeroed: the A query of every key made by
+// the reference's generator has m/2 copies of one point (pitfall 2) and costs half as much this way.
+// A group is cut into segments of <= kDedupSegment members so that one huge group is summed by many blocks.
+struct MsmDedup {
+  size_t merged = 0;      // bases folded into a representative (0: nothing to do)
+  uint32_t nsegments = 0, ngroups = 0;
+  DevBuf members;         // uint32[]: indices into the range, grouped, representative first
+  DevBuf segments;        // uint32[3 * nsegments]: first position in `members`, length, group
+  DevBuf groups;          // uint32[3 * ngroups]: representative, first segment, number of segments
+  DevBuf segment_sums;    // Fr[nsegments] scratch
+  void reset() {
+    merged = 0;
+    nsegments = ngroups = 0;
+    members.release();
+    segments.release();
+    groups.release();
+    segment_sums.release();
+  }
+};
+constexpr uint32_t kDedupSegment = 1024;
 struct MsmWorkspace {
   DevBuf digits, counts, offsets, cursor, entries, order, counts_sorted, iota, cub_tmp, buckets, red_a, red_b, plan;
   DevBuf ntasks, task_off, task_bucket, task_len, task_len_sorted, partials;
   DevBuf scalar_out, fold_cnt, fold_off, fold_bucket, fold_partials;  // fold_* hold two ping-pong halves
   DevBuf aff_cnt, aff_off, aff_totals, aff_pts[2], aff_scratch;        // batch-affine accumulation (msm_affine_*)
+  DevBuf merged_scalars;                                               // scalars after equal-base merging (MsmDedup)
   cudaStream_t stream = nullptr;   // every kernel of an MSM that uses this workspace runs on this stream
   // ring of pinned staging buffers + events for the asynchronous copy of the window sums to the host
   struct Staging {
@@ -56,7 +79,7 @@ extern double g_msm_phase_total[2][5];   // accumulated, [0] G1 calls, [1] G2 ca
 // Phase 1+2 (group independent): window plan, signed digits, histogram, counting sort of point indices by
 // (window, bucket), bucket visiting order by descending size. fr_tag: 0 = modulus A, 1 = modulus B.
 // plan.W == 0 on entry: choose a per-window plan for n. Otherwise the caller's plan (e.g. the one a table was built for).
-int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan);
+int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan, const MsmDedup *dedup = nullptr);
 int msm_make_plan(size_t n, bool merged, MsmPlan &plan);
 int msm_affine_levels(const uint32_t *counts, const uint32_t *offsets, uint32_t nbuckets, uint32_t max_count,
                       std::vector<size_t> &totals);
@@ -67,6 +90,7 @@ int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, ui
 // pre-shifted base tables (merged buckets), see msm_group.cuh
 int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n, MsmPlan &plan, DevBuf &table);
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
-                                const MsmPlan &plan, void *h_out, std::function<void()> &tail, int share_slot = -1);
+                                const MsmPlan &plan, void *h_out, std::function<void()> &tail, int share_slot = -1,
+                                const MsmDedup *dedup = nullptr);
 
 }  // namespace b200

@@ -411,3 +411,53 @@ def test_concurrent_proofs_match_reference_golden(b200, dev):
     assert b200.prove_batch(list(zip(keys[:2], inputs[:2]))) == expected[:2]
     for P in keys:
         P.close()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_equal_bases_are_merged_bit_exactly(b200, dev, curve):
+    """Key-load time merging of equal bases (MsmDedup): a query with one group larger than a segment (1024), a small
+    group, a pair, a duplicated point at infinity and scalars that cancel; table MSM (merging on) == table-free MSM."""
+    import torch
+    k = 12
+    m = 1 << k
+    g1, g2 = b200.affine_bytes(curve, 1), b200.affine_bytes(curve, 2)
+
+    def gen(group, n, first):
+        t = torch.empty(n * b200.affine_bytes(curve, group), dtype=torch.uint8, device=dev)
+        b200.check(b200.lib().b200_gen_points(curve, group, t.data_ptr(), n, first))
+        return t
+
+    A, B1, B2 = gen(1, m + 1, 11), gen(1, m + 1, 5000), gen(2, m + 1, 9000)
+    L, H = gen(1, m - 1, 13000), gen(1, m - 1, 17000)
+    Av = A.view(m + 1, g1)
+    Av[100:3100] = Av[7].clone()          # 3001 copies: three segments
+    Av[3200:3205] = Av[3300].clone()      # group of 6
+    Av[4000] = Av[4001].clone()           # a pair
+    Av[50] = 0
+    Av[51] = 0                            # two points at infinity
+    torch.cuda.synchronize()
+    key = b200.Params.from_device(curve, m - 1, m, A, B1, B2, L, H)
+    assert key.precompute() > 0
+    c = util.curve_obj(curve)
+    rng = random.Random(99 + curve)
+    scalars = [rng.randrange(c.r) for _ in range(m + 1)]
+    scalars[7] = (-sum(scalars[100:3100])) % c.r   # the big group sums to zero
+    scalars[3300] = 0
+    scalars[4000] = c.r - 1
+    sc = b200.to_device(b"".join(util.fe_bytes(M.to_mont(s, c.r)) for s in scalars))
+    got = b200.g_to_affine(curve, 1, key.msm(0, sc, m + 1))
+    exp = b200.g_to_affine(curve, 1, b200.msm(curve, 1, sc, A, m + 1))
+    assert got == exp
+    # and through a whole proof: tables (merging) vs table-free
+    g = torch.Generator(device="cpu").manual_seed(4321 + curve)
+    n_in = (m + 1) + 3 * m + 1
+    img = torch.randint(0, 256, (n_in, FE), dtype=torch.uint8, generator=g)
+    img[:, 94:] = 0
+    p1 = key.prove(img)
+    b200.set_precompute(False)
+    try:
+        p2 = key.prove(img)
+    finally:
+        b200.set_precompute(True)
+    assert p1 == p2
+    key.close()
