@@ -355,10 +355,11 @@ def b200_arm(args):
                                 if plans else None),
                 "issued_note": "IMAD.WIDE actually issued per point = windows x 10 multiplications x 1152, over the same time",
                 "windows": {("MNT4753" if c == 0 else "MNT6753") + ("_g2" if g2 else "_g1"): v for (c, g2), v in plans.items()},
-                "traffic": 15.06e9 + 15.63e9,
+                "traffic": 14.65e9 + 15.78e9,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-point launch, ncu --set full "
-                                "(profiles/prof_accumulate_g1_tables_r01_raw.csv); algorithmic: 36 windows x 2^20 x 192 B = 7.2 GB "
-                                "of table reads, the rest is per-thread stack traffic; 0.6 TB/s, far below the HBM roofline",
+                                "(profiles/prof_accumulate_g1_r01_v3_raw.csv); algorithmic: 36 windows x 2^20 x 192 B = 7.2 GB "
+                                "of table reads, the rest is per-thread stack traffic (field operands live in local memory); "
+                                "0.6 TB/s, far below the HBM roofline",
                 "launches": len(iso["g1"]), "avg_launch_ms": statistics.mean(g1_big) if g1_big else None,
                 "a_query_equal_bases_merged_ms": [round(t, 2) for _, _, t, _ in iso["a_merged"]],
                 "peak_source": "measured live by b200_imad_peak (IMAD.WIDE carry-chain microbenchmark on all SMs)",
@@ -370,7 +371,11 @@ def b200_arm(args):
     acc_ms_g2 = sum(t for _, _, t, _ in iso["g2"])
     roofline_g2 = {"kernel": "msm_accumulate_kernel<G2>", "achieved": g2_mac / (acc_ms_g2 / 1e3) / 1e12,
                    "peak": peak / 1e12, "unit": "TMAC32/s", "frac": (g2_mac / (acc_ms_g2 / 1e3)) / peak if peak else None,
-                   "launch_ms": [round(t, 2) for _, _, t, _ in iso["g2"]]}
+                   "launch_ms": [round(t, 2) for _, _, t, _ in iso["g2"]],
+                   "traffic": 147.5e9 + 228.1e9,
+                   "traffic_note": "2^20-point Fq2 launch (profiles/prof_accumulate_g2_r01_v3_raw.csv): 14.5 GB algorithmic; the "
+                                   "2.7 KB stack frames of 75 776 resident threads (205 MB) exceed the 126 MB L2, so operand "
+                                   "round trips reach DRAM at 2.4 TB/s - the reason the pipe is 85 % busy here vs 94 % for G1"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
