@@ -337,85 +337,14 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 }
 
 
-// GPU half of one MSM. Returns after the accumulation has finished and the (latency-bound) bucket reduction has been
-// ENQUEUED on the workspace's stream; the window sums arrive asynchronously in `stage` (wait on stage->done).
-// share_slot >= 0: reuse the scalar-side preparation (digits, sort, tasks) that workspace `share_slot` made for the SAME
-// scalars and window plan instead of repeating it (this MSM then only waits for that slot's prep_done event).
+// Bucket accumulation, default mode: one thread per task (XYZZ mixed additions), parallel fold of heavy buckets,
+// per-bucket combine of the task sums. `pw` owns the entry lists / task arrays (this MSM's workspace or the one it
+// shares its scalar preparation with). Nothing here waits on the host.
 template <class G>
-int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan, MsmWorkspace::Staging *&stage,
-                  int share_slot = -1, const MsmDedup *dedup = nullptr) {
+int msm_accumulate_xyzz(const void *d_points, const MsmPlan &plan, MsmWorkspace &ws, MsmWorkspace &pw) {
   typedef typename G::F F;
-  typedef typename G::ScalarPrime FrP;
-  MsmWorkspace &ws = msm_workspace();
   cudaStream_t st = ws.stream;
-  MsmWorkspace *prep_ws = &ws;
-  if (share_slot >= 0) {
-    prep_ws = &msm_workspace_slot(share_slot);
-    plan = *prep_ws->prepared;
-    B200_CUDA_CHECK(cudaStreamWaitEvent(st, prep_ws->prep_done, 0));
-  } else {
-    B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan, dedup));
-  }
-  MsmWorkspace &pw = *prep_ws;  // owner of entries / offsets / task arrays
-  const int W = plan.merged ? 1 : plan.W;  // number of independent bucket sets to reduce
-  const uint32_t nb = plan.nb;
   const size_t nbuckets = plan.nbuckets;
-  B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
-  stage = ws.next_staging((size_t)W * sizeof(Proj<F>));
-  if (!stage) return set_error(-5, "msm: pinned staging allocation failed");
-
-  B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
-  if (msm_use_batch_affine()) {
-    // ---- bucket accumulation by rounds of batched affine additions
-    std::vector<size_t> totals;
-    B200_CHECK(msm_affine_levels(pw.counts.as<uint32_t>(), pw.offsets.as<uint32_t>(), (uint32_t)nbuckets, plan.max_count, totals));
-    const int rounds = (int)totals.size() - 1;
-    const uint32_t *cnt = ws.aff_cnt.as<uint32_t>(), *off = ws.aff_off.as<uint32_t>();
-    AffineSource<F> src{(const Affine<F> *)d_points, pw.entries.as<uint32_t>(), nullptr};
-    for (int r = 1; r <= rounds; r++) {
-      const size_t total_out = totals[r];
-      if (total_out == 0) break;
-      // one full wave of resident threads per round: M = outputs per thread (>= 24 so that the shared inversion,
-      // ~60 multiplications' worth of ALU work, stays a small part of the 6 multiplications per addition)
-      static int wave = 0;
-      if (!wave) {
-        int per_sm = 0, dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_affine_round_kernel<G>, 128, 0);
-        wave = (per_sm > 0 ? per_sm : 1) * sms * 128;
-      }
-      uint32_t M = (uint32_t)((total_out + wave - 1) / wave);
-      M = M < 24 ? 24 : M;
-      const size_t nthreads = (total_out + M - 1) / M;
-      DevBuf &outbuf = ws.aff_pts[r & 1];
-      B200_CHECK(outbuf.reserve(total_out * sizeof(Affine<F>)));
-      B200_CHECK(ws.aff_scratch.reserve(nthreads * M * sizeof(F)));
-      msm_affine_round_kernel<G><<<grid_for(nthreads, 128), 128, 0, st>>>(
-          src, off + (size_t)(r - 1) * nbuckets, cnt + (size_t)(r - 1) * nbuckets, off + (size_t)r * nbuckets,
-          (uint32_t)nbuckets, (uint32_t)total_out, M, outbuf.as<Affine<F>>(), ws.aff_scratch.as<F>());
-      B200_CUDA_CHECK(cudaGetLastError());
-      note_launch();
-      src = AffineSource<F>{nullptr, nullptr, outbuf.as<Affine<F>>()};
-    }
-    msm_affine_finish_kernel<G><<<grid_for(nbuckets, 128), 128, 0, st>>>(
-        src, off + (size_t)rounds * nbuckets, cnt + (size_t)rounds * nbuckets, (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
-    B200_CUDA_CHECK(cudaGetLastError());
-    note_launch();
-    if (getenv("B200_AFF_DEBUG")) {
-      std::vector<Proj<F>> hb(nbuckets);
-      cudaStreamSynchronize(st);
-      cudaMemcpy(hb.data(), ws.buckets.p, nbuckets * sizeof(Proj<F>), cudaMemcpyDeviceToHost);
-      for (size_t b = 0; b < nbuckets && b < 8; b++) {
-        const uint32_t *w = (const uint32_t *)&hb[b];
-        printf("bucket %zu:", b);
-        for (size_t k = 0; k < sizeof(Proj<F>) / 4; k++) printf("%s%08x", k % 24 == 0 ? "\n  " : "", w[k / 24 * 24 + 23 - k % 24]);
-        printf("\n");
-      }
-    }
-  } else {
-  // ---- bucket accumulation: one thread per task, then per-bucket combine of the task sums. Nothing below waits
-  // on the host: the caller may already prepare the next MSM on the other stream.
   B200_CHECK(ws.partials.reserve((plan.ntasks ? plan.ntasks : 1) * sizeof(Proj<F>)));
   if (plan.ntasks) {
     msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128, 0, st>>>(
@@ -463,7 +392,83 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
                                                                  ws.buckets.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
+  return 0;
+}
+
+// Bucket accumulation, opt-in mode: rounds of batched affine additions (see msm_affine_round_kernel).
+template <class G>
+int msm_accumulate_batch_affine(const void *d_points, const MsmPlan &plan, MsmWorkspace &ws, MsmWorkspace &pw) {
+  typedef typename G::F F;
+  cudaStream_t st = ws.stream;
+  const size_t nbuckets = plan.nbuckets;
+  std::vector<size_t> totals;
+  B200_CHECK(msm_affine_levels(pw.counts.as<uint32_t>(), pw.offsets.as<uint32_t>(), (uint32_t)nbuckets, plan.max_count, totals));
+  const int rounds = (int)totals.size() - 1;
+  const uint32_t *cnt = ws.aff_cnt.as<uint32_t>(), *off = ws.aff_off.as<uint32_t>();
+  AffineSource<F> src{(const Affine<F> *)d_points, pw.entries.as<uint32_t>(), nullptr};
+  for (int r = 1; r <= rounds; r++) {
+    const size_t total_out = totals[r];
+    if (total_out == 0) break;
+    // one full wave of resident threads per round: M = outputs per thread (>= 24: the shared binary-gcd inversion
+    // costs as many instructions as ~48 additions, profiles/r01_v3_summary.md)
+    static int wave = 0;
+    if (!wave) {
+      int per_sm = 0, dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_affine_round_kernel<G>, 128, 0);
+      wave = (per_sm > 0 ? per_sm : 1) * sms * 128;
+    }
+    uint32_t M = (uint32_t)((total_out + wave - 1) / wave);
+    M = M < 24 ? 24 : M;
+    const size_t nthreads = (total_out + M - 1) / M;
+    DevBuf &outbuf = ws.aff_pts[r & 1];
+    B200_CHECK(outbuf.reserve(total_out * sizeof(Affine<F>)));
+    B200_CHECK(ws.aff_scratch.reserve(nthreads * M * sizeof(F)));
+    msm_affine_round_kernel<G><<<grid_for(nthreads, 128), 128, 0, st>>>(
+        src, off + (size_t)(r - 1) * nbuckets, cnt + (size_t)(r - 1) * nbuckets, off + (size_t)r * nbuckets,
+        (uint32_t)nbuckets, (uint32_t)total_out, M, outbuf.as<Affine<F>>(), ws.aff_scratch.as<F>());
+    B200_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    src = AffineSource<F>{nullptr, nullptr, outbuf.as<Affine<F>>()};
   }
+  msm_affine_finish_kernel<G><<<grid_for(nbuckets, 128), 128, 0, st>>>(
+      src, off + (size_t)rounds * nbuckets, cnt + (size_t)rounds * nbuckets, (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+// GPU half of one MSM. Returns after the accumulation has finished and the (latency-bound) bucket reduction has been
+// ENQUEUED on the workspace's stream; the window sums arrive asynchronously in `stage` (wait on stage->done).
+// share_slot >= 0: reuse the scalar-side preparation (digits, sort, tasks) that workspace `share_slot` made for the SAME
+// scalars and window plan instead of repeating it (this MSM then only waits for that slot's prep_done event).
+template <class G>
+int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan, MsmWorkspace::Staging *&stage,
+                  int share_slot = -1, const MsmDedup *dedup = nullptr) {
+  typedef typename G::F F;
+  typedef typename G::ScalarPrime FrP;
+  MsmWorkspace &ws = msm_workspace();
+  cudaStream_t st = ws.stream;
+  MsmWorkspace *prep_ws = &ws;
+  if (share_slot >= 0) {
+    prep_ws = &msm_workspace_slot(share_slot);
+    plan = *prep_ws->prepared;
+    B200_CUDA_CHECK(cudaStreamWaitEvent(st, prep_ws->prep_done, 0));
+  } else {
+    B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan, dedup));
+  }
+  MsmWorkspace &pw = *prep_ws;  // owner of entries / offsets / task arrays
+  const int W = plan.merged ? 1 : plan.W;  // number of independent bucket sets to reduce
+  const uint32_t nb = plan.nb;
+  const size_t nbuckets = plan.nbuckets;
+  B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
+  stage = ws.next_staging((size_t)W * sizeof(Proj<F>));
+  if (!stage) return set_error(-5, "msm: pinned staging allocation failed");
+
+  B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
+  if (msm_use_batch_affine()) B200_CHECK(msm_accumulate_batch_affine<G>(d_points, plan, ws, pw));
+  else B200_CHECK(msm_accumulate_xyzz<G>(d_points, plan, ws, pw));
 
   // ---- bucket reduction (enqueued, not awaited): chunks of K buckets, then tree sum per bucket set
   B200_CUDA_CHECK(cudaEventRecord(stage->t0, st));
