@@ -348,7 +348,7 @@ def b200_arm(args):
     acc_ms_g1 = sum(t for _, _, t, _ in iso["g1"])
     achieved = g1_mac / (acc_ms_g1 / 1e3)
     g1_big = [t for c, _, t, _ in iso["g1"] if c == 0]
-    roofline = {"bound": "imad (INT32 multiplier pipe; neither HBM nor tensor bound, SURVEY.md 8d)",
+    roofline = {"bound": "imad", "bound_note": "INT32 multiplier (IMAD.WIDE / fmaheavy) pipe; neither HBM nor tensor bound, SURVEY.md 8d",
                 "kernel": "msm_accumulate_kernel<G1>", "achieved": achieved / 1e12, "peak": peak / 1e12,
                 "unit": "TMAC32/s", "frac": achieved / peak if peak else None,
                 "frac_issued": (sum(plans[(c, False)]["windows"] * 10 * 1152 * n for c, n, _, _ in iso["g1"]) / (acc_ms_g1 / 1e3) / peak
@@ -431,7 +431,7 @@ def b200_arm(args):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_g2": roofline_g2,
-            "roofline_ntt": roofline_ntt, "proof_latency_s": {n: v["latency_s"] for n, v in per_curve.items()},
+            "roofline_ntt": roofline_ntt, "proof_pair_latency_s": ms_dev / args.steps / 1e3, "proof_latency_s": {n: v["latency_s"] for n, v in per_curve.items()},
             "per_curve": per_curve,
             "msm_points_per_s": {
                 "note": "one MSM alone on one GPU, accumulate + reduce phases, points of this rank's slice",

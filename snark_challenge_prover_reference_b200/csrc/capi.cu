@@ -532,7 +532,14 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   double t0 = now_ms();
   // w first (it drives four of the five MSMs); ca/cb/cc follow asynchronously on the default stream right before
   // compute_H, under the MSMs that are already running (truly asynchronous when the image is in pinned memory)
-  B200_CUDA_CHECK(cudaMemcpy(p->w.p, in, (m + 1) * 96, cudaMemcpyDefault));
+  // (a rank of a sharded proof only needs the part of w its slices of A/B1/B2 (w[i]) and L (w[i+2]) read)
+  {
+    const size_t n1 = m + 1, n3 = m - 1, one1 = n1 / (size_t)world, one3 = n3 / (size_t)world;
+    const size_t lo1 = (size_t)rank * one1, hi1 = rank == world - 1 ? n1 : lo1 + one1;
+    const size_t lo3 = (size_t)rank * one3 + 2, hi3 = (rank == world - 1 ? n3 : (size_t)rank * one3 + one3) + 2;
+    const size_t lo = std::min(lo1, lo3), hi = std::max(hi1, hi3);
+    B200_CUDA_CHECK(cudaMemcpy((char *)p->w.p + lo * 96, in + lo * 96, (hi - lo) * 96, cudaMemcpyDefault));
+  }
   double t1 = now_ms();
   const int curve = p->curve;
   const size_t g1a = affine_bytes(curve, 1), g2a = affine_bytes(curve, 2);
@@ -718,6 +725,10 @@ int b200_prove_batch(b200_proof_job *jobs, int count) {
   B200_CHECK(require_device());
   constexpr int kMaxJobs = 8;
   if (!jobs || count < 1 || count > kMaxJobs) return set_error(-1, "prove_batch: count %d not in [1, %d]", count, kMaxJobs);
+  for (int i = 0; i < count; i++)
+    for (int k = i + 1; k < count; k++)
+      if (jobs[i].key == jobs[k].key)
+        return set_error(-1, "prove_batch: jobs %d and %d use the same key object (its per-proof buffers are not shared)", i, k);
   static std::mutex pool_mu;
   static ProofWorker *pool[kMaxJobs] = {nullptr};  // leaked on purpose: the threads outlive static destruction
   std::lock_guard<std::mutex> g(pool_mu);          // one batch at a time

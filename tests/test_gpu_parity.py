@@ -409,6 +409,8 @@ def test_concurrent_proofs_match_reference_golden(b200, dev):
     with pytest.raises(b200.B200Error, match="proof job 1"):
         b200.prove_batch([(keys[0], inputs[0]), (keys[1], inputs[1][:-FE])])
     assert b200.prove_batch(list(zip(keys[:2], inputs[:2]))) == expected[:2]
+    with pytest.raises(b200.B200Error, match="same key"):
+        b200.prove_batch([(keys[0], inputs[0]), (keys[0], inputs[0])])
     for P in keys:
         P.close()
 
