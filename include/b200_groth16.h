@@ -170,6 +170,10 @@ int b200_msm_phase_totals(double *out10, int reset);
 int b200_msm_last_plan(int *out3);
 /* time of the last MSM phases (ms): 0 digits, 1 sort, 2 accumulate, 3 reduce, 4 host tail */
 int b200_msm_last_phase_ms(double *out5);
+/* diagnostics: begin != 0 marks t = 0 on the default stream; afterwards (begin == 0) out15[slot*3 + {0,1,2}] = ms at which
+ * the MSM issued on stream `slot` (issue order of b200_prove: B2, A, B1, L, H) started accumulating, started its
+ * bucket reduction and finished it. Single proof at a time. */
+int b200_prove_timeline(int begin, double *out15);
 
 #ifdef __cplusplus
 }

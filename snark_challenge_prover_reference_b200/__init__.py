@@ -87,6 +87,7 @@ _SIGNATURES = {
     "b200_msm_g1": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_msm_g2": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_prove_batch": (_i, [_vp, _i]),
+    "b200_prove_timeline": (_i, [_i, _vp]),
     "b200_msm_set_window": (_i, [_i]),
     "b200_msm_set_batch_affine": (_i, [_i]),
     "b200_msm_last_phase_ms": (_i, [ctypes.POINTER(ctypes.c_double)]),
@@ -374,6 +375,17 @@ def prove_batch(jobs, timings=False):
     check(lib().b200_prove_batch(ctypes.addressof(arr), len(jobs)))
     res = [o.raw[:a.out_bytes] for o, a in zip(outs, arr)]
     return (res, [a.timings.as_dict() for a in arr]) if timings else res
+
+
+def prove_timeline(begin=False):
+    """Diagnostics (b200_prove_timeline): begin=True marks t = 0; afterwards returns, per MSM in issue order
+    (B2, A, B1, L, H), the ms at which accumulation started, reduction started and reduction ended."""
+    if begin:
+        check(lib().b200_prove_timeline(1, None))
+        return None
+    out = (ctypes.c_double * 15)()
+    check(lib().b200_prove_timeline(0, ctypes.addressof(out)))
+    return {name: [round(out[i * 3 + k], 2) for k in range(3)] for i, name in enumerate(("B2", "A", "B1", "L", "H"))}
 
 
 def set_batch_affine(on):

@@ -341,6 +341,11 @@ int b200_msm_last_plan(int *out3) {
   msm_last_plan(out3);
   return 0;
 }
+int b200_prove_timeline(int begin, double *out15) {
+  if (begin) msm_timeline_begin();
+  else if (out15) msm_timeline_get(out15);
+  return 0;
+}
 int b200_msm_last_phase_ms(double *out5) {
   msm_last_phase_ms(out5);
   return 0;
@@ -557,7 +562,10 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   // The GPU half of each MSM runs here, back to back; the serial host halves (window combine, 753 doublings each)
   // run on worker threads while the next MSM occupies the GPU.
   // Issue order: B2 (G2, the longest), A, B1, L - all driven by w - each on its own stream; then compute_H on the
-  // default stream (it overlaps the MSMs already in flight), then the H MSM, which is fenced on the default stream.
+  // default stream, then the H MSM, which is fenced on the default stream. Measured alternatives (round 1,
+  // tools/profile_shard.py timelines): compute_H first on a high-priority stream, and short kernels / accumulations
+  // on separate high / low priority streams, both lengthen the proof (391 -> 407 / 411 ms): whatever runs beside an
+  // accumulation kernel takes register-file space from it for longer than it saves.
   const size_t outoff[5] = {0, g1p, 2 * g1p, 2 * g1p + g2p, 3 * g1p + g2p};
   const int order[5] = {2, 0, 1, 4, 3};
   std::vector<std::future<void>> tails;

@@ -47,6 +47,30 @@ void msm_phase_totals(double *out10, int reset) {
       if (reset) g_msm_phase_total[g][i] = 0;
     }
 }
+static cudaEvent_t g_timeline_base = nullptr;
+static double g_timeline[kMsmSlots][3];
+void msm_timeline_begin() {
+  if (!g_timeline_base) cudaEventCreate(&g_timeline_base);
+  cudaEventRecord(g_timeline_base, 0);
+  for (int s = 0; s < kMsmSlots; s++)
+    for (int k = 0; k < 3; k++) g_timeline[s][k] = -1;
+}
+void msm_timeline_note(int slot, cudaEvent_t ta, cudaEvent_t t0, cudaEvent_t t1) {
+  if (!g_timeline_base || slot < 0 || slot >= kMsmSlots) return;
+  cudaEvent_t ev[3] = {ta, t0, t1};
+  for (int k = 0; k < 3; k++) {
+    float ms = -1;
+    if (cudaEventElapsedTime(&ms, g_timeline_base, ev[k]) != cudaSuccess) {
+      cudaGetLastError();
+      ms = -1;
+    }
+    g_timeline[slot][k] = ms;
+  }
+}
+void msm_timeline_get(double *out15) {
+  for (int s = 0; s < kMsmSlots; s++)
+    for (int k = 0; k < 3; k++) out15[s * 3 + k] = g_timeline[s][k];
+}
 static int g_last_plan[3] = {0, 0, 0};
 void msm_last_plan(int *out3) {
   for (int i = 0; i < 3; i++) out3[i] = g_last_plan[i];
@@ -254,9 +278,12 @@ int msm_make_plan(size_t n, bool merged, MsmPlan &plan) {
   return 0;
 }
 
+static thread_local cudaStream_t g_input_stream = 0;
+void msm_set_input_stream(cudaStream_t st) { g_input_stream = st; }
 static thread_local bool g_high_priority = false;
 void msm_thread_high_priority(bool on) { g_high_priority = on; }
 static thread_local int g_slot = 0;
+int msm_current_slot() { return g_slot; }
 void msm_select_slot(int slot) { g_slot = ((slot % kMsmSlots) + kMsmSlots) % kMsmSlots; }
 static MsmWorkspace *workspace_slots() {
   static thread_local MsmWorkspace ws[kMsmSlots];
@@ -265,11 +292,23 @@ static MsmWorkspace *workspace_slots() {
 MsmWorkspace &msm_workspace_slot(int slot) {
   MsmWorkspace &ws = workspace_slots()[slot];
   if (!ws.stream) {
-    // streams of a worker thread of b200_prove_batch (the smaller proofs) outrank the caller's: their short kernels
-    // slot in as soon as an SM frees up instead of queueing behind the large proof's grids
+    // Default: one stream per MSM for all of its kernels (worker threads of b200_prove_batch - the smaller proofs -
+    // get high-priority streams so that they are not stuck behind the large proof's grids).
+    // B200_SPLIT_STREAMS=1 (experiment, slower: profiles/r01_v3_summary.md): short kernels on a high-priority stream,
+    // all accumulations of the thread on ONE low-priority stream.
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
-    cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, g_high_priority ? greatest : least);
+    static const bool split = getenv("B200_SPLIT_STREAMS") && getenv("B200_SPLIT_STREAMS")[0] == '1';
+    if (split) {
+      cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, greatest);
+      static thread_local cudaStream_t acc = nullptr;
+      if (!acc) cudaStreamCreateWithPriority(&acc, cudaStreamNonBlocking, g_high_priority ? (least + greatest) / 2 : least);
+      ws.acc_stream = acc;
+    } else {
+      cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, g_high_priority ? greatest : least);
+      ws.acc_stream = ws.stream;
+    }
+    cudaEventCreateWithFlags(&ws.acc_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ws.prep_done, cudaEventDisableTiming);
     ws.prepared = new MsmPlan();
   }
@@ -321,7 +360,7 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan, cons
     // inputs are produced on the default stream (copies, compute_H, generators): order this MSM after it
     static thread_local cudaEvent_t fence = nullptr;
     if (!fence) B200_CUDA_CHECK(cudaEventCreateWithFlags(&fence, cudaEventDisableTiming));
-    B200_CUDA_CHECK(cudaEventRecord(fence, 0));
+    B200_CUDA_CHECK(cudaEventRecord(fence, g_input_stream));
     B200_CUDA_CHECK(cudaStreamWaitEvent(st, fence, 0));
   }
   B200_CHECK(ws.digits.reserve((size_t)W * n * sizeof(int32_t)));

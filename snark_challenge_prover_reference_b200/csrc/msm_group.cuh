@@ -346,14 +346,19 @@ int msm_accumulate_xyzz(const void *d_points, const MsmPlan &plan, MsmWorkspace 
   cudaStream_t st = ws.stream;
   const size_t nbuckets = plan.nbuckets;
   B200_CHECK(ws.partials.reserve((plan.ntasks ? plan.ntasks : 1) * sizeof(Proj<F>)));
+  // the long kernel goes to the low-priority stream, fenced on both sides: after the entry lists / task arrays are
+  // ready (pw.prep_done; for an own preparation also everything queued before it on `st`), before fold / combine
+  B200_CUDA_CHECK(cudaStreamWaitEvent(ws.acc_stream, pw.prep_done, 0));
   if (plan.ntasks) {
-    msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128, 0, st>>>(
+    msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128, 0, ws.acc_stream>>>(
         (const Affine<F> *)d_points, pw.entries.as<uint32_t>(), pw.offsets.as<uint32_t>(), pw.task_off.as<uint32_t>(),
         pw.task_bucket.as<uint32_t>(), pw.task_len_sorted.as<uint32_t>(), pw.order.as<uint32_t>(),
         (uint32_t)plan.ntasks, plan.task_len, ws.partials.as<Proj<F>>());
     B200_CUDA_CHECK(cudaGetLastError());
     note_launch();
   }
+  B200_CUDA_CHECK(cudaEventRecord(ws.acc_done, ws.acc_stream));
+  B200_CUDA_CHECK(cudaStreamWaitEvent(st, ws.acc_done, 0));
   // skewed scalars: fold the task sums of heavy buckets in parallel until no bucket has more than kFoldWidth of them
   const Proj<F> *sums = ws.partials.as<Proj<F>>();
   const uint32_t *sum_bucket = pw.task_bucket.as<uint32_t>(), *sum_off = pw.task_off.as<uint32_t>(),
@@ -465,10 +470,16 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
   stage = ws.next_staging((size_t)W * sizeof(Proj<F>));
   if (!stage) return set_error(-5, "msm: pinned staging allocation failed");
+  stage->slot = msm_current_slot();
 
-  B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
-  if (msm_use_batch_affine()) B200_CHECK(msm_accumulate_batch_affine<G>(d_points, plan, ws, pw));
-  else B200_CHECK(msm_accumulate_xyzz<G>(d_points, plan, ws, pw));
+  if (msm_use_batch_affine()) {
+    B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
+    B200_CHECK(msm_accumulate_batch_affine<G>(d_points, plan, ws, pw));
+  } else {
+    B200_CUDA_CHECK(cudaStreamWaitEvent(ws.acc_stream, pw.prep_done, 0));
+    B200_CUDA_CHECK(cudaEventRecord(stage->ta, ws.acc_stream));
+    B200_CHECK(msm_accumulate_xyzz<G>(d_points, plan, ws, pw));
+  }
 
   // ---- bucket reduction (enqueued, not awaited): chunks of K buckets, then tree sum per bucket set
   B200_CUDA_CHECK(cudaEventRecord(stage->t0, st));
@@ -517,6 +528,7 @@ int msm_collect(const MsmPlan &plan, MsmWorkspace::Staging *stage, std::vector<P
   g_msm_phase_ms[2] = ms;
   g_msm_phase_total[F::kDegree == 1 ? 0 : 1][2] += ms;
   cudaEventElapsedTime(&ms, stage->t0, stage->t1);
+  msm_timeline_note(stage->slot, stage->ta, stage->t0, stage->t1);
   g_msm_phase_ms[3] = ms;
   g_msm_phase_total[F::kDegree == 1 ? 0 : 1][3] += ms;
   return 0;

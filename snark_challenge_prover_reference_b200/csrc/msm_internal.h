@@ -38,13 +38,19 @@ struct MsmWorkspace {
   DevBuf scalar_out, fold_cnt, fold_off, fold_bucket, fold_partials;  // fold_* hold two ping-pong halves
   DevBuf aff_cnt, aff_off, aff_totals, aff_pts[2], aff_scratch;        // batch-affine accumulation (msm_affine_*)
   DevBuf merged_scalars;                                               // scalars after equal-base merging (MsmDedup)
-  cudaStream_t stream = nullptr;   // every kernel of an MSM that uses this workspace runs on this stream
+  // Two streams per MSM: `stream` (HIGH priority) carries the short, latency-bound kernels - digits, counting sort,
+  // task lists, fold/combine, bucket reduction, tree sums; `acc_stream` (LOW priority) carries the long accumulation
+  // kernel. The block scheduler serves pending blocks of high-priority streams first, so the latency-bound phases of
+  // one MSM (and compute_H) run in the slots that free up while another MSM's accumulation saturates the multiplier.
+  cudaStream_t stream = nullptr, acc_stream = nullptr;
+  cudaEvent_t acc_done = nullptr;
   // ring of pinned staging buffers + events for the asynchronous copy of the window sums to the host
   struct Staging {
     void *pinned = nullptr;
     size_t bytes = 0;
     cudaEvent_t done = nullptr;
     cudaEvent_t ta = nullptr, t0 = nullptr, t1 = nullptr;  // accumulate starts at ta, reduce spans t0..t1
+    int slot = 0;                                           // workspace slot that issued it (timeline diagnostics)
   } ring[4];
   int ring_pos = 0;
   Staging *next_staging(size_t bytes);
@@ -60,6 +66,10 @@ constexpr int kMsmSlots = 5;
 MsmWorkspace &msm_workspace();
 MsmWorkspace &msm_workspace_slot(int slot);
 void msm_select_slot(int slot);
+int msm_current_slot();
+// MSMs prepared by the calling host thread wait for work already enqueued on this stream (the producer of their
+// scalars: copies, compute_H). Default: the legacy default stream.
+void msm_set_input_stream(cudaStream_t st);
 
 struct MsmPlan {
   int c = 0, W = 0;
@@ -73,6 +83,11 @@ struct MsmPlan {
   uint32_t max_count = 0;             // largest bucket (set by msm_prepare)
 };
 
+// Diagnostics: when a base event has been set (msm_timeline_begin), msm_collect stores for the issuing slot the times
+// (ms since the base) at which the accumulation started, the reduction started and the reduction ended.
+void msm_timeline_begin();
+void msm_timeline_note(int slot, cudaEvent_t ta, cudaEvent_t t0, cudaEvent_t t1);
+void msm_timeline_get(double *out15);
 extern double g_msm_phase_ms[5];         // last call: digits, sort, accumulate, reduce, host tail
 extern double g_msm_phase_total[2][5];   // accumulated, [0] G1 calls, [1] G2 calls
 

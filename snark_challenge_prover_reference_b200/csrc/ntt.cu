@@ -19,6 +19,11 @@
 
 namespace b200 {
 
+// stream of every launch below for the calling host thread (default: the legacy default stream, which is what the
+// public domain_* entry points promise; b200_prove* put compute_H on a high-priority stream of their own)
+static thread_local cudaStream_t g_ntt_stream = 0;
+void ntt_set_stream(cudaStream_t st) { g_ntt_stream = st; }
+
 // ---------------------------------------------------------------------------------------------- kernels
 template <class P>
 __global__ void __launch_bounds__(128) powers_kernel(Fp<P> *__restrict__ out, size_t n, const Fp<P> *__restrict__ base_p,
@@ -245,13 +250,13 @@ static int transform(Domain *d, void *d_a, int kind) {
     size_t smem = (size_t)kLimbs * ((1u << r) + 1) * sizeof(uint32_t);
     unsigned threads = 1u << (r - 1);
     size_t blocks = (size_t)1 << (k - r);
-    ntt_pass_kernel<P><<<(unsigned)blocks, threads, smem>>>(src, dst, k, s0, r, tw, p == 0 ? 1 : 0, p == 0 ? pre : nullptr,
+    ntt_pass_kernel<P><<<(unsigned)blocks, threads, smem, g_ntt_stream>>>(src, dst, k, s0, r, tw, p == 0 ? 1 : 0, p == 0 ? pre : nullptr,
                                                             last ? post_tab : nullptr, last ? post_const : nullptr);
     B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
     s0 += r;
   }
-  if (npass == 1) B200_CUDA_CHECK(cudaMemcpyAsync(a, scr, d->m * sizeof(F), cudaMemcpyDeviceToDevice, 0));
+  if (npass == 1) B200_CUDA_CHECK(cudaMemcpyAsync(a, scr, d->m * sizeof(F), cudaMemcpyDeviceToDevice, g_ntt_stream));
   return 0;
 }
 
@@ -261,7 +266,7 @@ int domain_transform(Domain *d, void *d_a, int kind) {
 
 template <class P>
 static int scale_by(Domain *d, void *d_a, int which) {
-  fr_scale_kernel<P><<<grid_for(d->m, 128), 128>>>((Fp<P> *)d_a, d->consts.as<Fp<P>>() + which, d->m);
+  fr_scale_kernel<P><<<grid_for(d->m, 128), 128, 0, g_ntt_stream>>>((Fp<P> *)d_a, d->consts.as<Fp<P>>() + which, d->m);
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
   return 0;
@@ -273,9 +278,9 @@ int domain_divide_by_z(Domain *d, void *d_a) {
 int fr_muleq(int curve, void *d_a, const void *d_b, size_t n) {
   if (n == 0) return 0;
   if (curve == 0)
-    fr_muleq_kernel<PrimeA><<<grid_for(n, 128), 128>>>((Fp<PrimeA> *)d_a, (const Fp<PrimeA> *)d_b, n);
+    fr_muleq_kernel<PrimeA><<<grid_for(n, 128), 128, 0, g_ntt_stream>>>((Fp<PrimeA> *)d_a, (const Fp<PrimeA> *)d_b, n);
   else
-    fr_muleq_kernel<PrimeB><<<grid_for(n, 128), 128>>>((Fp<PrimeB> *)d_a, (const Fp<PrimeB> *)d_b, n);
+    fr_muleq_kernel<PrimeB><<<grid_for(n, 128), 128, 0, g_ntt_stream>>>((Fp<PrimeB> *)d_a, (const Fp<PrimeB> *)d_b, n);
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
   return 0;
@@ -283,9 +288,9 @@ int fr_muleq(int curve, void *d_a, const void *d_b, size_t n) {
 int fr_subeq(int curve, void *d_a, const void *d_b, size_t n) {
   if (n == 0) return 0;
   if (curve == 0)
-    fr_subeq_kernel<PrimeA><<<grid_for(n, 128), 128>>>((Fp<PrimeA> *)d_a, (const Fp<PrimeA> *)d_b, n);
+    fr_subeq_kernel<PrimeA><<<grid_for(n, 128), 128, 0, g_ntt_stream>>>((Fp<PrimeA> *)d_a, (const Fp<PrimeA> *)d_b, n);
   else
-    fr_subeq_kernel<PrimeB><<<grid_for(n, 128), 128>>>((Fp<PrimeB> *)d_a, (const Fp<PrimeB> *)d_b, n);
+    fr_subeq_kernel<PrimeB><<<grid_for(n, 128), 128, 0, g_ntt_stream>>>((Fp<PrimeB> *)d_a, (const Fp<PrimeB> *)d_b, n);
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
   return 0;
@@ -304,8 +309,8 @@ int compute_h(Domain *d, void *d_ca, void *d_cb, void *d_cc, void *d_out) {
   B200_CHECK(fr_subeq(d->curve, d_ca, d_cc, m));
   B200_CHECK(domain_divide_by_z(d, d_ca));
   B200_CHECK(domain_transform(d, d_ca, kInverseCoset));
-  B200_CUDA_CHECK(cudaMemcpyAsync(d_out, d_ca, m * 96, cudaMemcpyDeviceToDevice, 0));
-  B200_CUDA_CHECK(cudaMemsetAsync((char *)d_out + m * 96, 0, 96, 0));
+  B200_CUDA_CHECK(cudaMemcpyAsync(d_out, d_ca, m * 96, cudaMemcpyDeviceToDevice, g_ntt_stream));
+  B200_CUDA_CHECK(cudaMemsetAsync((char *)d_out + m * 96, 0, 96, g_ntt_stream));
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // Host-callable entry points of ntt.cu (internal; the public surface is include/b200_groth16.h).
 #pragma once
 #include <stddef.h>
+#include <cuda_runtime.h>
 namespace b200 {
 struct Domain;
 int domain_create(int curve, size_t m, Domain **out);
@@ -14,4 +15,6 @@ int domain_divide_by_z(Domain *d, void *d_a);
 int fr_muleq(int curve, void *d_a, const void *d_b, size_t n);
 int fr_subeq(int curve, void *d_a, const void *d_b, size_t n);
 int compute_h(Domain *d, void *d_ca, void *d_cb, void *d_cc, void *d_out);
+// stream used by the transforms / point-wise kernels issued from the calling host thread (0 = legacy default)
+void ntt_set_stream(cudaStream_t st);
 }  // namespace b200

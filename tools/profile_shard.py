@@ -14,7 +14,8 @@ print("precompute s:", key.precompute(0, world))
 inp = bench.make_input(torch, curve, k, 5)
 for _ in range(reps):
     torch.cuda.synchronize(); t0 = time.time()
+    b.prove_timeline(begin=True)
     part, tm = key.prove_partial(inp, 0, world)
     print(round((time.time() - t0) * 1e3, 2), "ms", {a: round(v, 2) for a, v in tm.items()})
     print("  last msm:", {a: round(v, 2) for a, v in b.msm_phase_ms().items()}, b.msm_last_plan())
-    print("  totals:", {a: round(v, 2) for a, v in b.msm_phase_totals().items()} if hasattr(b, "msm_phase_totals") else "")
+    print("  timeline (ms since start: accumulate starts, reduce starts, reduce ends):", b.prove_timeline())
