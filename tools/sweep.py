@@ -38,7 +38,7 @@ def main():
                     print(json.dumps({"kind": "msm", "curve": b.CURVE_NAMES[curve], "log2n": lg, "tables": True,
                                       "skipped": "tables for all five queries do not fit: " + str(e)[-60:]}), flush=True)
                     continue
-                for which, group in ((0, 1), (2, 2)):
+                for which, group in ((1, 1), (2, 2)):  # B1 and B2 queries (the A query's equal bases would be merged)
                     best = None
                     for _ in range(3):
                         torch.cuda.synchronize()
