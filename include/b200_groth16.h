@@ -170,6 +170,11 @@ int b200_msm_phase_totals(double *out10, int reset);
 int b200_msm_last_plan(int *out3);
 /* time of the last MSM phases (ms): 0 digits, 1 sort, 2 accumulate, 3 reduce, 4 host tail */
 int b200_msm_last_phase_ms(double *out5);
+/* test hook (host only, no GPU): the key-load-time grouping of equal bases. members: indices grouped, representative
+ * first; groups: (representative, first segment, number of segments) triples; *n_members / *n_groups: capacity in,
+ * count out (u32 words); *merged: bases folded into a representative. Points at infinity are never grouped. */
+int b200_host_equal_bases(const void *h_points, size_t n, size_t point_bytes, uint32_t *members, size_t *n_members,
+                          uint32_t *groups, size_t *n_groups, size_t *merged);
 /* diagnostics: begin != 0 marks t = 0 on the default stream; afterwards (begin == 0) out15[slot*3 + {0,1,2}] = ms at which
  * the MSM issued on stream `slot` (issue order of b200_prove: B2, A, B1, L, H) started accumulating, started its
  * bucket reduction and finished it. Single proof at a time. */

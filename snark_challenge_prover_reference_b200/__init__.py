@@ -88,6 +88,7 @@ _SIGNATURES = {
     "b200_msm_g2": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_prove_batch": (_i, [_vp, _i]),
     "b200_prove_timeline": (_i, [_i, _vp]),
+    "b200_host_equal_bases": (_i, [_vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "b200_msm_set_window": (_i, [_i]),
     "b200_msm_set_batch_affine": (_i, [_i]),
     "b200_msm_last_phase_ms": (_i, [ctypes.POINTER(ctypes.c_double)]),
@@ -375,6 +376,27 @@ def prove_batch(jobs, timings=False):
     check(lib().b200_prove_batch(ctypes.addressof(arr), len(jobs)))
     res = [o.raw[:a.out_bytes] for o, a in zip(outs, arr)]
     return (res, [a.timings.as_dict() for a in arr]) if timings else res
+
+
+def host_equal_bases(points, n, point_bytes):
+    """Host-side grouping of equal bases (test hook, needs no GPU): returns (merged, [[rep, member, ...], ...])."""
+    cap = ctypes.c_size_t(n)
+    gcap = ctypes.c_size_t(3 * n)
+    members = (ctypes.c_uint32 * max(n, 1))()
+    groups = (ctypes.c_uint32 * max(3 * n, 1))()
+    merged = ctypes.c_size_t()
+    buf = ctypes.create_string_buffer(bytes(points), len(points))
+    check(lib().b200_host_equal_bases(ctypes.addressof(buf), n, point_bytes, ctypes.addressof(members), ctypes.byref(cap),
+                                      ctypes.addressof(groups), ctypes.byref(gcap), ctypes.byref(merged)))
+    # every group's members are contiguous in `members`, representative first, groups in the order of `groups`
+    reps = [groups[3 * g] for g in range(gcap.value // 3)]
+    out = []
+    for i in members[:cap.value]:
+        if len(out) < len(reps) and i == reps[len(out)]:
+            out.append([i])
+        else:
+            out[-1].append(i)
+    return merged.value, out
 
 
 def prove_timeline(begin=False):

@@ -156,16 +156,19 @@ static bool use_precompute() {
 // Equal bases of one G1 point range (key-load time, host): 64-bit hash of the 192 wire bytes, sort, confirm with memcmp.
 // Only worth a separate scalar pass when a sizeable part of the range folds away (the A query: m/2 of m+1 bases);
 // a stray duplicate pair (B1, B2) is left to the P+P branch of the bucket accumulation.
-static int find_equal_bases(const void *d_points, size_t n, size_t point_bytes, MsmDedup &dd) {
-  dd.reset();
-  if (n < 8) return 0;
-  std::vector<unsigned char> pts(n * point_bytes);
-  B200_CUDA_CHECK(cudaMemcpy(pts.data(), d_points, pts.size(), cudaMemcpyDeviceToHost));
+// host part: groups of equal points in `pts` (n wire-format points). members: indices grouped, representative first;
+// segments: (first position in members, length, group) triples; groups: (representative, first segment, #segments)
+// triples. Returns the number of bases folded away. Points at infinity (y == 0) are never grouped: the kernels skip them.
+static size_t group_equal_bases(const unsigned char *pts, size_t n, size_t point_bytes, std::vector<uint32_t> &members,
+                                std::vector<uint32_t> &segments, std::vector<uint32_t> &groups) {
+  members.clear();
+  segments.clear();
+  groups.clear();
   std::vector<std::pair<uint64_t, uint32_t>> keyed;
   keyed.reserve(n);
   for (size_t i = 0; i < n; i++) {
-    const unsigned char *q = pts.data() + i * point_bytes;
-    bool inf = true;  // y == 0 encodes O: skipped by the kernels anyway
+    const unsigned char *q = pts + i * point_bytes;
+    bool inf = true;
     for (size_t k = point_bytes / 2; k < point_bytes && inf; k++) inf = q[k] == 0;
     if (inf) continue;
     uint64_t h = 0xcbf29ce484222325ull;
@@ -178,18 +181,17 @@ static int find_equal_bases(const void *d_points, size_t n, size_t point_bytes, 
     keyed.emplace_back(h, (uint32_t)i);
   }
   std::sort(keyed.begin(), keyed.end());
-  std::vector<uint32_t> members, segments, groups;
   size_t merged = 0;
   for (size_t a = 0; a < keyed.size();) {
     size_t b = a + 1;
     while (b < keyed.size() && keyed[b].first == keyed[a].first) b++;
     if (b - a >= 2) {
       // members of the run that really equal its first element (a hash collision just stays unmerged)
-      const unsigned char *rep = pts.data() + (size_t)keyed[a].second * point_bytes;
+      const unsigned char *rep = pts + (size_t)keyed[a].second * point_bytes;
       const size_t first = members.size();
       members.push_back(keyed[a].second);
       for (size_t k = a + 1; k < b; k++)
-        if (memcmp(rep, pts.data() + (size_t)keyed[k].second * point_bytes, point_bytes) == 0)
+        if (memcmp(rep, pts + (size_t)keyed[k].second * point_bytes, point_bytes) == 0)
           members.push_back(keyed[k].second);
       const size_t len = members.size() - first;
       if (len < 2) {
@@ -209,6 +211,16 @@ static int find_equal_bases(const void *d_points, size_t n, size_t point_bytes, 
     }
     a = b;
   }
+  return merged;
+}
+
+static int find_equal_bases(const void *d_points, size_t n, size_t point_bytes, MsmDedup &dd) {
+  dd.reset();
+  if (n < 8) return 0;
+  std::vector<unsigned char> pts(n * point_bytes);
+  B200_CUDA_CHECK(cudaMemcpy(pts.data(), d_points, pts.size(), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> members, segments, groups;
+  const size_t merged = group_equal_bases(pts.data(), n, point_bytes, members, segments, groups);
   if (merged < std::max<size_t>(4, n / 32)) return 0;
   dd.nsegments = (uint32_t)(segments.size() / 3);
   dd.ngroups = (uint32_t)(groups.size() / 3);
@@ -339,6 +351,18 @@ int b200_msm_phase_totals(double *out5, int reset) {
 }
 int b200_msm_last_plan(int *out3) {
   msm_last_plan(out3);
+  return 0;
+}
+int b200_host_equal_bases(const void *h_points, size_t n, size_t point_bytes, uint32_t *members, size_t *n_members,
+                          uint32_t *groups, size_t *n_groups, size_t *merged) {
+  if (!h_points || point_bytes == 0 || point_bytes % 16) return set_error(-1, "equal_bases: bad arguments");
+  std::vector<uint32_t> m, s, g;
+  const size_t folded = group_equal_bases((const unsigned char *)h_points, n, point_bytes, m, s, g);
+  if (members && n_members && *n_members >= m.size()) memcpy(members, m.data(), m.size() * 4);
+  if (groups && n_groups && *n_groups >= g.size()) memcpy(groups, g.data(), g.size() * 4);
+  if (n_members) *n_members = m.size();
+  if (n_groups) *n_groups = g.size();
+  if (merged) *merged = folded;
   return 0;
 }
 int b200_prove_timeline(int begin, double *out15) {

@@ -90,3 +90,27 @@ def test_compute_fails_loudly_without_gpu(b200):
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
     with pytest.raises(b200.B200Error):
         b200.msm(0, 1, 0, 0, 4)
+
+
+def test_equal_bases_are_grouped_on_the_host(b200):
+    """Key-load-time grouping behind the MSM's equal-base merging (host only): one big group spanning several
+    1024-member segments, a pair, points at infinity that must stay ungrouped, everything else distinct."""
+    import random
+    rng = random.Random(5)
+    pb, n = 192, 5000
+    pts = [bytes(rng.randrange(256) for _ in range(pb)) for _ in range(n)]
+    big = list(range(100, 3000, 1)) + [4000, 4999]
+    for i in big:
+        pts[i] = pts[7]
+    pts[3500] = pts[3600]
+    inf = pts[1][:pb // 2] + bytes(pb // 2)          # y == 0: the point at infinity, twice
+    pts[1] = inf
+    pts[2] = inf
+    merged, groups = b200.host_equal_bases(b"".join(pts), n, pb)
+    as_sets = sorted((sorted(g) for g in groups), key=len)
+    assert as_sets == [[3500, 3600], sorted([7] + big)]
+    assert merged == len(big) + 1
+    assert all(g[0] == min(g) or g[0] in g for g in groups)
+    # nothing to merge
+    merged, groups = b200.host_equal_bases(b"".join(pts[3601:3700]), 99, pb)
+    assert merged == 0 and groups == []
