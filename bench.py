@@ -407,6 +407,9 @@ def b200_arm(args):
                     "frac": (ch_bytes / (ch_ms / 1e3) / 1e9) / hbm_peak if ch_ms else None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
                     "ms_per_step": ch_ms / args.steps,
+                    "traffic": 717e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the three passes of ONE 2^20 "
+                    "transform (ncu --set full, profiles/prof_ntt_r01_v3_raw.csv) vs 201 MB algorithmic per transform (603 MB "
+                    "for three read-write sweeps); fmaheavy pipe 80 % busy",
                     "imad_frac": (args.steps * sum((7 * 588 * k + 4 * 1176) * (1 << k) for _, k in shapes) / (ch_ms / 1e3)) / peak if ch_ms else None,
                     "note": "753-bit butterflies are IMAD-bound (588 MAC32 per 96 B element-stage, 61 MAC32/byte): imad_frac is "
                             "the fraction of the measured IMAD.WIDE peak, the binding roofline; see DESIGN.md 4.3"}
