@@ -31,6 +31,16 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _product_library_is_built():
+    """Tests that spawn worker processes import the package on their own: make sure the in-tree library exists before
+    anything runs (a fresh checkout has no build artefacts; nvcc cross-compiles without a GPU)."""
+    import snark_challenge_prover_reference_b200 as b
+    if not os.path.exists(b.LIB_PATH):
+        from snark_challenge_prover_reference_b200 import build as _b
+        _b.build()
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """CPU oracle (C restatement of the reference). Test infrastructure only."""
