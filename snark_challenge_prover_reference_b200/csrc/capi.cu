@@ -144,7 +144,7 @@ struct b200_params {
   Precomputed pre;
 };
 
-static int g_use_precompute = -1;  // -1: read B200_PRECOMPUTE from the environment (default on)
+static std::atomic<int> g_use_precompute{-1};  // -1: read B200_PRECOMPUTE from the environment (default on)
 static bool use_precompute() {
   if (g_use_precompute < 0) {
     const char *e = getenv("B200_PRECOMPUTE");

@@ -26,11 +26,11 @@
 
 namespace b200 {
 
-double g_msm_phase_ms[5] = {0, 0, 0, 0, 0};
-double g_msm_phase_total[2][5];
-static int g_forced_window = 0;
+std::atomic<double> g_msm_phase_ms[5];
+std::atomic<double> g_msm_phase_total[2][5];
+static std::atomic<int> g_forced_window{0};
 // B200_BATCH_AFFINE=1: bucket accumulation by rounds of batched affine additions (experimental, see msm_group.cuh)
-static int g_batch_affine = -1;  // -1: take B200_BATCH_AFFINE from the environment on first use
+static std::atomic<int> g_batch_affine{-1};  // -1: take B200_BATCH_AFFINE from the environment on first use
 bool msm_use_batch_affine() {
   if (g_batch_affine < 0) {
     const char *e = getenv("B200_BATCH_AFFINE");
@@ -48,7 +48,7 @@ void msm_phase_totals(double *out10, int reset) {
     }
 }
 static cudaEvent_t g_timeline_base = nullptr;
-static double g_timeline[kMsmSlots][3];
+static std::atomic<double> g_timeline[kMsmSlots][3];
 void msm_timeline_begin() {
   if (!g_timeline_base) cudaEventCreate(&g_timeline_base);
   cudaEventRecord(g_timeline_base, 0);
@@ -71,7 +71,7 @@ void msm_timeline_get(double *out15) {
   for (int s = 0; s < kMsmSlots; s++)
     for (int k = 0; k < 3; k++) out15[s * 3 + k] = g_timeline[s][k];
 }
-static int g_last_plan[3] = {0, 0, 0};
+static std::atomic<int> g_last_plan[3];
 void msm_last_plan(int *out3) {
   for (int i = 0; i < 3; i++) out3[i] = g_last_plan[i];
 }

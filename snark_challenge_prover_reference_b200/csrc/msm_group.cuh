@@ -511,7 +511,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   B200_CUDA_CHECK(cudaMemcpyAsync(stage->pinned, cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost, st));
   B200_CUDA_CHECK(cudaEventRecord(stage->t1, st));
   B200_CUDA_CHECK(cudaEventRecord(stage->done, st));
-  for (int i = 0; i < 2; i++) g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i] += g_msm_phase_ms[i];
+  for (int i = 0; i < 2; i++) msm_stat_add(g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i], g_msm_phase_ms[i]);
   return 0;
 }
 
@@ -526,11 +526,11 @@ int msm_collect(const MsmPlan &plan, MsmWorkspace::Staging *stage, std::vector<P
   float ms = 0;
   cudaEventElapsedTime(&ms, stage->ta, stage->t0);
   g_msm_phase_ms[2] = ms;
-  g_msm_phase_total[F::kDegree == 1 ? 0 : 1][2] += ms;
+  msm_stat_add(g_msm_phase_total[F::kDegree == 1 ? 0 : 1][2], ms);
   cudaEventElapsedTime(&ms, stage->t0, stage->t1);
   msm_timeline_note(stage->slot, stage->ta, stage->t0, stage->t1);
   g_msm_phase_ms[3] = ms;
-  g_msm_phase_total[F::kDegree == 1 ? 0 : 1][3] += ms;
+  msm_stat_add(g_msm_phase_total[F::kDegree == 1 ? 0 : 1][3], ms);
   return 0;
 }
 
@@ -566,7 +566,7 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, plan, stage));
   B200_CHECK(msm_collect<G>(plan, stage, win));
   g_msm_phase_ms[4] = msm_host_phase<G>(plan, win, h_out);
-  g_msm_phase_total[F::kDegree == 1 ? 0 : 1][4] += g_msm_phase_ms[4];
+  msm_stat_add(g_msm_phase_total[F::kDegree == 1 ? 0 : 1][4], g_msm_phase_ms[4]);
   return 0;
 }
 

@@ -3,6 +3,7 @@
 // Split this way so the slow-to-compile group code builds in parallel.
 #pragma once
 #include <stdint.h>
+#include <atomic>
 #include <functional>
 #include <vector>
 #include "common.cuh"
@@ -88,8 +89,12 @@ struct MsmPlan {
 void msm_timeline_begin();
 void msm_timeline_note(int slot, cudaEvent_t ta, cudaEvent_t t0, cudaEvent_t t1);
 void msm_timeline_get(double *out15);
-extern double g_msm_phase_ms[5];         // last call: digits, sort, accumulate, reduce, host tail
-extern double g_msm_phase_total[2][5];   // accumulated, [0] G1 calls, [1] G2 calls
+// diagnostics shared by all host threads (two proofs may be in flight): relaxed atomics, no ordering implied
+extern std::atomic<double> g_msm_phase_ms[5];         // last call: digits, sort, accumulate, reduce, host tail
+extern std::atomic<double> g_msm_phase_total[2][5];   // accumulated, [0] G1 calls, [1] G2 calls
+static inline void msm_stat_add(std::atomic<double> &a, double v) {
+  a.store(a.load(std::memory_order_relaxed) + v, std::memory_order_relaxed);
+}
 
 // Phase 1+2 (group independent): window plan, signed digits, histogram, counting sort of point indices by
 // (window, bucket), bucket visiting order by descending size. fr_tag: 0 = modulus A, 1 = modulus B.
