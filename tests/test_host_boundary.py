@@ -90,6 +90,14 @@ def test_compute_fails_loudly_without_gpu(b200):
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
     with pytest.raises(b200.B200Error):
         b200.msm(0, 1, 0, 0, 4)
+    # every entry point that would compute: key loading, whole proofs, batches
+    import util
+    params, inp, _ = util.golden(0, 5)
+    with pytest.raises(b200.B200Error):
+        b200.Params.from_bytes(0, params)
+    arr = (b200.ProofJob * 1)()
+    assert b200.lib().b200_prove_batch(ctypes.addressof(arr), 1) != 0
+    assert b"CUDA" in b200.lib().b200_last_error() or b"fallback" in b200.lib().b200_last_error()
 
 
 def test_equal_bases_are_grouped_on_the_host(b200):
