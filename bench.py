@@ -183,6 +183,17 @@ def make_key(pkg, torch, curve, k, dev):
     return pkg.Params.from_device(curve, d, m, A, B1, B2, L, H)
 
 
+def regroup_partials(blobs, pbytes):
+    """blobs[r] = rank r's partial sums of every proof of the step, concatenated (what one all_gather delivers);
+    returns, per proof, the rank-major concatenation b200_prove_combine expects."""
+    out, off = [], 0
+    for nb in pbytes:
+        out.append(b"".join(bl[off:off + nb] for bl in blobs))
+        off += nb
+    assert all(len(bl) == off for bl in blobs), "partial-sum blobs have unexpected length"
+    return out
+
+
 def make_input(torch, curve, k, seed):
     """pinned host image of an input file: w[m+1] (w[0] = 1 in Montgomery form), ca, cb, cc [d+1], r"""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -257,12 +268,9 @@ def b200_arm(args):
             proofs = []
             if rank == 0:
                 blobs = [bytes(t.cpu().numpy().tobytes()) for t in allp]
-                off = 0
-                for i, (curve, k) in enumerate(shapes):
-                    mine_i = b"".join(bl[off:off + pbytes[i]] for bl in blobs)
-                    off += pbytes[i]
+                for i, ((curve, k), parts_i) in enumerate(zip(shapes, regroup_partials(blobs, pbytes))):
                     r_fr = bytes(host_inputs[i][-1].numpy().tobytes())
-                    proofs.append(pkg.prove_combine(curve, mine_i, world, r_fr))
+                    proofs.append(pkg.prove_combine(curve, parts_i, world, r_fr))
         if timings is not None:
             wall = time.perf_counter() - t0
             for tm in tms:

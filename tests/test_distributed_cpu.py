@@ -60,3 +60,52 @@ def test_two_rank_sharded_proof_over_gloo(curve):
     port = 29600 + curve + (os.getpid() % 200)
     mp.spawn(_worker, args=(world, port, curve, 5, ret), nprocs=world, join=True)
     assert ret.get("ok") is True
+
+
+def _oracle_partials(b200, O, curve, k, rank, world):
+    params, inp, expected = util.golden(curve, k)
+    d, m, q = util.split_params(curve, params)
+    x = util.split_input(inp, d, m)
+    H = util.orc_compute_h(O, curve, d, x["ca"], x["cb"], x["cc"])
+    jobs = [(1, x["w"], q["A"], m + 1), (1, x["w"], q["B1"], m + 1), (2, x["w"], q["B2"], m + 1),
+            (1, H, q["H"], d), (1, x["w"][2 * 96:], q["L"], m - 1)]
+    part = b""
+    for group, sc, pts, n in jobs:
+        lo, hi = shard_range(n, rank, world)
+        ab = b200.affine_bytes(curve, group)
+        out = ctypes.create_string_buffer(b200.proj_bytes(curve, group))
+        sb, pb = util.buf(sc[lo * 96:hi * 96]), util.buf(pts[lo * ab:hi * ab])
+        O.orc_msm(curve, group, ctypes.addressof(sb), ctypes.addressof(pb), hi - lo, ctypes.addressof(out), 1)
+        part += out.raw
+    return part, x["r"], expected
+
+
+def _worker_step(rank, world, port, ret):
+    """bench.py's N>1 step: BOTH curves' partial sums in one blob per rank, one all_gather, regroup, combine."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import snark_challenge_prover_reference_b200 as b200
+    O = util.load_oracle()
+    cases = [(0, 5), (1, 5)]
+    parts = [_oracle_partials(b200, O, c, k, rank, world) for c, k in cases]
+    mine = torch.frombuffer(bytearray(b"".join(p[0] for p in parts)), dtype=torch.uint8)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        blobs = [t.numpy().tobytes() for t in gathered]
+        grouped = bench.regroup_partials(blobs, [b200.partial_bytes(c) for c, _ in cases])
+        ret["ok"] = all(b200.prove_combine(c, grouped[i], world, parts[i][1]) == parts[i][2]
+                        for i, (c, _) in enumerate(cases))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_with_both_curves_in_one_gather():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29850 + (os.getpid() % 100)
+    mp.spawn(_worker_step, args=(world, port, ret), nprocs=world, join=True)
+    assert ret.get("ok") is True
