@@ -300,7 +300,29 @@ struct alignas(16) Fp {
     host_mul(r, a, b);
 #endif
   }
-  B200_HD static B200_INLINE void sqr(Fp &r, const Fp &a) { mul(r, a, a); }
+#if defined(__CUDACC__) && defined(B200_SQR_DEDICATED)
+  // -DB200_SQR_DEDICATED: squarings use the generated 876-MAC squaring (276 off-diagonal products doubled + 24 squares
+  // + Montgomery reduction of the 48-limb value) instead of the 1152-MAC multiply. Validated against Python integers
+  // through the PTX interpreter (tests/test_ptx_model.py); NOT yet timed on the GPU (round 1 ran out of GPU budget;
+  // the Karatsuba variant showed that fewer multiplier instructions do not automatically mean less time), so it is
+  // off by default.
+  static __device__ __noinline__ void sqr_dev(uint32_t *r, const uint32_t *a) {
+    uint32_t x[kLimbs], z[kLimbs];
+    load_limbs(x, a);
+    if (P::kTag == 'A')
+      fp_sqr_ptx_A(z, x);
+    else
+      fp_sqr_ptx_B(z, x);
+    store_limbs(r, z);
+  }
+#endif
+  B200_HD static B200_INLINE void sqr(Fp &r, const Fp &a) {
+#if defined(__CUDA_ARCH__) && defined(B200_SQR_DEDICATED)
+    sqr_dev(r.l, a.l);
+#else
+    mul(r, a, a);
+#endif
+  }
 
   // out-of-line add / sub / small-constant multiply for the tower fields (keeps Fq2/Fq3 code a short list of calls:
   // with the ~100-instruction carry chains inlined ~40 times the G2 kernels no longer fit the instruction cache)

@@ -23,13 +23,17 @@ def test_generated_ptx_matches_python_ints():
     for tag, p in M.PRIMES.items():
         mul, add, sub = G.gen_mul_body(p), G.gen_add_body(p), G.gen_sub_body(p)
         mulk, _ = G.gen_mul_karatsuba_body(p)
+        sqr, _ = G.gen_sqr_body(p)
         rinv = pow(M.R, -1, p)
         cases = [(0, 0), (p - 1, p - 1), (1, p - 1), (p - 1, 1), (0, p - 1), ((1 << 384) - 1, (1 << 384) - 1),
                  (p - 1, (1 << 384) - 1), (1 << 752, 1 << 752)]
+        cases += [(int("ffffffff" * 23, 16) % p, sum(0xffffffff << (64 * i) for i in range(12)) % p)]
         cases += [(rng.randrange(p), rng.randrange(p)) for _ in range(60)]
         for a, b in cases:
             assert _run(mul, a, b) == a * b * rinv % p
             assert _run(mulk, a, b) == a * b * rinv % p
+            assert _run(sqr, a, a) == a * a * rinv % p
+            assert _run(sqr, b, b) == b * b * rinv % p
             assert _run(add, a, b) == (a + b) % p
             assert _run(sub, a, b) == (a - b) % p
 
@@ -42,5 +46,7 @@ def test_checked_in_header_is_current():
         assert G.emit_function("fp_mul_ptx_%s" % tag, G.gen_mul_body(p)) in text
         kl, nk = G.gen_mul_karatsuba_body(p)
         assert G.emit_function("fp_mulk_ptx_%s" % tag, kl, nk=nk) in text
+        sl, ns = G.gen_sqr_body(p)
+        assert G.emit_function("fp_sqr_ptx_%s" % tag, sl, sqr=True, nk=ns) in text
         assert G.emit_function("fp_add_ptx_%s" % tag, G.gen_add_body(p)) in text
         assert G.emit_function("fp_sub_ptx_%s" % tag, G.gen_sub_body(p)) in text
