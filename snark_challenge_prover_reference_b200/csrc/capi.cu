@@ -116,6 +116,9 @@ static void host_fp_op_t(int op, const void *a, const void *b, void *r) {
     case 2: Fp<P>::mul(z, x, y); break;
     case 3: Fp<P>::inv(z, x); break;
     case 4: Fp<P>::from_mont(z, x); break;
+    case 6: Fp<P>::inv_binary(z, x); break;
+    case 7: Fp<P>::inv_bingcd(z, x); break;
+    case 8: Fp<P>::inv_fermat(z, x); break;
     default: Fp<P>::to_mont(z, x); break;
   }
   memcpy(r, &z, 96);
@@ -386,7 +389,7 @@ int b200_g1_from_affine(int curve, const void *xy, void *out) { DISPATCH_GROUP(c
 int b200_g2_from_affine(int curve, const void *xy, void *out) { DISPATCH_GROUP(curve, 2, from_affine(xy, out)); }
 
 int b200_host_fp_op(int tag, int op, const void *a, const void *b, void *r) {
-  if (op < 0 || op > 5) return set_error(-1, "bad op");
+  if (op < 0 || op > 8) return set_error(-1, "bad op");
   if (tag == 0) host_fp_op_t<PrimeA>(op, a, b, r);
   else host_fp_op_t<PrimeB>(op, a, b, r);
   return 0;

@@ -464,16 +464,215 @@ struct alignas(16) Fp {
     }
     mul(r, ci, r3);
   }
-  // r = a^-1 (Fermat, a^(p-2)); a != 0. The reference uses an extended gcd (fp.tcc:641-685); the inverse is unique.
+  // r = a^-1 by the batched binary gcd (Pornin, "Optimized Binary GCD for Modular Inversion", 2020): the 2*753
+  // single-bit steps of inv_binary are grouped 31 at a time; each group runs on 64-bit approximations of (a, b) (low 31
+  // bits exact, top 33 bits) and yields factors |f|,|g| <= 2^31 that are then applied ONCE to the full-width values:
+  //   (a, b) <- ((f0 a + g0 b) / 2^31, (f1 a + g1 b) / 2^31),  (u, v) <- the same combination mod p (the division by
+  //   2^31 made exact by adding the right multiple of p).
+  // 49 rounds; ~25 K instructions instead of ~770 K. Host and device code (no divergence inside a round).
+  // Round-2 building block for the batch-affine accumulation; the host uses it for to_affine.
+  B200_HD static void inv_bingcd(Fp &r, const Fp &x) {
+    constexpr int kW = kLimbs + 1;  // 25 limbs: products by a 32-bit factor, and p << 31
+    uint32_t a[kLimbs], b[kLimbs], u[kLimbs], v[kLimbs];
+    for (int i = 0; i < kLimbs; i++) {
+      a[i] = x.l[i];
+      b[i] = P::p(i);
+      u[i] = 0;
+      v[i] = 0;
+    }
+    u[0] = 1;
+    // |f| * s (25 limbs)
+    auto mul_small = [](uint32_t (&out)[kW], const uint32_t (&s)[kLimbs], uint32_t f) {
+      uint64_t c = 0;
+      for (int i = 0; i < kLimbs; i++) {
+        c += (uint64_t)s[i] * f;
+        out[i] = (uint32_t)c;
+        c >>= 32;
+      }
+      out[kLimbs] = (uint32_t)c;
+    };
+    for (int round = 0; round < 49; round++) {
+      // ---- 64-bit approximations: n = bit length of max(a, b)
+      int top = kLimbs - 1;
+      while (top > 1 && (a[top] | b[top]) == 0) top--;
+      uint64_t abar, bbar;
+      {
+        const uint32_t hi = a[top] | b[top];
+        int lz = 0;
+        for (uint32_t t = hi; lz < 32 && !(t & 0x80000000u); t <<= 1) lz++;
+        const int n = 32 * (top + 1) - lz;
+        if (n <= 64) {
+          abar = (uint64_t)a[0] | ((uint64_t)a[1] << 32);
+          bbar = (uint64_t)b[0] | ((uint64_t)b[1] << 32);
+        } else {
+          const int pos = n - 33, w = pos >> 5, off = pos & 31;  // bits [pos, pos + 33)
+          auto window = [&](const uint32_t (&s)[kLimbs]) -> uint64_t {
+            uint64_t lo = (uint64_t)s[w] | ((uint64_t)(w + 1 < kLimbs ? s[w + 1] : 0u) << 32);
+            uint64_t hi2 = w + 2 < kLimbs ? s[w + 2] : 0u;
+            uint64_t val = lo >> off;
+            if (off) val |= hi2 << (64 - off);
+            return val & 0x1ffffffffull;
+          };
+          abar = (window(a) << 31) | (a[0] & 0x7fffffffu);
+          bbar = (window(b) << 31) | (b[0] & 0x7fffffffu);
+        }
+      }
+      // ---- 31 binary-gcd steps on the approximations, branch-free
+      int64_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+      for (int it = 0; it < 31; it++) {
+        const uint64_t odd = 0ull - (abar & 1ull);
+        const uint64_t sw = odd & (0ull - (uint64_t)(abar < bbar));
+        const uint64_t tx = (abar ^ bbar) & sw;
+        abar ^= tx;
+        bbar ^= tx;
+        const int64_t tf = (f0 ^ f1) & (int64_t)sw, tg = (g0 ^ g1) & (int64_t)sw;
+        f0 ^= tf;
+        f1 ^= tf;
+        g0 ^= tg;
+        g1 ^= tg;
+        abar -= bbar & odd;
+        f0 -= f1 & (int64_t)odd;
+        g0 -= g1 & (int64_t)odd;
+        abar >>= 1;
+        f1 <<= 1;
+        g1 <<= 1;
+      }
+      // ---- apply to (a, b): t = f*a + g*b (signed), exact division by 2^31, then make it non-negative
+      int64_t fs[2] = {f0, f1}, gs[2] = {g0, g1};
+      uint32_t na[2][kLimbs];
+      for (int k = 0; k < 2; k++) {
+        const bool fneg = fs[k] < 0, gneg = gs[k] < 0;
+        const uint32_t fa = (uint32_t)(fneg ? -fs[k] : fs[k]), ga = (uint32_t)(gneg ? -gs[k] : gs[k]);
+        uint32_t pf[kW], pg[kW], mag[kW];
+        mul_small(pf, a, fa);
+        mul_small(pg, b, ga);
+        bool neg;
+        if (fneg == gneg) {
+          uint64_t c = 0;
+          for (int i = 0; i < kW; i++) {
+            c += (uint64_t)pf[i] + pg[i];
+            mag[i] = (uint32_t)c;
+            c >>= 32;
+          }
+          neg = fneg;  // both factors negative -> negative (a zero factor never has the sign bit set)
+        } else {
+          // pf*sign(f) + pg*sign(g): compute pos - negpart, negate on borrow
+          const uint32_t(&posv)[kW] = fneg ? pg : pf;
+          const uint32_t(&negv)[kW] = fneg ? pf : pg;
+          uint64_t brw = 0;
+          for (int i = 0; i < kW; i++) {
+            uint64_t t = (uint64_t)posv[i] - negv[i] - brw;
+            mag[i] = (uint32_t)t;
+            brw = (t >> 32) & 1u;
+          }
+          neg = brw != 0;
+          if (neg) {
+            uint64_t c = 1;
+            for (int i = 0; i < kW; i++) {
+              c += (uint64_t)(uint32_t)~mag[i];
+              mag[i] = (uint32_t)c;
+              c >>= 32;
+            }
+          }
+        }
+        for (int i = 0; i < kLimbs; i++) na[k][i] = (mag[i] >> 31) | (mag[i + 1] << 1);
+        if (neg) {  // keep (a, b) non-negative: flip the factors so that the (u, v) update matches
+          fs[k] = -fs[k];
+          gs[k] = -gs[k];
+        }
+      }
+      // ---- apply to (u, v) mod p:  acc = p*2^31 + f*u + g*v >= 0; acc += q*p with q = acc * (-p^-1) mod 2^31;
+      //      acc / 2^31 < 3p; two conditional subtractions
+      uint32_t nu[2][kLimbs];
+      for (int k = 0; k < 2; k++) {
+        const bool fneg = fs[k] < 0, gneg = gs[k] < 0;
+        const uint32_t fa = (uint32_t)(fneg ? -fs[k] : fs[k]), ga = (uint32_t)(gneg ? -gs[k] : gs[k]);
+        uint32_t acc[kW], t[kW];
+        acc[0] = 0;
+        {
+          uint32_t prev = 0;
+          for (int i = 0; i < kLimbs; i++) {
+            const uint32_t pi = P::p(i);
+            acc[i] = (pi << 31) | (prev >> 1);
+            prev = pi;
+          }
+          acc[kLimbs] = prev >> 1;
+        }
+        for (int part = 0; part < 2; part++) {
+          mul_small(t, part == 0 ? u : v, part == 0 ? fa : ga);
+          const bool sub = part == 0 ? fneg : gneg;
+          if (!sub) {
+            uint64_t c = 0;
+            for (int i = 0; i < kW; i++) {
+              c += (uint64_t)acc[i] + t[i];
+              acc[i] = (uint32_t)c;
+              c >>= 32;
+            }
+          } else {
+            uint64_t brw = 0;
+            for (int i = 0; i < kW; i++) {
+              uint64_t d = (uint64_t)acc[i] - t[i] - brw;
+              acc[i] = (uint32_t)d;
+              brw = (d >> 32) & 1u;
+            }
+          }
+        }
+        const uint32_t q = (acc[0] * P::kInv32) & 0x7fffffffu;
+        {
+          uint64_t c = 0;
+          for (int i = 0; i < kLimbs; i++) {
+            c += (uint64_t)P::p(i) * q + acc[i];
+            acc[i] = (uint32_t)c;
+            c >>= 32;
+          }
+          acc[kLimbs] = (uint32_t)(c + acc[kLimbs]);
+        }
+        uint32_t res[kLimbs];
+        for (int i = 0; i < kLimbs; i++) res[i] = (acc[i] >> 31) | (acc[i + 1] << 1);
+        for (int rep = 0; rep < 2; rep++) {  // res < 3p
+          uint32_t d[kLimbs];
+          uint64_t brw = 0;
+          for (int i = 0; i < kLimbs; i++) {
+            uint64_t t2 = (uint64_t)res[i] - P::p(i) - brw;
+            d[i] = (uint32_t)t2;
+            brw = (t2 >> 32) & 1u;
+          }
+          const uint32_t keep = 0u - (uint32_t)brw;  // all-ones: res < p, keep it
+          for (int i = 0; i < kLimbs; i++) res[i] = (res[i] & keep) | (d[i] & ~keep);
+        }
+        for (int i = 0; i < kLimbs; i++) nu[k][i] = res[i];
+      }
+      for (int i = 0; i < kLimbs; i++) {
+        a[i] = na[0][i];
+        b[i] = na[1][i];
+        u[i] = nu[0][i];
+        v[i] = nu[1][i];
+      }
+    }
+    // b == 1 and v = x^-1 as a plain integer (x = the Montgomery residue): one multiplication by R^3 -> a^-1 * R
+    Fp vi, r3;
+    for (int i = 0; i < kLimbs; i++) {
+      vi.l[i] = v[i];
+      r3.l[i] = P::r3(i);
+    }
+    mul(r, vi, r3);
+  }
+  // r = a^-1; a != 0 (0 maps to 0). The reference uses an extended gcd (fp.tcc:641-685); the inverse is unique, so any
+  // algorithm gives the same canonical bytes. Device: bitwise binary gcd (validated on the GPU in round 1); host:
+  // batched binary gcd (30x fewer instructions; the device switches to it once it has been timed there).
   B200_HD static void inv(Fp &r, const Fp &a) {
 #if defined(__CUDA_ARCH__)
     inv_binary(r, a);
 #else
+    inv_bingcd(r, a);
+#endif
+  }
+  // a^(p-2) (Fermat): kept as an independent cross-check of the gcd-based inversions (tests)
+  B200_HD static void inv_fermat(Fp &r, const Fp &a) {
     uint32_t e[kLimbs];
     for (int i = 0; i < kLimbs; i++) e[i] = P::p(i);
     e[0] -= 2;  // p is odd and p mod 2^32 >= 3, no borrow
     pow_words(r, a, e, kLimbs);
-#endif
   }
 };
 

@@ -31,6 +31,17 @@ def test_host_field_ops(b200, oracle, tag):
             assert b200.host_fp_op(tag, op, a, b) == util.orc_fp(oracle, tag, op, a, b)
     a = util.fe_bytes(rng.randrange(1, p))
     assert b200.host_fp_op(tag, 3, a) == util.orc_fp(oracle, tag, 3, a)
+    # three independent inversion routines (bitwise binary gcd = the device's, batched binary gcd, Fermat) agree with
+    # the oracle's xgcd on random and edge values
+    rng2 = random.Random(77 + tag)
+    for x in [1, 2, p - 1, p - 2, (p + 1) // 2, M.R % p, 1 << 31, (1 << 64) + 1] + [rng2.randrange(1, p) for _ in range(40)]:
+        xb = util.fe_bytes(x)
+        want = util.orc_fp(oracle, tag, 3, xb)
+        assert b200.host_fp_op(tag, 7, xb) == want
+        assert b200.host_fp_op(tag, 8, xb) == want
+    for x in [3, p - 5] + [rng2.randrange(1, p) for _ in range(6)]:
+        xb = util.fe_bytes(x)
+        assert b200.host_fp_op(tag, 6, xb) == util.orc_fp(oracle, tag, 3, xb)
     assert b200.host_fp_op(tag, 4, a) == util.orc_fp(oracle, tag, 4, a)
     assert b200.host_fp_op(tag, 5, a) == util.orc_fp(oracle, tag, 5, a)
 
