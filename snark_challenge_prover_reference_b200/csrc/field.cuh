@@ -661,10 +661,10 @@ struct alignas(16) Fp {
   // algorithm gives the same canonical bytes. Device: bitwise binary gcd (validated on the GPU in round 1); host:
   // batched binary gcd (30x fewer instructions; the device switches to it once it has been timed there).
   B200_HD static void inv(Fp &r, const Fp &a) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(B200_INV_BINGCD)
     inv_binary(r, a);
 #else
-    inv_bingcd(r, a);
+    inv_bingcd(r, a);  // -DB200_INV_BINGCD selects it on the device too (compiles for sm_100a; not yet timed there)
 #endif
   }
   // a^(p-2) (Fermat): kept as an independent cross-check of the gcd-based inversions (tests)
