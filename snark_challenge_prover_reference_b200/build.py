@@ -34,12 +34,32 @@ def _headers():
     return hs
 
 
+def _flags():
+    return FLAGS + os.environ.get("B200_NVCC_EXTRA", "").split()
+
+
+def _stamp_matches():
+    """build/flags.stamp records the effective nvcc flag list (B200_NVCC_EXTRA included): objects compiled with
+    another flag set are stale even when their mtimes are newer than the sources."""
+    want = " ".join(_flags())
+    path = os.path.join(OBJ, "flags.stamp")
+    have = open(path).read() if os.path.exists(path) else None
+    if have != want:
+        for f in os.listdir(OBJ):
+            if f.endswith(".o"):
+                os.remove(os.path.join(OBJ, f))
+        with open(path, "w") as fh:
+            fh.write(want)
+        return False
+    return True
+
+
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     path = os.path.join(CSRC, src)
     if _newer(obj, [path] + _headers()):
         return obj, ""
-    cmd = [NVCC] + FLAGS + os.environ.get("B200_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+    cmd = [NVCC] + _flags() + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout[-4000:], r.stderr[-8000:]))
@@ -53,6 +73,7 @@ def build(force=False, verbose=False):
             os.remove(os.path.join(OBJ, f))
         if os.path.exists(LIB):
             os.remove(LIB)
+    _stamp_matches()
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     objs = [o for o, _ in results]

@@ -418,6 +418,14 @@ int b200_imad_peak(double *mac32_per_s, double *ms) {
 }
 
 // ---- proving key
+// Dimensions come from a file header or from the caller: validate them before any size arithmetic (m - 1 and the byte
+// counts below would wrap). The query lengths are m+1, m+1, m+1, m-1, d; the domain has d+1 elements.
+static int check_key_dims(size_t d, size_t m) {
+  const size_t kMax = (size_t)1 << 30;
+  if (m < 2 || m >= kMax || d < 1 || d >= kMax)
+    return set_error(-4, "key dimensions d=%zu m=%zu out of range (need 1 <= d < 2^30, 2 <= m < 2^30)", d, m);
+  return 0;
+}
 static int params_finish(b200_params *p) {
   b200_domain *dom = nullptr;
   B200_CHECK(b200_domain_create(p->curve, p->d + 1, &dom));
@@ -436,9 +444,10 @@ int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_par
   size_t d, m;
   memcpy(&d, h_image, 8);
   memcpy(&m, (const char *)h_image + 8, 8);
+  B200_CHECK(check_key_dims(d, m));
   size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
   size_t need = 16 + g1 * (2 * (m + 1) + (m - 1) + d) + g2 * (m + 1);
-  if (m < 2 || bytes != need)
+  if (bytes != need)
     return set_error(-4, "parameter image has %zu bytes, expected %zu for d=%zu m=%zu", bytes, need, d, m);
   b200_params *p = new b200_params();
   p->curve = curve;
@@ -473,6 +482,8 @@ int b200_params_from_device(int curve, size_t d, size_t m, const void *A, const 
                             const void *H, b200_params **out) {
   B200_CHECK(require_device());
   if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
+  B200_CHECK(check_key_dims(d, m));
+  if (!A || !B1 || !B2 || !L || !H) return set_error(-1, "params_from_device: null query pointer");
   b200_params *p = new b200_params();
   p->curve = curve;
   p->d = d;
@@ -542,11 +553,13 @@ int b200_params_msm(b200_params *p, int which, const void *d_scalars, size_t n, 
   if (use_precompute() && n == ns[which]) {
     B200_CHECK(b200_params_precompute(p, 0, 1));
     const int j = job_of_query[which];
-    std::function<void()> tail;
+    MsmTail tail;
     msm_select_slot(0);
     B200_CHECK(msm_table_dispatch_deferred(p->curve, group, d_scalars, p->pre.table[j].p, n, p->pre.plan[j], h_out, tail,
                                            -1, &p->pre.dedup[j]));
-    tail();
+    std::string err;
+    const int rc = tail(err);
+    if (rc) return set_error(rc, "%s", err.c_str());
     return 0;
   }
   return msm_dispatch(p->curve, group, d_scalars, p->q[which], n, h_out);
@@ -595,7 +608,10 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   // accumulation kernel takes register-file space from it for longer than it saves.
   const size_t outoff[5] = {0, g1p, 2 * g1p, 2 * g1p + g2p, 3 * g1p + g2p};
   const int order[5] = {2, 0, 1, 4, 3};
-  std::vector<std::future<void>> tails;
+  // every tail reports its own status and message (it runs on another thread, whose thread-local error slot this thread
+  // cannot see); a failed tail fails the proof
+  struct TailResult { int rc = 0; std::string err; };
+  std::vector<std::future<TailResult>> tails;
   int rc_all = 0;
   double t2 = t1;
   for (int jj = 0; jj < 5 && rc_all == 0; jj++) {
@@ -615,7 +631,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     size_t one = J.n / (size_t)world;
     size_t lo = (size_t)rank * one, hi = (rank == world - 1) ? J.n : lo + one;
     double a = now_ms();
-    std::function<void()> tail;
+    MsmTail tail;
     msm_select_slot(jj);
     // A and B1 (slots 1, 2) run over the same scalars and window plan as B2 (slot 0): they reuse its digits, counting
     // sort and task list
@@ -627,14 +643,26 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
                                            p->pre.plan[j], o, tail, share, &p->pre.dedup[j]);
     else
       rc_all = msm_dispatch_deferred(curve, J.group, J.scalars + lo * 96, J.points + lo * J.stride, hi - lo, o, tail);
-    if (rc_all == 0) tails.push_back(std::async(std::launch::async, tail));
+    if (rc_all == 0)
+      tails.push_back(std::async(std::launch::async, [tail] {
+        TailResult r;
+        r.rc = tail(r.err);
+        return r;
+      }));
     *J.ms = now_ms() - a;
   }
   msm_select_slot(0);
   double t_join = now_ms();
-  for (auto &f : tails) f.get();
+  std::string issue_err = rc_all ? last_error() : std::string();
+  for (auto &f : tails) {
+    TailResult r = f.get();
+    if (r.rc && rc_all == 0) {
+      rc_all = r.rc;
+      issue_err = r.err;
+    }
+  }
   double join_ms = now_ms() - t_join;
-  if (rc_all) return rc_all;
+  if (rc_all) return set_error(rc_all, "%s", issue_err.c_str());
   if (tm) {
     tm->h2d_ms = t1 - t0;
     tm->compute_h_ms = t2 - t1;

@@ -373,10 +373,13 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan, cons
   B200_CHECK(ws.plan.reserve(256 * sizeof(uint32_t)));
   B200_CHECK(ws.scalar_out.reserve(64));
   B200_CUDA_CHECK(cudaMemcpyAsync(ws.plan.p, plan.windows.data(), W * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-  Timer tm(st);
+  // diagnostic timers: persistent events, recorded asynchronously; nothing waits on them (msm_collect reads them after
+  // the whole MSM has drained)
+  for (int i = 0; i < 4; i++)
+    if (!ws.tm_ev[i]) B200_CUDA_CHECK(cudaEventCreate(&ws.tm_ev[i]));
 
   // ---- digits + histogram (after folding the scalars of equal bases into one representative each)
-  tm.start();
+  B200_CUDA_CHECK(cudaEventRecord(ws.tm_ev[0], st));
   if (dedup && dedup->merged) {
     if (fr_tag == 0) B200_CHECK(msm_dedup_scalars<PrimeA>(d_scalars, n, *dedup, ws));
     else B200_CHECK(msm_dedup_scalars<PrimeB>(d_scalars, n, *dedup, ws));
@@ -394,10 +397,10 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan, cons
                                                          ws.counts.as<uint32_t>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
-  g_msm_phase_ms[0] = tm.stop();
+  B200_CUDA_CHECK(cudaEventRecord(ws.tm_ev[1], st));
 
   // ---- counting sort of the entries by bucket: scan + scatter
-  tm.start();
+  B200_CUDA_CHECK(cudaEventRecord(ws.tm_ev[2], st));
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ws.counts.as<uint32_t>(), ws.offsets.as<uint32_t>(), (int)nbuckets);
   B200_CHECK(ws.cub_tmp.reserve(tmp_bytes));
@@ -478,7 +481,7 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan, cons
                                                                 ws.order.as<uint32_t>(), (int)ntasks, 0, end_bit, st));
     }
   }
-  g_msm_phase_ms[1] = tm.stop();
+  B200_CUDA_CHECK(cudaEventRecord(ws.tm_ev[3], st));
   *ws.prepared = plan;
   g_last_plan[0] = plan.c;
   g_last_plan[1] = plan.W;
@@ -550,13 +553,13 @@ int msm_run_mnt4g2(const void *, const void *, size_t, void *);
 int msm_run_mnt6g1(const void *, const void *, size_t, void *);
 int msm_run_mnt6g2(const void *, const void *, size_t, void *);
 
-int msm_run_deferred_mnt4g1(const void *, const void *, size_t, void *, std::function<void()> &);
-int msm_run_deferred_mnt4g2(const void *, const void *, size_t, void *, std::function<void()> &);
-int msm_run_deferred_mnt6g1(const void *, const void *, size_t, void *, std::function<void()> &);
-int msm_run_deferred_mnt6g2(const void *, const void *, size_t, void *, std::function<void()> &);
+int msm_run_deferred_mnt4g1(const void *, const void *, size_t, void *, MsmTail &);
+int msm_run_deferred_mnt4g2(const void *, const void *, size_t, void *, MsmTail &);
+int msm_run_deferred_mnt6g1(const void *, const void *, size_t, void *, MsmTail &);
+int msm_run_deferred_mnt6g2(const void *, const void *, size_t, void *, MsmTail &);
 
 int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_points, size_t n, void *h_out,
-                          std::function<void()> &tail) {
+                          MsmTail &tail) {
   if (curve == 0 && group == 1) return msm_run_deferred_mnt4g1(d_scalars, d_points, n, h_out, tail);
   if (curve == 0 && group == 2) return msm_run_deferred_mnt4g2(d_scalars, d_points, n, h_out, tail);
   if (curve == 1 && group == 1) return msm_run_deferred_mnt6g1(d_scalars, d_points, n, h_out, tail);
@@ -566,7 +569,7 @@ int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const voi
 
 #define B200_DECL_G(name)                                                                                   \
   int msm_precompute_##name(const void *, size_t, MsmPlan &, DevBuf &);                                     \
-  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, std::function<void()> &, int, const MsmDedup *);
+  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, MsmTail &, int, const MsmDedup *);
 B200_DECL_G(mnt4g1) B200_DECL_G(mnt4g2) B200_DECL_G(mnt6g1) B200_DECL_G(mnt6g2)
 #undef B200_DECL_G
 
@@ -578,7 +581,7 @@ int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
-                                const MsmPlan &plan, void *h_out, std::function<void()> &tail, int share_slot,
+                                const MsmPlan &plan, void *h_out, MsmTail &tail, int share_slot,
                                 const MsmDedup *dedup) {
   if (curve == 0 && group == 1) return msm_run_table_deferred_mnt4g1(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
   if (curve == 0 && group == 2) return msm_run_table_deferred_mnt4g2(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);

@@ -2,12 +2,12 @@
 #include "msm_group.cuh"
 namespace b200 {
 int msm_run_mnt6g2(const void *s, const void *p, size_t n, void *out) { return msm_run<Mnt6G2>(s, p, n, out); }
-int msm_run_deferred_mnt6g2(const void *s, const void *p, size_t n, void *out, std::function<void()> &tail) {
+int msm_run_deferred_mnt6g2(const void *s, const void *p, size_t n, void *out, MsmTail &tail) {
   return msm_run_deferred<Mnt6G2>(s, p, n, out, tail);
 }
 int msm_precompute_mnt6g2(const void *p, size_t n, MsmPlan &plan, DevBuf &table) { return msm_precompute<Mnt6G2>(p, n, plan, table); }
 int msm_run_table_deferred_mnt6g2(const void *s, const void *t, size_t n, const MsmPlan &plan, void *out,
-                                  std::function<void()> &tail, int share_slot, const MsmDedup *dedup) {
+                                  MsmTail &tail, int share_slot, const MsmDedup *dedup) {
   return msm_run_table_deferred<Mnt6G2>(s, t, n, plan, out, tail, share_slot, dedup);
 }
 }  // namespace b200

@@ -471,6 +471,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   stage = ws.next_staging((size_t)W * sizeof(Proj<F>));
   if (!stage) return set_error(-5, "msm: pinned staging allocation failed");
   stage->slot = msm_current_slot();
+  for (int i = 0; i < 4; i++) stage->prep_ev[i] = share_slot >= 0 ? nullptr : ws.tm_ev[i];
 
   if (msm_use_batch_affine()) {
     B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
@@ -511,7 +512,6 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   B200_CUDA_CHECK(cudaMemcpyAsync(stage->pinned, cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost, st));
   B200_CUDA_CHECK(cudaEventRecord(stage->t1, st));
   B200_CUDA_CHECK(cudaEventRecord(stage->done, st));
-  for (int i = 0; i < 2; i++) msm_stat_add(g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i], g_msm_phase_ms[i]);
   return 0;
 }
 
@@ -524,6 +524,13 @@ int msm_collect(const MsmPlan &plan, MsmWorkspace::Staging *stage, std::vector<P
   win.resize(W);
   memcpy(win.data(), stage->pinned, (size_t)W * sizeof(Proj<F>));
   float ms = 0;
+  if (stage->prep_ev[0]) {  // this MSM prepared its own digits / sort (events completed: they precede `done`)
+    for (int i = 0; i < 2; i++) {
+      cudaEventElapsedTime(&ms, stage->prep_ev[2 * i], stage->prep_ev[2 * i + 1]);
+      g_msm_phase_ms[i] = ms;
+      msm_stat_add(g_msm_phase_total[F::kDegree == 1 ? 0 : 1][i], ms);
+    }
+  }
   cudaEventElapsedTime(&ms, stage->ta, stage->t0);
   g_msm_phase_ms[2] = ms;
   msm_stat_add(g_msm_phase_total[F::kDegree == 1 ? 0 : 1][2], ms);
@@ -570,26 +577,45 @@ int msm_run(const void *d_scalars, const void *d_points, size_t n, void *h_out) 
   return 0;
 }
 
+// The host tail of a deferred MSM. It may run on a thread other than the issuing one: the device that was current
+// at issue time is made current there, and a failure (e.g. an asynchronous kernel fault surfacing at the event wait)
+// is returned with its message instead of being left in the tail thread's thread-local error slot.
+template <class G>
+MsmTail msm_make_tail(std::shared_ptr<MsmPlan> plan, MsmWorkspace::Staging *stage, void *h_out) {
+  typedef typename G::F F;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return [plan, stage, h_out, dev](std::string &err) -> int {
+    cudaError_t e = cudaSetDevice(dev);
+    int rc = e == cudaSuccess ? 0 : set_error(-100 - (int)e, "msm tail: cudaSetDevice(%d): %s", dev, cudaGetErrorString(e));
+    std::vector<Proj<F>> win;
+    if (rc == 0) rc = msm_collect<G>(*plan, stage, win);
+    if (rc) {
+      err = last_error();
+      return rc;
+    }
+    g_msm_phase_ms[4] = msm_host_phase<G>(*plan, win, h_out);
+    return 0;
+  };
+}
+
 // Same sum, but the wait for the bucket reduction and the serial host tail are returned as a closure, so that the
 // caller can run them on another thread while the next MSM already occupies the GPU (b200_prove does this for its five
 // MSMs, alternating the two workspaces/streams).
 template <class G>
-int msm_run_deferred(const void *d_scalars, const void *d_points, size_t n, void *h_out, std::function<void()> &tail) {
+int msm_run_deferred(const void *d_scalars, const void *d_points, size_t n, void *h_out, MsmTail &tail) {
   typedef typename G::F F;
   if (n == 0) {
     Proj<F> zero;
     proj_set_zero(zero);
     memcpy(h_out, &zero, sizeof(zero));
-    tail = []() {};
+    tail = [](std::string &) { return 0; };
     return 0;
   }
   auto plan = std::make_shared<MsmPlan>();
   MsmWorkspace::Staging *stage = nullptr;
   B200_CHECK(msm_gpu_phase<G>(d_scalars, d_points, n, *plan, stage));
-  tail = [plan, stage, h_out]() {
-    std::vector<Proj<F>> win;
-    if (msm_collect<G>(*plan, stage, win) == 0) g_msm_phase_ms[4] = msm_host_phase<G>(*plan, win, h_out);
-  };
+  tail = msm_make_tail<G>(plan, stage, h_out);
   return 0;
 }
 
@@ -667,22 +693,19 @@ int msm_precompute(const void *d_points, size_t n, MsmPlan &plan, DevBuf &table)
 // MSM over a table built by msm_precompute (plan must be the table's plan).
 template <class G>
 int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n, const MsmPlan &table_plan, void *h_out,
-                           std::function<void()> &tail, int share_slot, const MsmDedup *dedup) {
+                           MsmTail &tail, int share_slot, const MsmDedup *dedup) {
   typedef typename G::F F;
   if (n == 0) {
     Proj<F> zero;
     proj_set_zero(zero);
     memcpy(h_out, &zero, sizeof(zero));
-    tail = []() {};
+    tail = [](std::string &) { return 0; };
     return 0;
   }
   auto plan = std::make_shared<MsmPlan>(table_plan);
   MsmWorkspace::Staging *stage = nullptr;
   B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage, share_slot, dedup));
-  tail = [plan, stage, h_out]() {
-    std::vector<Proj<F>> win;
-    if (msm_collect<G>(*plan, stage, win) == 0) g_msm_phase_ms[4] = msm_host_phase<G>(*plan, win, h_out);
-  };
+  tail = msm_make_tail<G>(plan, stage, h_out);
   return 0;
 }
 

@@ -7,6 +7,7 @@
 #include <functional>
 #include <vector>
 #include "common.cuh"
+#include "msm.h"
 
 namespace b200 {
 
@@ -45,6 +46,7 @@ struct MsmWorkspace {
   // one MSM (and compute_H) run in the slots that free up while another MSM's accumulation saturates the multiplier.
   cudaStream_t stream = nullptr, acc_stream = nullptr;
   cudaEvent_t acc_done = nullptr;
+  cudaEvent_t tm_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // diagnostics: digits start/end, sort start/end
   // ring of pinned staging buffers + events for the asynchronous copy of the window sums to the host
   struct Staging {
     void *pinned = nullptr;
@@ -52,6 +54,7 @@ struct MsmWorkspace {
     cudaEvent_t done = nullptr;
     cudaEvent_t ta = nullptr, t0 = nullptr, t1 = nullptr;  // accumulate starts at ta, reduce spans t0..t1
     int slot = 0;                                           // workspace slot that issued it (timeline diagnostics)
+    cudaEvent_t prep_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // the issuing workspace's tm_ev (null: shared prep)
   } ring[4];
   int ring_pos = 0;
   Staging *next_staging(size_t bytes);
@@ -110,7 +113,7 @@ int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, ui
 // pre-shifted base tables (merged buckets), see msm_group.cuh
 int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n, MsmPlan &plan, DevBuf &table);
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
-                                const MsmPlan &plan, void *h_out, std::function<void()> &tail, int share_slot = -1,
+                                const MsmPlan &plan, void *h_out, MsmTail &tail, int share_slot = -1,
                                 const MsmDedup *dedup = nullptr);
 
 }  // namespace b200
