@@ -7,22 +7,25 @@
 
 A step = one MNT4753 proof at 2^20 constraints + one MNT6753 proof at 2^15 constraints (the challenge sizes of
 generate_parameters.cpp:127), i.e. per proof 7 Fr NTTs (compute_H) + 5 MSMs (A, B1, L, H in G1; B2 in G2) + the
-O(1) tail, on a synthetic proving key / witness of exactly that shape built on the device (see make_key()).
+O(1) tail. Both arms run on THE SAME FILES: a synthetic proving key + witness of exactly that shape, written once in
+the reference's own file formats by tools/synth_key (multiples of the generators with the duplicate / infinity
+structure of real keys; libsnark's ./main never validates a key), cached under B200_BENCH_CACHE.
 Metric: constraints proved per second (whole job). Latency per proof is in the extra key `proof_latency_s`.
 
   value : inputs (w, ca, cb, cc) already resident in HBM when the timed region starts.
   e2e   : the same step through the C-ABI call with the input image in pinned HOST memory: the H2D copy of the
           403 MB + 12.6 MB input images and the D2H of the partial sums are inside the timed region. The proving key
           stays resident, as in the reference, whose own timer starts after the key is loaded (main.cpp:203,270).
-  N > 1 : every MSM is sharded by contiguous point range over the ranks (multiexp.tcc:417-431 does the same over
-          OpenMP threads); the only exchange is an all_gather of 5 partial group elements (<= 2016 B) per proof over
-          NCCL; compute_H is replicated. Total work is fixed => "scaling": "strong".
+  N > 1 : every MNT4753 MSM is sharded by contiguous point range over the ranks (multiexp.tcc:417-431 does the same
+          over OpenMP threads); the only exchange is an all_gather of the partial group elements per step over NCCL;
+          compute_H is replicated. Total work is fixed => "scaling": "strong".
 
-`--impl reference` times the UNMODIFIED reference CPU prover (oracle/_ref/main, OpenMP on all host cores) on a
-bounded sample of the same workload (`generate_parameters fast`: MNT4753 2^14 + MNT6753 2^10).
+`--impl reference` times the UNMODIFIED reference CPU prover (oracle/_ref/main, OpenMP on all host cores) on the same
+files, i.e. the full workload, ONCE (`steps_effective`: 1 - a full-size CPU proof pair takes minutes), and leaves its
+output next to the files; the b200 arm compares the sha256 of its own proofs with it (`parity`).
 """
 import argparse
-import ctypes
+import csv
 import hashlib
 import json
 import os
@@ -40,8 +43,15 @@ REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 CACHE = os.environ.get("B200_BENCH_CACHE", "/tmp/b200_bench_cache")
 METRIC = "groth16_prove_constraints_per_s"
 UNIT = "constraints/s"
+CURVES = ("MNT4753", "MNT6753")
 # algorithmic work per MSM point: W=48 windows x mixed add (11 / 31 / 64 Fq mul) x 1176 MAC32
 MAC32_PER_POINT = {"g1": 620928, "g2_fq2": 1749888, "g2_fq3": 3612672}
+# what the kernels ISSUE per bucket insertion, in Fq multiplications of 1152 IMAD.WIDE each (24 x (24 + 24), the
+# interleaved CIOS of fp_ptx_gen.cuh): XYZZ mixed addition 8M + 2S; over Fq2 a multiplication is 3 and a squaring 2
+# base multiplications, over Fq3 6 and 5. Batch-affine: 5M + 1S per addition (3 of them the shared inversion).
+ISSUED_MULS = {"xyzz": {"g1": 10, "g2_fq2": 8 * 3 + 2 * 2, "g2_fq3": 8 * 6 + 2 * 5},
+               "affine": {"g1": 6, "g2_fq2": 5 * 3 + 2, "g2_fq3": 5 * 6 + 5}}
+IMAD_PER_MUL = 1152
 
 
 def parse():
@@ -53,36 +63,91 @@ def parse():
     ap.add_argument("--log2-mnt4", type=int, default=20)
     ap.add_argument("--log2-mnt6", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-rerun", action="store_true", help="reference arm: ignore a cached measurement of this box")
     return ap.parse_args()
 
 
+def workload_name(k4, k6, world=None):
+    s = "MNT4753 2^%d + MNT6753 2^%d Groth16 prove (7 NTT + 5 MSM each)" % (k4, k6)
+    return s if world is None else s + ", MSMs sharded over %d GPU(s) by point range" % world
+
+
+# ------------------------------------------------------------------------------------------------ workload files
+def synth_tool():
+    exe = os.path.join(ROOT, "tools", "_bin", "synth_key")
+    src = os.path.join(ROOT, "tools", "synth_key.cpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-mbmi2", "-pthread", "-I",
+                               os.path.join(ROOT, "snark_challenge_prover_reference_b200", "csrc"), src, "-o", exe])
+    return exe
+
+
+def ensure_synth(k4, k6, wait_only=False):
+    """The step's files: <dir>/MNT{4,6}753-{parameters,input} in the reference's formats. Written once per box by one
+    process (wait_only: another local rank writes them; poll for the marker)."""
+    d = os.path.join(CACHE, "synth_k%d_k%d" % (k4, k6))
+    marker = os.path.join(d, ".done")
+    if wait_only:
+        t0 = time.time()
+        while not os.path.exists(marker):
+            if time.time() - t0 > 1800:
+                raise SystemExit("bench.py: timed out waiting for %s" % marker)
+            time.sleep(0.5)
+        return d
+    if not os.path.exists(marker):
+        os.makedirs(d, exist_ok=True)
+        tool = synth_tool()
+        for name, k in zip(CURVES, (k4, k6)):
+            subprocess.check_call([tool, name, str(k), os.path.join(d, name + "-parameters"),
+                                   os.path.join(d, name + "-input")])
+        open(marker, "w").write("ok\n")
+    return d
+
+
+def sha256_file(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def ensure_fast_params():
-    """`generate_parameters fast` (the reference's own generator) -> CACHE/{MNT4753,MNT6753}-{parameters,input}"""
-    os.makedirs(CACHE, exist_ok=True)
-    names = ["MNT4753-parameters", "MNT4753-input", "MNT6753-parameters", "MNT6753-input"]
-    if not all(os.path.exists(os.path.join(CACHE, n)) for n in names):
-        gen = os.path.join(REF_DIR, "generate_parameters")
-        if not os.path.exists(gen):
-            return None
-        subprocess.check_call([gen, "fast"], cwd=CACHE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    return CACHE
-
-
-def run_reference_once(cache, cores):
-    """one sample step: ./main MNT4753 (2^14) + ./main MNT6753 (2^10); returns (seconds over the reference's own
-    'input -> output' region, per-curve dict)"""
+def run_reference_main(d, cores, out_suffix="-output-ref"):
+    """./main <curve> compute on the files of directory d, both curves; returns {"secs", "detail", "phases", "sha256"}
+    over the reference's own timed region ('Total time from input to output', main.cpp:203-270: key load excluded)."""
     env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-    total = 0.0
-    detail = {}
-    for curve in ("MNT4753", "MNT6753"):
+    res = {"secs": 0.0, "detail": {}, "phases": {}, "sha256": {}, "load_params_s": {}}
+    for curve in CURVES:
         out = subprocess.run([os.path.join(REF_DIR, "main"), curve, "compute", curve + "-parameters", curve + "-input",
-                              curve + "-output-ref"], cwd=cache, env=env, capture_output=True, text=True, check=True).stdout
-        m = re.search(r"Total time from input to output: : (\d+) ms", out)
-        t = float(m.group(1)) / 1e3
-        detail[curve] = t
-        total += t
-    return total, detail
+                              curve + out_suffix], cwd=d, env=env, capture_output=True, text=True, check=True).stdout
+        t = float(re.search(r"Total time from input to output: : (\d+) ms", out).group(1)) / 1e3
+        res["detail"][curve] = t
+        res["secs"] += t
+        res["load_params_s"][curve] = float(re.search(r"load params: (\d+) ms", out).group(1)) / 1e3
+        res["phases"][curve] = {m.group(1).strip(): float(m.group(2))
+                                for m in re.finditer(r"\(leave\) ([A-Za-z0-9 ]+?)\s*\t\[([0-9.]+)s", out)
+                                if "multiexp" in m.group(1) or m.group(1).strip() == "Compute the polynomial H"}
+        res["sha256"][curve] = sha256_file(os.path.join(d, curve + out_suffix))
+    return res
+
+
+def reference_result(k4, k6, rerun=False):
+    """Measure (or reuse this box's earlier measurement of) the reference prover on the step's files."""
+    d = ensure_synth(k4, k6)
+    path = os.path.join(d, "ref_result.json")
+    if os.path.exists(path) and not rerun:
+        res = json.load(open(path))
+        res["cached"] = True
+        return res
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    res = run_reference_main(d, cores)
+    res.update({"cores": cores, "wall_s": time.time() - t0, "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),
+                "constraints": (1 << k4) + (1 << k6), "cached": False})
+    json.dump(res, open(path, "w"))
+    return res
 
 
 def reference_arm(args):
@@ -92,26 +157,24 @@ def reference_arm(args):
     if not os.path.exists(os.path.join(REF_DIR, "main")):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/main not built (oracle/build_ref.sh needs /root/reference)"}))
         return
-    cores = os.cpu_count() or 1
-    cache = ensure_fast_params()
-    constraints = (1 << 14) + (1 << 10)
-    for _ in range(args.warmup):
-        run_reference_once(cache, cores)
-    t0 = time.time()
-    times = [run_reference_once(cache, cores) for _ in range(args.steps)]
-    wall = time.time() - t0
-    secs = sum(t for t, _ in times)
-    value = constraints * args.steps / secs
-    sample = ("`generate_parameters fast` (MNT4753 2^14 + MNT6753 2^10 constraints) through the unmodified libsnark "
-              "main, OMP_NUM_THREADS=%d; timed region = the reference's own 'Total time from input to output'" % cores)
+    k4, k6 = args.log2_mnt4, args.log2_mnt6
+    res = reference_result(k4, k6, rerun=args.ref_rerun)
+    value = res["constraints"] / res["secs"]
+    sample = ("the FULL workload, once: the same synthetic key / witness files the b200 arm proves (tools/synth_key), "
+              "through the unmodified libsnark ./main, OMP_NUM_THREADS=%d; timed region = the reference's own 'Total "
+              "time from input to output' (key load excluded, main.cpp:203,270)%s" %
+              (res["cores"], "; measurement reused from an earlier --impl reference call on this box (%s)" % res["when"]
+               if res["cached"] else ""))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "strong",
+            "steps_effective": 1, "warmup": args.warmup, "warmup_effective": 0,
+            "ms_per_step": 1e3 * res["secs"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32x24 (753-bit integers)", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "MNT4753 2^20 + MNT6753 2^15 Groth16 prove (7 NTT + 5 MSM each)",
-                       "sample": sample, "wall_s": wall},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+            "config": {"workload": workload_name(k4, k6), "sample": sample, "wall_s": res["wall_s"],
+                       "same_files_as_b200_arm": True},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "proof_latency_s": times[-1][1], "gpu_launches": 0}
+            "proof_latency_s": res["detail"], "reference_phases_s": res["phases"],
+            "reference_load_params_s": res["load_params_s"], "proof_sha256": res["sha256"], "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -147,42 +210,6 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def rand_fr(torch, n, seed, pinned=False):
-    """n uniformly random 752-bit values: every value < 2^752 < r is the Montgomery representation of some element"""
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    raw = torch.randint(0, 256, (n, FE), dtype=torch.uint8, generator=g)
-    raw[:, 94:] = 0
-    return raw.pin_memory() if pinned else raw
-
-
-def make_key(pkg, torch, curve, k, dev):
-    """Synthetic proving key of the challenge's shape on the device: multiples of the generators (so every base is
-    a valid curve point), with the structure observed in real keys (SURVEY.md 8 pitfalls): A has m/2 copies of one
-    point and O at index m; B1/B2 have O at indices 0 and m and a duplicate pair."""
-    m = 1 << k
-    d = m - 1
-    g1, g2 = pkg.affine_bytes(curve, 1), pkg.affine_bytes(curve, 2)
-
-    def gen(group, n, first):
-        t = torch.empty(n * pkg.affine_bytes(curve, group), dtype=torch.uint8, device=dev)
-        pkg.check(pkg.lib().b200_gen_points(curve, group, t.data_ptr(), n, first))
-        return t
-
-    A, B1, B2 = gen(1, m + 1, 1000003), gen(1, m + 1, 2000003), gen(2, m + 1, 3000017)
-    L, H = gen(1, m - 1, 4000037), gen(1, d, 5000011)
-    Av = A.view(m + 1, g1)
-    Av[2:m - 1:2] = Av[2].clone()
-    Av[m - 1] = Av[2]
-    Av[m] = 0
-    for Q, sz in ((B1, g1), (B2, g2)):
-        Qv = Q.view(m + 1, sz)
-        Qv[0] = 0
-        Qv[m] = 0
-        Qv[m - 2] = Qv[m - 3]
-    torch.cuda.synchronize()
-    return pkg.Params.from_device(curve, d, m, A, B1, B2, L, H)
-
-
 def regroup_partials(blobs, pbytes):
     """blobs[r] = rank r's partial sums of every proof of the step, concatenated (what one all_gather delivers);
     returns, per proof, the rank-major concatenation b200_prove_combine expects."""
@@ -194,31 +221,36 @@ def regroup_partials(blobs, pbytes):
     return out
 
 
-def make_input(torch, curve, k, seed):
-    """pinned host image of an input file: w[m+1] (w[0] = 1 in Montgomery form), ca, cb, cc [d+1], r"""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import mnt753 as M
-    m = 1 << k
-    n = (m + 1) + 3 * m + 1
-    img = rand_fr(torch, n, seed, pinned=True)
-    r = M.MOD_A if curve == 0 else M.MOD_B
-    one = (M.R % r).to_bytes(FE, "little")
-    img[0] = torch.frombuffer(bytearray(one), dtype=torch.uint8)
-    return img
+def step_plan(world, mode=None):
+    """Who proves what in one step. Only the 2^20 MNT4753 proof is worth sharding: one rank's share of the 2^15 MNT6753
+    proof would be 4096 points at N = 8, all latency. From 4 GPUs on the small proof runs WHOLE on the last rank while
+    the other N-1 ranks share the large one ("dedicated"); below that both are sharded over all ranks ("shard").
+    Returns (mode, ranks sharing MNT4753, rank proving MNT6753 or None when it is sharded too)."""
+    mode = mode or os.environ.get("B200_BENCH_MNT6_MODE") or ("dedicated" if world >= 4 else "shard")
+    if world == 1 or mode == "shard":
+        return "shard", list(range(world)), None
+    return "dedicated", list(range(world - 1)), world - 1
 
 
-def parity_on_reference_sample(pkg, cache):
-    """prove the reference-generated fast parameters on the GPU and compare sha256 with ./main's output"""
-    res = {}
-    for curve, name in ((0, "MNT4753"), (1, "MNT6753")):
-        ref_out = os.path.join(cache, name + "-output-ref")
-        if not os.path.exists(ref_out):
-            return None
-        key = pkg.Params.from_bytes(curve, open(os.path.join(cache, name + "-parameters"), "rb").read())
-        proof = key.prove(open(os.path.join(cache, name + "-input"), "rb").read())
-        key.close()
-        res[name] = hashlib.sha256(proof).hexdigest() == hashlib.sha256(open(ref_out, "rb").read()).hexdigest()
-    return res
+def ncu_traffic(csv_name, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the first launch of a kernel in a committed
+    `ncu --page raw --csv` export under profiles/ (row 0 names, row 1 units, then one row per launch)."""
+    path = os.path.join(ROOT, "profiles", csv_name)
+    try:
+        rows = list(csv.reader(open(path)))
+        h, units = rows[0], rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        for r in rows[2:]:
+            if kernel_substr in r[h.index("Kernel Name")]:
+                tot = 0.0
+                for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    i = h.index(name)
+                    tot += float(r[i].replace(",", "")) * scale[units[i]]
+                return {"bytes": tot, "source": "profiles/" + csv_name, "launch_ms": float(r[h.index("gpu__time_duration.sum")].replace(",", ""))
+                        if units[h.index("gpu__time_duration.sum")] == "ms" else None}
+    except Exception as e:  # a missing / reshaped export must not break the bench line
+        return {"bytes": None, "source": "profiles/%s unreadable: %s" % (csv_name, e)}
+    return {"bytes": None, "source": "profiles/%s has no launch of %s" % (csv_name, kernel_substr)}
 
 
 def b200_arm(args):
@@ -242,41 +274,75 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    shapes = ((0, args.log2_mnt4), (1, args.log2_mnt6))
-    keys = [make_key(pkg, torch, c, k, dev) for c, k in shapes]
-    # key-only preprocessing (tables of pre-shifted bases in the spare HBM), outside every timed region like the
-    # reference's own key loading (main.cpp:200-203); `no_tables` below reports the same step without it
+    k4, k6 = args.log2_mnt4, args.log2_mnt6
+    shapes = ((0, k4), (1, k6))
+    files = ensure_synth(k4, k6, wait_only=local != 0)
+    mode, big_ranks, small_rank = step_plan(world)
+    # which proofs this rank takes part in: (index into shapes, rank within the proof's group, size of that group)
+    my_jobs = []
+    if rank in big_ranks:
+        my_jobs.append((0, big_ranks.index(rank), len(big_ranks)))
+    if small_rank is None:
+        my_jobs.append((1, rank, world))
+    elif rank == small_rank:
+        my_jobs.append((1, 0, 1))
+
+    # ---- key load (B::read_params) + key-only preprocessing, outside every timed region like the reference's own key
+    # loading (main.cpp:200-203); both are reported
+    keys, load_ms, preprocess_s = {}, {}, {}
     pkg.set_precompute(True)
-    preprocess_s = [key.precompute(rank, world) for key in keys]
-    host_inputs = [make_input(torch, c, k, 77 + c) for c, k in shapes]
-    dev_inputs = [h.to(dev) for h in host_inputs]
+    for i, r, w in my_jobs:
+        name = CURVES[i]
+        t0 = time.perf_counter()
+        keys[i] = pkg.Params.from_file(shapes[i][0], os.path.join(files, name + "-parameters"))
+        load_ms[name] = dict(keys[i].load_ms(), wall=1e3 * (time.perf_counter() - t0))
+        preprocess_s[name] = keys[i].precompute(r, w)
+    import numpy as np
+    host_inputs, dev_inputs = {}, {}
+    for i, _, _ in my_jobs:
+        raw = np.fromfile(os.path.join(files, CURVES[i] + "-input"), dtype=np.uint8)
+        host_inputs[i] = torch.from_numpy(raw).pin_memory()
+        dev_inputs[i] = host_inputs[i].to(dev)
+    r_fr = [open(os.path.join(files, CURVES[i] + "-input"), "rb").read()[-FE:] for i in range(2)]
     constraints = sum(1 << k for _, k in shapes)
     pbytes = [pkg.partial_bytes(c) for c, _ in shapes]
+    proof_len = [pkg.proof_bytes(c) for c, _ in shapes]
+    slot = [max(pbytes[i], proof_len[i]) for i in range(2)]   # per-rank bytes exchanged per proof
 
     def prove_all(inputs, timings=None):
-        """one step: both proofs IN FLIGHT TOGETHER (b200_prove_batch: the 2^15 MNT6753 proof runs underneath the
-        2^20 MNT4753 one); N > 1: one all_gather of every rank's partial sums, rank 0 combines. Returns the proof
-        bytes on rank 0."""
+        """one step: this rank's proofs IN FLIGHT TOGETHER (b200_prove_batch); N > 1: one all_gather of every rank's
+        partial sums (or finished small proof), rank 0 combines. Returns the two proofs' bytes on rank 0."""
         t0 = time.perf_counter()
         if world == 1:
-            proofs, tms = pkg.prove_batch([(keys[i], inputs[i]) for i in range(len(shapes))], timings=True)
+            proofs, tms = pkg.prove_batch([(keys[i], inputs[i]) for i, _, _ in my_jobs], timings=True)
         else:
-            parts, tms = pkg.prove_batch([(keys[i], inputs[i], rank, world) for i in range(len(shapes))], timings=True)
-            mine = torch.frombuffer(bytearray(b"".join(parts)), dtype=torch.uint8).to(dev)
+            jobs = [(keys[i], inputs[i], r, w) if w > 1 else (keys[i], inputs[i]) for i, r, w in my_jobs]
+            outs, tms = pkg.prove_batch(jobs, timings=True) if jobs else ([], [])
+            blob = bytearray(sum(slot))
+            for (i, _, _), o in zip(my_jobs, outs):
+                off = sum(slot[:i])
+                blob[off:off + len(o)] = o
+            mine = torch.frombuffer(blob, dtype=torch.uint8).to(dev)
             allp = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allp, mine)
             proofs = []
             if rank == 0:
                 blobs = [bytes(t.cpu().numpy().tobytes()) for t in allp]
-                for i, ((curve, k), parts_i) in enumerate(zip(shapes, regroup_partials(blobs, pbytes))):
-                    r_fr = bytes(host_inputs[i][-1].numpy().tobytes())
-                    proofs.append(pkg.prove_combine(curve, parts_i, world, r_fr))
+                parts = regroup_partials(blobs, slot)
+                big = b"".join(parts[0][r * slot[0]:r * slot[0] + pbytes[0]] for r in big_ranks)
+                proofs.append(pkg.prove_combine(0, big, len(big_ranks), r_fr[0]))
+                if small_rank is None:
+                    small = b"".join(parts[1][r * slot[1]:r * slot[1] + pbytes[1]] for r in range(world))
+                    proofs.append(pkg.prove_combine(1, small, world, r_fr[1]))
+                else:
+                    proofs.append(parts[1][small_rank * slot[1]:small_rank * slot[1] + proof_len[1]])
         if timings is not None:
             wall = time.perf_counter() - t0
-            for tm in tms:
+            for (i, _, _), tm in zip(my_jobs, tms):
                 # latency of this proof inside the concurrent step (its own call's wall clock); step_wall_s = both
                 tm["wall_s"] = tm["total_ms"] / 1e3
                 tm["step_wall_s"] = wall
+                tm["curve"] = CURVES[i]
                 timings.append(tm)
         return proofs
 
@@ -306,11 +372,15 @@ def b200_arm(args):
     ms_e2e, tms_e2e, proofs_e2e = timed(host_inputs, args.steps)
     pkg.set_precompute(False)
     prove_all(dev_inputs)
-    ms_nt, _, proofs_nt = timed(dev_inputs, max(1, min(2, args.steps)))
     nt_steps = max(1, min(2, args.steps))
+    ms_nt, _, proofs_nt = timed(dev_inputs, nt_steps)
     pkg.set_precompute(True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    if world > 1:
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
 
     if rank != 0:
         if world > 1:
@@ -320,15 +390,29 @@ def b200_arm(args):
     assert proofs_dev == proofs_nt, "table and table-free MSM paths disagree"
     value = constraints * args.steps / (ms_dev / 1e3)
     e2e = constraints * args.steps / (ms_e2e / 1e3)
-    h2d = sum(h.numel() for h in host_inputs)
-    d2h = sum(pbytes)
+    h2d = sum(h.numel() for h in host_inputs.values())
+    d2h = sum(pbytes[i] if w > 1 else proof_len[i] for i, _, w in my_jobs)
 
-    # Roofline of the dominant kernel, msm_accumulate_kernel<G1> (4 of the 5 MSMs of each proof). Inside a proof the
+    # ---- parity with the reference on the step's own files (written by --impl reference on this box)
+    parity = {}
+    ref_path = os.path.join(files, "ref_result.json")
+    ref = json.load(open(ref_path)) if os.path.exists(ref_path) else None
+    mine_sha = {CURVES[i]: hashlib.sha256(proofs_dev[i]).hexdigest() for i in range(2)}
+    if ref:
+        parity["sha256_equal_to_reference_main_full_size"] = {c: mine_sha[c] == ref["sha256"][c] for c in CURVES}
+        parity["reference_run"] = "oracle/_ref/main on the same files, %s (--impl reference on this box)" % ref["when"]
+    else:
+        parity["sha256_equal_to_reference_main_full_size"] = None
+        parity["reference_run"] = "no reference output for these files on this box (run `bench.py --impl reference` first)"
+    parity["proof_sha256"] = mine_sha
+
+    # ---- roofline of the dominant kernel: the G1 bucket accumulation (4 of the 5 MSMs of each proof). Inside a proof the
     # five MSMs run concurrently on five streams, so per-kernel event times overlap; the kernel is therefore timed
     # here in isolation (same key, same scalars, one MSM at a time through b200_params_msm, CUDA events around the
     # accumulation launches on the MSM's stream). Bound: the INT32 multiplier (IMAD.WIDE / fmaheavy) pipe.
     imad = pkg.imad_peak()
     peak = max(imad["mad_wide_mac32_per_s"], imad["carry_chain_mac32_per_s"])
+    accum_mode = "affine" if pkg.batch_affine_enabled() else "xyzz"
     iso = {"g1": [], "g2": [], "a_merged": []}
     plans = {}
     if world == 1:
@@ -344,46 +428,41 @@ def b200_arm(args):
                 iso["g2" if which == 2 else ("a_merged" if which == 0 else "g1")].append(
                     (curve, n, ph["accumulate"], ph["reduce"]))
                 plans[(curve, which == 2)] = pkg.msm_last_plan()
-    else:
-        # sharded run: per-kernel event times of rank 0 inside the timed region (the five MSMs of a proof overlap on
-        # five streams, so these over-state the kernel time; the isolated measurement is the N=1 line's)
-        for i, (curve, k) in enumerate(shapes):
-            n = (1 << k) // world
-            for _ in range(4):
-                iso["g1"].append((curve, n, phases["g1"]["accumulate"] / (8 * args.steps), phases["g1"]["reduce"] / (8 * args.steps)))
-            iso["g2"].append((curve, n, phases["g2"]["accumulate"] / (2 * args.steps), phases["g2"]["reduce"] / (2 * args.steps)))
-    g1_mac = sum(MAC32_PER_POINT["g1"] * n for _, n, _, _ in iso["g1"])
-    acc_ms_g1 = sum(t for _, _, t, _ in iso["g1"])
-    achieved = g1_mac / (acc_ms_g1 / 1e3)
-    g1_big = [t for c, _, t, _ in iso["g1"] if c == 0]
-    roofline = {"bound": "imad", "bound_note": "INT32 multiplier (IMAD.WIDE / fmaheavy) pipe; neither HBM nor tensor bound, SURVEY.md 8d",
-                "kernel": "msm_accumulate_kernel<G1>", "achieved": achieved / 1e12, "peak": peak / 1e12,
-                "unit": "TMAC32/s", "frac": achieved / peak if peak else None,
-                "frac_issued": (sum(plans[(c, False)]["windows"] * 10 * 1152 * n for c, n, _, _ in iso["g1"]) / (acc_ms_g1 / 1e3) / peak
-                                if plans else None),
-                "issued_note": "IMAD.WIDE actually issued per point = windows x 10 multiplications x 1152, over the same time",
-                "windows": {("MNT4753" if c == 0 else "MNT6753") + ("_g2" if g2 else "_g1"): v for (c, g2), v in plans.items()},
-                "traffic": 14.65e9 + 15.78e9,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-point launch, ncu --set full "
-                                "(profiles/prof_accumulate_g1_r01_v3_raw.csv); algorithmic: 36 windows x 2^20 x 192 B = 7.2 GB "
-                                "of table reads, the rest is per-thread stack traffic (field operands live in local memory); "
-                                "0.6 TB/s, far below the HBM roofline",
-                "launches": len(iso["g1"]), "avg_launch_ms": statistics.mean(g1_big) if g1_big else None,
-                "a_query_equal_bases_merged_ms": [round(t, 2) for _, _, t, _ in iso["a_merged"]],
-                "peak_source": "measured live by b200_imad_peak (IMAD.WIDE carry-chain microbenchmark on all SMs)",
-                "timing": "kernel timed alone with CUDA events on its stream (inside a proof 5 MSMs overlap)",
-                "note": "achieved uses SURVEY 8d's algorithmic 620928 MAC32/point (48 windows x 11 mul x 1176); with the "
-                        "pre-shifted base tables and XYZZ additions the kernel issues 36-42 windows x 10 mul, so frac > 1 "
-                        "means less work per point, not a faster pipe: ncu shows the fmaheavy pipe 84-94 % busy (profiles/)"}
-    g2_mac = sum((MAC32_PER_POINT["g2_fq2"] if c == 0 else MAC32_PER_POINT["g2_fq3"]) * n for c, n, _, _ in iso["g2"])
-    acc_ms_g2 = sum(t for _, _, t, _ in iso["g2"])
-    roofline_g2 = {"kernel": "msm_accumulate_kernel<G2>", "achieved": g2_mac / (acc_ms_g2 / 1e3) / 1e12,
-                   "peak": peak / 1e12, "unit": "TMAC32/s", "frac": (g2_mac / (acc_ms_g2 / 1e3)) / peak if peak else None,
-                   "launch_ms": [round(t, 2) for _, _, t, _ in iso["g2"]],
-                   "traffic": 147.5e9 + 228.1e9,
-                   "traffic_note": "2^20-point Fq2 launch (profiles/prof_accumulate_g2_r01_v3_raw.csv): 14.5 GB algorithmic; the "
-                                   "2.7 KB stack frames of 75 776 resident threads (205 MB) exceed the 126 MB L2, so operand "
-                                   "round trips reach DRAM at 2.4 TB/s - the reason the pipe is 85 % busy here vs 94 % for G1"}
+    roofline = roofline_g2 = None
+    if world == 1:
+        acc_ms_g1 = sum(t for _, _, t, _ in iso["g1"])
+        g1_alg = sum(MAC32_PER_POINT["g1"] * n for _, n, _, _ in iso["g1"])
+        g1_issued = sum(plans[(c, False)]["windows"] * ISSUED_MULS[accum_mode]["g1"] * IMAD_PER_MUL * n for c, n, _, _ in iso["g1"])
+        g1_big = [t for c, _, t, _ in iso["g1"] if c == 0]
+        tr = ncu_traffic("prof_accumulate_g1_r02_raw.csv", "Mnt4G1")
+        roofline = {"bound": "imad", "bound_note": "INT32 multiplier (IMAD.WIDE / fmaheavy) pipe; neither HBM nor tensor bound, SURVEY.md 8d",
+                    "kernel": "G1 bucket accumulation (%s)" % accum_mode,
+                    "achieved": g1_issued / (acc_ms_g1 / 1e3) / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s",
+                    "frac": g1_issued / (acc_ms_g1 / 1e3) / peak,
+                    "frac_note": "ISSUED IMAD.WIDE (windows x %d Fq multiplications per bucket insertion x 1152) / time / measured peak" % ISSUED_MULS[accum_mode]["g1"],
+                    "frac_algorithmic": g1_alg / (acc_ms_g1 / 1e3) / peak,
+                    "algorithmic_note": "SURVEY 8d credits 620928 MAC32 per point (48 windows x 11 mul x 1176); the kernel does the same sum "
+                                        "with fewer windows (pre-shifted tables) and cheaper additions, so this ratio may exceed 1: it "
+                                        "measures work avoided, not pipe speed",
+                    "peak_nominal": imad["nominal_mac32_per_s"] / 1e12,
+                    "windows": {CURVES[c] + ("_g2" if g2 else "_g1"): v for (c, g2), v in plans.items()},
+                    "traffic": tr["bytes"], "traffic_source": tr["source"],
+                    "traffic_algorithmic": plans[(0, False)]["windows"] * ((1 << k4) - 1) * 192.0,
+                    "launches": len(iso["g1"]), "avg_launch_ms": statistics.mean(g1_big) if g1_big else None,
+                    "a_query_equal_bases_merged_ms": [round(t, 2) for _, _, t, _ in iso["a_merged"]],
+                    "peak_source": "measured live by b200_imad_peak (independent IMAD.WIDE chains on all SMs, 50 ms runs)",
+                    "timing": "kernel timed alone with CUDA events on its stream (inside a proof 5 MSMs overlap)"}
+        acc_ms_g2 = sum(t for _, _, t, _ in iso["g2"])
+        g2_alg = sum((MAC32_PER_POINT["g2_fq2"] if c == 0 else MAC32_PER_POINT["g2_fq3"]) * n for c, n, _, _ in iso["g2"])
+        g2_issued = sum(plans[(c, True)]["windows"] * ISSUED_MULS[accum_mode]["g2_fq2" if c == 0 else "g2_fq3"] * IMAD_PER_MUL * n
+                        for c, n, _, _ in iso["g2"])
+        tr2 = ncu_traffic("prof_accumulate_g2_r02_raw.csv", "Mnt4G2")
+        roofline_g2 = {"kernel": "G2 bucket accumulation (%s)" % accum_mode, "achieved": g2_issued / (acc_ms_g2 / 1e3) / 1e12,
+                       "peak": peak / 1e12, "unit": "TMAC32/s", "frac": g2_issued / (acc_ms_g2 / 1e3) / peak,
+                       "frac_algorithmic": g2_alg / (acc_ms_g2 / 1e3) / peak,
+                       "launch_ms": [round(t, 2) for _, _, t, _ in iso["g2"]],
+                       "traffic": tr2["bytes"], "traffic_source": tr2["source"],
+                       "traffic_algorithmic": plans[(0, True)]["windows"] * ((1 << k4) + 1) * 384.0}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -391,76 +470,101 @@ def b200_arm(args):
         pass
     # compute_H timed alone (inside a proof it is enqueued asynchronously under the MSMs): CUDA events on the default
     # stream, which is the stream ntt.cu launches on
-    ch_ms = 0.0
-    for i, (curve, k) in enumerate(shapes):
-        m = 1 << k
-        dom = pkg.Domain(curve, m)
-        bufs = [dev_inputs[i][:m].clone() for _ in range(3)]
-        out = torch.empty((m + 1) * FE, dtype=torch.uint8, device=dev)
-        dom.compute_h(*bufs, out)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(args.steps):
+    roofline_ntt = None
+    if world == 1:
+        ch_ms = 0.0
+        for i, (curve, k) in enumerate(shapes):
+            m = 1 << k
+            dom = pkg.Domain(curve, m)
+            bufs = [dev_inputs[i][:m * FE].clone() for _ in range(3)]
+            out = torch.empty((m + 1) * FE, dtype=torch.uint8, device=dev)
             dom.compute_h(*bufs, out)
-        e1.record()
-        torch.cuda.synchronize()
-        ch_ms += e0.elapsed_time(e1)
-        dom.close()
-    # compute_H: 7 NTTs of m elements + pointwise ops; algorithmic HBM bytes 7*192*m + 4*96*m
-    ch_bytes = args.steps * sum((7 * 192 + 4 * 96) * (1 << k) for _, k in shapes)
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roofline_ntt = {"bound": "hbm", "kernel": "ntt_pass_kernel (compute_H: 7 NTT + pointwise)",
-                    "achieved": ch_bytes / (ch_ms / 1e3) / 1e9 if ch_ms else None, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": (ch_bytes / (ch_ms / 1e3) / 1e9) / hbm_peak if ch_ms else None,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
-                    "ms_per_step": ch_ms / args.steps,
-                    "traffic": 717e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the three passes of ONE 2^20 "
-                    "transform (ncu --set full, profiles/prof_ntt_r01_v3_raw.csv) vs 201 MB algorithmic per transform (603 MB "
-                    "for three read-write sweeps); fmaheavy pipe 80 % busy",
-                    "imad_frac": (args.steps * sum((7 * 588 * k + 4 * 1176) * (1 << k) for _, k in shapes) / (ch_ms / 1e3)) / peak if ch_ms else None,
-                    "note": "753-bit butterflies are IMAD-bound (588 MAC32 per 96 B element-stage, 61 MAC32/byte): imad_frac is "
-                            "the fraction of the measured IMAD.WIDE peak, the binding roofline; see DESIGN.md 4.3"}
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.steps):
+                dom.compute_h(*bufs, out)
+            e1.record()
+            torch.cuda.synchronize()
+            ch_ms += e0.elapsed_time(e1)
+            dom.close()
+        # compute_H: 7 NTTs of m elements + pointwise ops; algorithmic HBM bytes 7*192*m + 4*96*m
+        ch_bytes = args.steps * sum((7 * 192 + 4 * 96) * (1 << k) for _, k in shapes)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        trn = ncu_traffic("prof_ntt_r01_v3_raw.csv", "ntt_pass_kernel")
+        roofline_ntt = {"bound": "hbm", "kernel": "ntt_pass_kernel (compute_H: 7 NTT + pointwise)",
+                        "achieved": ch_bytes / (ch_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": (ch_bytes / (ch_ms / 1e3) / 1e9) / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
+                        "ms_per_step": ch_ms / args.steps,
+                        "traffic_first_pass": trn["bytes"], "traffic_source": trn["source"],
+                        "imad_frac": (args.steps * sum((7 * 588 * k + 4 * 1176) * (1 << k) for _, k in shapes) / (ch_ms / 1e3)) / peak,
+                        "note": "753-bit butterflies are IMAD-bound (588 MAC32 per 96 B element-stage, 61 MAC32/byte): imad_frac is "
+                                "the fraction of the measured IMAD.WIDE peak, the binding roofline; see DESIGN.md 4.3"}
 
     per_curve = {}
     for i, (curve, k) in enumerate(shapes):
-        ts = [t for j, t in enumerate(tms_dev) if j % len(shapes) == i]
-        per_curve[pkg.CURVE_NAMES[curve]] = {
-            "log2_constraints": k, "latency_s": statistics.mean(t["wall_s"] for t in ts),
-            "phases_ms": {key: statistics.mean(t[key] for t in ts) for key in ts[0] if key.endswith("_ms")}}
+        ts = [t for t in tms_dev if t["curve"] == CURVES[i]]
+        if ts:
+            per_curve[CURVES[i]] = {
+                "log2_constraints": k, "latency_s": statistics.mean(t["wall_s"] for t in ts),
+                "phases_ms": {key: statistics.mean(t[key] for t in ts) for key in ts[0] if key.endswith("_ms")}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32x24 (753-bit integers)", "data": "synthetic", "impl": "b200",
-            "config": {"workload": "MNT4753 2^%d + MNT6753 2^%d Groth16 prove (7 NTT + 5 MSM each), MSMs sharded over %d GPU(s) by point range"
-                                   % (args.log2_mnt4, args.log2_mnt6, world),
+            "config": {"workload": workload_name(k4, k6, world),
+                       "files": "tools/synth_key output in the reference's formats; the reference arm proves the same files",
                        "l2": "inputs larger than L2: each step streams >1.6 GB of bases and 416 MB of scalars",
                        "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys",
-                       "key_preprocess": "pre-shifted base tables 2^(start_j)*P_i per MSM window, built once per key "
-                                         "in %s s (MNT4753, MNT6753), outside the timed region; see no_tables" % json.dumps([round(x, 2) for x in preprocess_s])},
+                       "multi_gpu": {"mode": mode, "mnt4753_ranks": big_ranks, "mnt6753_rank": small_rank},
+                       "accumulation": accum_mode,
+                       "key_preprocess": "pre-shifted base tables 2^(start_j)*P_i per MSM window, built once per key, "
+                                         "outside the timed region (see key_load); see no_tables"},
+            "key_load": {"from_file_ms": load_ms, "precompute_s": preprocess_s,
+                         "note": "rank 0's keys; B::read_params = chunked pinned reads + async H2D (reference: 8.0 s parse "
+                                 "for the MNT4753 key, BASELINE.md 2); precompute = base tables + equal-base grouping"},
             "no_tables": {"value": constraints * nt_steps / (ms_nt / 1e3), "unit": UNIT, "ms_per_step": ms_nt / nt_steps,
                           "note": "same step with B200_PRECOMPUTE=0 (per-window buckets + host window combine)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "roofline_g2": roofline_g2,
-            "roofline_ntt": roofline_ntt, "proof_pair_latency_s": ms_dev / args.steps / 1e3, "proof_latency_s": {n: v["latency_s"] for n, v in per_curve.items()},
-            "per_curve": per_curve,
-            "msm_points_per_s": {
-                "note": "one MSM alone on one GPU, accumulate + reduce phases, points of this rank's slice",
-                "g1_2^%d" % args.log2_mnt4: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g1"] if c == 0), default=None),
-                "g2_fq2_2^%d" % args.log2_mnt4: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g2"] if c == 0), default=None),
-                "g1_2^%d" % args.log2_mnt6: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g1"] if c == 1), default=None),
-                "g2_fq3_2^%d" % args.log2_mnt6: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g2"] if c == 1), default=None)},
+            "roofline_ntt": roofline_ntt, "proof_pair_latency_s": ms_dev / args.steps / 1e3,
+            "proof_latency_s": {n: v["latency_s"] for n, v in per_curve.items()},
+            "per_curve": per_curve, "parity": parity,
             "msm_phase_ms_per_step": {g: {k: v / args.steps for k, v in ph.items()} for g, ph in phases.items()},
             "imad_peak": imad}
+    if world == 1:
+        line["msm_points_per_s"] = {
+            "note": "one MSM alone on one GPU, accumulate + reduce phases",
+            "g1_2^%d" % k4: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g1"] if c == 0), default=None),
+            "g2_fq2_2^%d" % k4: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g2"] if c == 0), default=None),
+            "g1_2^%d" % k6: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g1"] if c == 1), default=None),
+            "g2_fq3_2^%d" % k6: max((n / ((a + r) / 1e3) for c, n, a, r in iso["g2"] if c == 1), default=None)}
     if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(REF_DIR, "main")):
-        cores = os.cpu_count() or 1
-        cache = ensure_fast_params()
-        secs, detail = run_reference_once(cache, cores)
-        cval = ((1 << 14) + (1 << 10)) / secs
-        line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "reference",
-                                "sample": "`generate_parameters fast` (MNT4753 2^14 + MNT6753 2^10) through the unmodified "
-                                          "libsnark main (Bos-Coster, OpenMP), one run; seconds per curve: %s" % json.dumps(detail)}
-        line["parity"] = {"sha256_equal_to_reference_main_on_fast_params": parity_on_reference_sample(pkg, cache)}
+        if ref:
+            cval = ref["constraints"] / ref["secs"]
+            line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": ref["cores"], "kind": "reference",
+                                    "sample": "the full workload (same files), measured once by `bench.py --impl reference` on this "
+                                              "box at %s; seconds per curve: %s" % (ref["when"], json.dumps(ref["detail"]))}
+        else:
+            # no full-size reference run on this box yet: a bounded sample, the same generator at 1/16 of the size
+            ks = (max(k4 - 4, 4), max(k6 - 4, 4))
+            sd = ensure_synth(*ks)
+            cores = os.cpu_count() or 1
+            res = run_reference_main(sd, cores)
+            line["cpu_baseline"] = {"value": ((1 << ks[0]) + (1 << ks[1])) / res["secs"], "unit": UNIT, "cores": cores,
+                                    "kind": "reference",
+                                    "sample": "BOUNDED SAMPLE: MNT4753 2^%d + MNT6753 2^%d (1/16 of the workload, same generator) through "
+                                              "the unmodified libsnark main, one run; `bench.py --impl reference` measures the full "
+                                              "workload; seconds per curve: %s" % (ks[0], ks[1], json.dumps(res["detail"]))}
+            # and the sample's proofs must agree too
+            ok = {}
+            for i, name in enumerate(CURVES):
+                key = pkg.Params.from_file(i, os.path.join(sd, name + "-parameters"))
+                proof = key.prove(open(os.path.join(sd, name + "-input"), "rb").read())
+                key.close()
+                ok[name] = hashlib.sha256(proof).hexdigest() == res["sha256"][name]
+            parity["sha256_equal_to_reference_main_on_sample"] = ok
     elif world == 1:
         line["cpu_baseline"] = None
     print(json.dumps(line))

@@ -99,6 +99,14 @@ typedef struct b200_params b200_params;
 /* h_image = byte image of a parameter file (libsnark/main.cpp:42-61): d, m, A[m+1], B1[m+1], B2[m+1], L[m-1], H[d].
  * replaces B::read_params (prover_reference_functions.cpp:291-345) */
 int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_params **out);
+/* Load a parameter file straight from disk (the reference's B::read_params takes a path too,
+ * prover_reference_functions.cpp:291-345, and parses it element by element with fread, serialization.hpp:83-111: 8.0 s
+ * for the 1.2 GB MNT4753 key). Here: one bulk read per 64 MB chunk into two pinned staging buffers,
+ * each chunk's host->device copy running asynchronously under the read of the next one; the wire encoding IS the
+ * device layout, so nothing is parsed. b200_params_load_ms: out3 = {file read, waiting for copies, total} of that load
+ * (zeros for keys that were not loaded from a file). */
+int b200_params_from_file(int curve, const char *path, b200_params **out);
+int b200_params_load_ms(const b200_params *p, double *out3);
 /* adopt caller-owned device arrays (synthetic keys built on the device) */
 int b200_params_from_device(int curve, size_t d, size_t m, const void *d_A, const void *d_B1, const void *d_B2,
                             const void *d_L, const void *d_H, b200_params **out);
@@ -155,14 +163,19 @@ int b200_prove_batch(b200_proof_job *jobs, int count);
 /* ---- test / bench hooks: element-wise application of the device primitives the kernels are built from ------- */
 /* op: 0 add 1 sub 2 mul 3 sqr 4 from_mont 5 to_mont 6 inv ; tag: 0 = modulus A, 1 = modulus B */
 int b200_dev_fp_op(int tag, int op, const void *d_a, const void *d_b, void *d_r, size_t n);
-/* G2 coordinate-field op (Fq2 for MNT4753, Fq3 for MNT6753). op: 0 add 1 sub 2 mul 3 sqr */
+/* G2 coordinate-field op (Fq2 for MNT4753, Fq3 for MNT6753). op: 0 add 1 sub 2 mul 3 sqr 4 inv (fp2.tcc:128-142, fp3.tcc:125-143) */
 int b200_dev_fqe_op(int curve, int op, const void *d_a, const void *d_b, void *d_r, size_t n);
 /* group: 1 = G1, 2 = G2. op: 0 add(proj,proj) 1 dbl(proj) 2 mixed_add(proj, affine) 3 to_affine(proj)->affine */
 int b200_dev_group_op(int curve, int group, int op, const void *d_p, const void *d_q, void *d_r, size_t n);
 /* synthetic bases: out[i] = (first + i) * G  in affine wire format, G = the curve's G1/G2 generator */
 int b200_gen_points(int curve, int group, void *d_out_affine, size_t n, uint64_t first);
-/* IMAD roofline microbenchmark: independent IMAD.WIDE chains on every SM; returns MAC32/s */
+/* IMAD roofline microbenchmark on every SM, runs of >= 50 ms each (shorter ones under-read: the clock is still
+ * ramping). mac32_per_s[0] = independent IMAD.WIDE chains, [1] = the multiplier's (mad.lo.cc, madc.hi.cc) carry-chain
+ * pattern, [2] = the NOMINAL rate 32 IMAD.WIDE / clk / SM x SMs x the device's maximum SM clock; ms[0..1] = the timed
+ * runs, ms[2] = that clock in MHz. */
 int b200_imad_peak(double *mac32_per_s, double *ms);
+/* 1 when bucket accumulation currently uses batched affine additions, 0 for XYZZ mixed additions */
+int b200_msm_get_batch_affine(void);
 /* number of CUDA kernels this library has launched so far (bench.py: gpu_launches) */
 unsigned long long b200_launch_count(void);
 /* accumulated MSM phase times (ms) since the last reset: out10 = G1 {digits, sort, accumulate, reduce, host tail},

@@ -91,6 +91,7 @@ _SIGNATURES = {
     "b200_host_equal_bases": (_i, [_vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "b200_msm_set_window": (_i, [_i]),
     "b200_msm_set_batch_affine": (_i, [_i]),
+    "b200_msm_get_batch_affine": (_i, []),
     "b200_msm_last_phase_ms": (_i, [ctypes.POINTER(ctypes.c_double)]),
     "b200_msm_last_plan": (_i, [ctypes.POINTER(ctypes.c_int)]),
     "b200_msm_phase_totals": (_i, [ctypes.POINTER(ctypes.c_double), _i]),
@@ -105,6 +106,8 @@ _SIGNATURES = {
     "b200_g2_from_affine": (_i, [_i, _vp, _vp]),
     "b200_host_fp_op": (_i, [_i, _i, _vp, _vp, _vp]),
     "b200_params_from_host": (_i, [_i, _vp, _sz, ctypes.POINTER(_vp)]),
+    "b200_params_from_file": (_i, [_i, ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "b200_params_load_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_double)]),
     "b200_params_from_device": (_i, [_i, _sz, _sz, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "b200_params_destroy": (_i, [_vp]),
     "b200_params_precompute": (_i, [_vp, _i, _i]),
@@ -294,6 +297,19 @@ class Params:
         return cls(curve, h)
 
     @classmethod
+    def from_file(cls, curve, path):
+        """B::read_params: load a parameter file (chunked reads into pinned memory, asynchronous H2D)"""
+        h = ctypes.c_void_p()
+        check(lib().b200_params_from_file(curve, os.fsencode(path), ctypes.byref(h)))
+        return cls(curve, h)
+
+    def load_ms(self):
+        """{read, copy_wait, total} milliseconds of from_file"""
+        out = (ctypes.c_double * 3)()
+        check(lib().b200_params_load_ms(self.h, out))
+        return {"read": out[0], "copy_wait": out[1], "total": out[2]}
+
+    @classmethod
     def from_device(cls, curve, d, m, A, B1, B2, L, H):
         h = ctypes.c_void_p()
         check(lib().b200_params_from_device(curve, d, m, _ptr(A), _ptr(B1), _ptr(B2), _ptr(L), _ptr(H), ctypes.byref(h)))
@@ -419,8 +435,13 @@ def set_precompute(on):
     check(lib().b200_set_precompute(1 if on else 0))
 
 
+def batch_affine_enabled():
+    return bool(lib().b200_msm_get_batch_affine())
+
+
 def imad_peak():
-    v = (ctypes.c_double * 2)()
-    ms = (ctypes.c_double * 2)()
+    v = (ctypes.c_double * 3)()
+    ms = (ctypes.c_double * 3)()
     check(lib().b200_imad_peak(v, ms))
-    return {"mad_wide_mac32_per_s": v[0], "carry_chain_mac32_per_s": v[1], "ms": [ms[0], ms[1]]}
+    return {"mad_wide_mac32_per_s": v[0], "carry_chain_mac32_per_s": v[1], "nominal_mac32_per_s": v[2],
+            "ms": [ms[0], ms[1]], "sm_clock_mhz": ms[2]}

@@ -5,6 +5,7 @@
 #include <functional>
 #include <condition_variable>
 #include <future>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cstdlib>
@@ -140,6 +141,7 @@ struct Precomputed {
 struct b200_params {
   int curve;
   size_t d, m;
+  double load_ms[3] = {0, 0, 0};  // from_file: read, copy wait, total
   const void *q[5];  // A, B1, B2, L, H (device)
   DevBuf owned;      // backing store when loaded from a host image
   b200_domain *dom;
@@ -343,6 +345,7 @@ int b200_msm_set_batch_affine(int on) {
   msm_set_batch_affine(on);
   return 0;
 }
+int b200_msm_get_batch_affine(void) { return msm_use_batch_affine() ? 1 : 0; }
 int b200_msm_set_window(int c) {
   msm_set_window(c);
   return 0;
@@ -426,6 +429,16 @@ static int check_key_dims(size_t d, size_t m) {
     return set_error(-4, "key dimensions d=%zu m=%zu out of range (need 1 <= d < 2^30, 2 <= m < 2^30)", d, m);
   return 0;
 }
+static void params_set_queries(b200_params *p) {
+  const size_t g1 = affine_bytes(p->curve, 1), g2 = affine_bytes(p->curve, 2), m = p->m;
+  char *base = (char *)p->owned.p;
+  p->q[0] = base;
+  p->q[1] = base + g1 * (m + 1);
+  p->q[2] = base + 2 * g1 * (m + 1);
+  p->q[3] = base + 2 * g1 * (m + 1) + g2 * (m + 1);
+  p->q[4] = base + 2 * g1 * (m + 1) + g2 * (m + 1) + g1 * (m - 1);
+}
+
 static int params_finish(b200_params *p) {
   b200_domain *dom = nullptr;
   B200_CHECK(b200_domain_create(p->curve, p->d + 1, &dom));
@@ -464,12 +477,7 @@ int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_par
     delete p;
     return set_error(-100 - (int)e, "H2D of parameters failed: %s", cudaGetErrorString(e));
   }
-  char *base = (char *)p->owned.p;
-  p->q[0] = base;
-  p->q[1] = base + g1 * (m + 1);
-  p->q[2] = base + 2 * g1 * (m + 1);
-  p->q[3] = base + 2 * g1 * (m + 1) + g2 * (m + 1);
-  p->q[4] = base + 2 * g1 * (m + 1) + g2 * (m + 1) + g1 * (m - 1);
+  params_set_queries(p);
   rc = params_finish(p);
   if (rc) {
     b200_params_destroy(p);
@@ -478,6 +486,90 @@ int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_par
   *out = p;
   return 0;
 }
+int b200_params_from_file(int curve, const char *path, b200_params **out) {
+  B200_CHECK(require_device());
+  if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
+  const double t0 = now_ms();
+  FILE *f = fopen(path, "rb");
+  if (!f) return set_error(-4, "cannot open parameter file %s", path);
+  struct Closer {
+    FILE *f;
+    ~Closer() { fclose(f); }
+  } closer{f};
+  uint64_t hdr[2];
+  if (fread(hdr, 1, 16, f) != 16) return set_error(-4, "parameter file %s is shorter than its header", path);
+  const size_t d = (size_t)hdr[0], m = (size_t)hdr[1];
+  B200_CHECK(check_key_dims(d, m));
+  const size_t g1 = affine_bytes(curve, 1), g2 = affine_bytes(curve, 2);
+  const size_t body = g1 * (2 * (m + 1) + (m - 1) + d) + g2 * (m + 1);
+  if (fseek(f, 0, SEEK_END) != 0) return set_error(-4, "cannot seek in %s", path);
+  const long fsize = ftell(f);
+  if (fsize < 0 || (size_t)fsize != body + 16)
+    return set_error(-4, "parameter file %s has %ld bytes, expected %zu for d=%zu m=%zu", path, fsize, body + 16, d, m);
+  fseek(f, 16, SEEK_SET);
+  std::unique_ptr<b200_params> p(new b200_params());
+  p->curve = curve;
+  p->d = d;
+  p->m = m;
+  p->dom = nullptr;
+  B200_CHECK(p->owned.alloc(body));
+  // two pinned staging buffers; chunk k's copy runs while chunk k+1 is being read
+  constexpr size_t kChunk = (size_t)64 << 20;
+  struct Stage {
+    void *h = nullptr;
+    cudaEvent_t done = nullptr;
+    ~Stage() {
+      if (h) cudaFreeHost(h);
+      if (done) cudaEventDestroy(done);
+    }
+  } stage[2];
+  cudaStream_t copy_stream = nullptr;
+  B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  struct StreamCloser {
+    cudaStream_t s;
+    ~StreamCloser() { cudaStreamDestroy(s); }
+  } sc{copy_stream};
+  const size_t chunk = body < kChunk ? (body ? body : 16) : kChunk;
+  for (int i = 0; i < 2; i++) {
+    B200_CUDA_CHECK(cudaMallocHost(&stage[i].h, chunk));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&stage[i].done, cudaEventDisableTiming));
+  }
+  double read_ms = 0, wait_ms = 0;
+  int k = 0;
+  for (size_t off = 0; off < body; off += chunk, k ^= 1) {
+    const size_t n = body - off < chunk ? body - off : chunk;
+    double a = now_ms();
+    B200_CUDA_CHECK(cudaEventSynchronize(stage[k].done));  // the copy that last used this buffer (no-op the first time)
+    double b = now_ms();
+    if (fread(stage[k].h, 1, n, f) != n) return set_error(-4, "short read on %s", path);
+    double c = now_ms();
+    wait_ms += b - a;
+    read_ms += c - b;
+    B200_CUDA_CHECK(cudaMemcpyAsync((char *)p->owned.p + off, stage[k].h, n, cudaMemcpyHostToDevice, copy_stream));
+    B200_CUDA_CHECK(cudaEventRecord(stage[k].done, copy_stream));
+  }
+  {
+    double a = now_ms();
+    B200_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+    wait_ms += now_ms() - a;
+  }
+  params_set_queries(p.get());
+  int rc = params_finish(p.get());
+  if (rc) {
+    b200_domain_destroy(p->dom);
+    return rc;
+  }
+  p->load_ms[0] = read_ms;
+  p->load_ms[1] = wait_ms;
+  p->load_ms[2] = now_ms() - t0;
+  *out = p.release();
+  return 0;
+}
+int b200_params_load_ms(const b200_params *p, double *out3) {
+  for (int i = 0; i < 3; i++) out3[i] = p->load_ms[i];
+  return 0;
+}
+
 int b200_params_from_device(int curve, size_t d, size_t m, const void *A, const void *B1, const void *B2, const void *L,
                             const void *H, b200_params **out) {
   B200_CHECK(require_device());

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(128) field_op_kernel(int op, const F *__restri
     case 0: F::add(z, x, y); break;
     case 1: F::sub(z, x, y); break;
     case 2: F::mul(z, x, y); break;
-    default: F::sqr(z, x); break;
+    case 3: F::sqr(z, x); break;
+    default: F::inv(z, x); break;  // op 4 (tower fields: Fp2::inv / Fp3::inv; the base field goes through fp_conv_kernel)
   }
   r[i] = z;
 }
@@ -116,11 +117,17 @@ int imad_peak(double *mac32_per_s2, double *ms2) {
   B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
   const int blocks = prop.multiProcessorCount * 8, threads = 256;
   Timer tm;
+  // nominal: 32 IMAD.WIDE per clock per SM (half the 32-bit IMAD rate) at the maximum SM clock
+  int khz = 0;
+  B200_CUDA_CHECK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+  mac32_per_s2[2] = 32.0 * prop.multiProcessorCount * (double)khz * 1e3;
+  ms2[2] = khz / 1e3;
   for (int variant = 0; variant < 2; variant++) {
-    int iters = variant == 0 ? 8192 : 4096;
+    // >= 50 ms per run: a 3 ms run ends before the SM clock has ramped up and under-reads the pipe by ~10 %
+    int iters = variant == 0 ? (1 << 18) : (1 << 16);
     double macs = variant == 0 ? (double)blocks * threads * 8.0 * iters : (double)blocks * threads * 24.0 * iters;
     float best = 1e30f;
-    for (int rep = 0; rep < 4; rep++) {
+    for (int rep = 0; rep < 3; rep++) {
       tm.start();
       if (variant == 0)
         imad_wide_kernel<<<blocks, threads>>>(buf.as<unsigned long long>(), 0x7fffffffu, iters);
@@ -155,7 +162,7 @@ int dev_fp_op(int tag, int op, const void *a, const void *b, void *r, size_t n) 
 }
 int dev_fqe_op(int curve, int op, const void *a, const void *b, void *r, size_t n) {
   if (n == 0) return 0;
-  if (op < 0 || op > 3) return set_error(-1, "dev_fqe_op: bad op %d", op);
+  if (op < 0 || op > 4) return set_error(-1, "dev_fqe_op: bad op %d", op);
   if (curve == 0) {
     typedef Mnt4G2::F F;
     field_op_kernel<F><<<grid_for(n, 128), 128>>>(op, (const F *)a, (const F *)b, (F *)r, n);

@@ -190,9 +190,8 @@ BUNDLE typename B::vector_Fr *B::input_cc(groth16_input *input) { return new vec
 BUNDLE typename B::field *B::input_r(groth16_input *input) { return new field(input->r); }
 
 BUNDLE typename B::groth16_params *B::read_params(const char *path) {
-  std::vector<unsigned char> img = slurp(path);
   auto box = std::make_shared<params_box>();
-  B200_OK(b200_params_from_host(CURVE, img.data(), img.size(), &box->h));
+  B200_OK(b200_params_from_file(CURVE, path, &box->h));  // chunked reads into pinned memory, asynchronous H2D
   // key-only preprocessing (pre-shifted base tables), part of loading the key like the reference's own parsing
   {
     const char *e = getenv("B200_PRECOMPUTE");

@@ -67,7 +67,7 @@ def test_tower_ops_vs_oracle(b200, oracle, dev, curve):
     bb = b"".join(util.rand_fe_bytes(rng, c.q, d) for _ in range(n))
     da, db = b200.to_device(a), b200.to_device(bb)
     dr = torch.empty(n * d * FE, dtype=torch.uint8, device=dev)
-    for op in (0, 1, 2, 3):
+    for op in (0, 1, 2, 3, 4):  # add sub mul sqr inv (Fp2::inv / Fp3::inv called directly, not through to_affine)
         b200.check(b200.lib().b200_dev_fqe_op(curve, op, da.data_ptr(), db.data_ptr(), dr.data_ptr(), n))
         out = b200.from_device(dr)
         sz = d * FE
@@ -277,7 +277,8 @@ def test_msm_linearity_large(b200, dev, accum):
 
 
 # ------------------------------------------------------------------------------------------------ NTT / compute_H
-@pytest.mark.parametrize("curve,logm", [(0, 1), (0, 2), (0, 5), (0, 8), (0, 9), (0, 13), (1, 1), (1, 3), (1, 8), (1, 12)])
+@pytest.mark.parametrize("curve,logm", [(0, 1), (0, 2), (0, 5), (0, 8), (0, 9), (0, 13), (0, 17), (1, 1), (1, 3), (1, 8), (1, 12),
+                                        (1, 15)])
 def test_domain_ops_vs_oracle(b200, oracle, dev, curve, logm):
     c = util.curve_obj(curve)
     m = 1 << logm
@@ -297,7 +298,9 @@ def test_domain_rejects_bad_sizes(b200, dev):
             b200.Domain(curve, m)
 
 
-@pytest.mark.parametrize("curve,logm", [(0, 6), (1, 6), (0, 11), (1, 10)])
+# logm = 17: three passes (6 + 6 + 5 stages) - the middle pass has s0 > 0 and neither a pre- nor a post-table, like the
+# 2^20 transform of the challenge size; 2^15 is MNT6753's challenge size
+@pytest.mark.parametrize("curve,logm", [(0, 6), (1, 6), (0, 11), (1, 10), (0, 17), (1, 15)])
 def test_compute_h_vs_oracle(b200, oracle, dev, curve, logm):
     import torch
     c = util.curve_obj(curve)
@@ -416,7 +419,7 @@ def test_concurrent_proofs_match_reference_golden(b200, dev):
 
 
 @pytest.mark.parametrize("curve", [0, 1])
-def test_equal_bases_are_merged_bit_exactly(b200, dev, curve):
+def test_equal_bases_are_merged_bit_exactly(b200, oracle, dev, curve):
     """Key-load time merging of equal bases (MsmDedup): a query with one group larger than a segment (1024), a small
     group, a pair, a duplicated point at infinity and scalars that cancel; table MSM (merging on) == table-free MSM."""
     import torch
@@ -450,6 +453,7 @@ def test_equal_bases_are_merged_bit_exactly(b200, dev, curve):
     got = b200.g_to_affine(curve, 1, key.msm(0, sc, m + 1))
     exp = b200.g_to_affine(curve, 1, b200.msm(curve, 1, sc, A, m + 1))
     assert got == exp
+    assert got == util.orc_msm_affine(oracle, curve, 1, b200.from_device(sc), b200.from_device(A), m + 1, chunks=8)
     # and through a whole proof: tables (merging) vs table-free
     g = torch.Generator(device="cpu").manual_seed(4321 + curve)
     n_in = (m + 1) + 3 * m + 1
@@ -463,3 +467,104 @@ def test_equal_bases_are_merged_bit_exactly(b200, dev, curve):
         b200.set_precompute(True)
     assert p1 == p2
     key.close()
+
+
+# ------------------------------------------------------------------------------------------------ table-mode MSM vs oracle
+def _structured_key(b200, dev, curve, k):
+    """device-side synthetic key of 2^k constraints with the structure of real keys (SURVEY.md 8 pitfalls 1-2)"""
+    import torch
+    m = 1 << k
+    g1, g2 = b200.affine_bytes(curve, 1), b200.affine_bytes(curve, 2)
+
+    def gen(group, n, first):
+        t = torch.empty(n * b200.affine_bytes(curve, group), dtype=torch.uint8, device=dev)
+        b200.check(b200.lib().b200_gen_points(curve, group, t.data_ptr(), n, first))
+        return t
+
+    A, B1, B2 = gen(1, m + 1, 1000003), gen(1, m + 1, 2000003), gen(2, m + 1, 3000017)
+    L, H = gen(1, m - 1, 4000037), gen(1, m - 1, 5000011)
+    Av = A.view(m + 1, g1)
+    Av[2:m - 1:2] = Av[2].clone()
+    Av[m - 1] = Av[2]
+    Av[m] = 0
+    for Q, sz in ((B1, g1), (B2, g2)):
+        Qv = Q.view(m + 1, sz)
+        Qv[0] = 0
+        Qv[m] = 0
+        Qv[m - 2] = Qv[m - 3]
+    torch.cuda.synchronize()
+    return b200.Params.from_device(curve, m - 1, m, A, B1, B2, L, H), (A, B1, B2, L, H)
+
+
+def _scalars_with_specials(curve, n, seed):
+    c = util.curve_obj(curve)
+    rng = random.Random(seed)
+    scalars = [rng.randrange(c.r) for _ in range(n)]
+    scalars[0] = 1
+    scalars[1] = 0
+    scalars[5] = c.r - 1
+    scalars[7] = 1 << 752  # exercises the carry into the top window
+    return b"".join(util.fe_bytes(M.to_mont(s, c.r)) for s in scalars)
+
+
+@pytest.mark.parametrize("curve,window", [(0, 21), (1, 17), (0, 19)])
+def test_table_msm_forced_wide_windows_vs_oracle(b200, oracle, dev, curve, window, accum):
+    """The headline schedule - pre-shifted base tables, ONE merged bucket set, window widths 17..21 (36-45 windows) -
+    against the oracle, for all five queries of a key (A with its m/2 equal bases merged, B2 in G2): the window width
+    the 2^20 proof picks is forced on a 2^12 key, so the oracle finishes in seconds."""
+    k = 12
+    m = 1 << k
+    b200.set_precompute(True)
+    b200.lib().b200_msm_set_window(window)
+    try:
+        key, qs = _structured_key(b200, dev, curve, k)
+        assert key.precompute() > 0
+    finally:
+        b200.lib().b200_msm_set_window(0)
+    sc = _scalars_with_specials(curve, m + 1, 9100 + curve + window)
+    d_sc = b200.to_device(sc)
+    which = (0, 1, 2, 3, 4) if window != 19 else (1, 4)
+    for w in which:
+        n = m + 1 if w < 3 else m - 1
+        group = 2 if w == 2 else 1
+        got = b200.g_to_affine(curve, group, key.msm(w, d_sc, n))
+        plan = b200.msm_last_plan()
+        assert plan["c"] == window and plan["windows"] == (754 + window - 1) // window, plan
+        exp = util.orc_msm_affine(oracle, curve, group, sc[:n * FE], b200.from_device(qs[w]), n, chunks=8)
+        assert got == exp, (curve, window, w)
+    key.close()
+
+
+def test_table_msm_natural_window_2_16_vs_oracle(b200, oracle, dev, accum):
+    """n = 2^16 + 1 G1 points: the window width chosen by the library itself is >= 17 here (table mode)."""
+    import torch
+    curve, k = 0, 16
+    m = 1 << k
+    key, qs = _structured_key(b200, dev, curve, k)
+    assert key.precompute() > 0
+    sc = _scalars_with_specials(curve, m + 1, 9200)
+    got = b200.g_to_affine(curve, 1, key.msm(1, b200.to_device(sc), m + 1))
+    assert b200.msm_last_plan()["c"] >= 17
+    assert got == util.orc_msm_affine(oracle, curve, 1, sc, b200.from_device(qs[1]), m + 1, chunks=16)
+    key.close()
+
+
+@pytest.mark.parametrize("curve,group", [(0, 1), (0, 2), (1, 1), (1, 2)])
+def test_host_synth_key_matches_device_generator(b200, dev, curve, group, tmp_path):
+    """tools/synth_key (host, the bench's file generator) and gen_points_kernel produce the same multiples of the
+    generator."""
+    import subprocess, sys, os, torch
+    sys.path.insert(0, util.ROOT)
+    import bench
+    k = 6
+    m = 1 << k
+    pf, inf = str(tmp_path / "p"), str(tmp_path / "i")
+    subprocess.check_call([bench.synth_tool(), bench.CURVES[curve], str(k), pf, inf])
+    _, _, q = util.split_params(curve, open(pf, "rb").read())
+    name, first, n = ("L", 4000037, m - 1) if group == 1 else ("B2", 3000017, m + 1)
+    ab = b200.affine_bytes(curve, group)
+    out = torch.empty(n * ab, dtype=torch.uint8, device=dev)
+    b200.check(b200.lib().b200_gen_points(curve, group, out.data_ptr(), n, first))
+    got = b200.from_device(out)
+    lo, hi = (0, n) if group == 1 else (1, m - 2)   # B2 carries O at 0 and m and a duplicate pair at m-2
+    assert got[lo * ab:hi * ab] == q[name][lo * ab:hi * ab]
