@@ -210,6 +210,54 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def rand_fr(torch, n, seed, pinned=False):
+    """n uniformly random 752-bit values: every value < 2^752 < r is the Montgomery representation of some element"""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    raw = torch.randint(0, 256, (n, FE), dtype=torch.uint8, generator=g)
+    raw[:, 94:] = 0
+    return raw.pin_memory() if pinned else raw
+
+
+def make_key(pkg, torch, curve, k, dev):
+    """Device-side twin of tools/synth_key (same bases, same structure) for the profiling tools and the sweeps, which
+    need keys of many sizes without going through files."""
+    m = 1 << k
+    d = m - 1
+    g1, g2 = pkg.affine_bytes(curve, 1), pkg.affine_bytes(curve, 2)
+
+    def gen(group, n, first):
+        t = torch.empty(n * pkg.affine_bytes(curve, group), dtype=torch.uint8, device=dev)
+        pkg.check(pkg.lib().b200_gen_points(curve, group, t.data_ptr(), n, first))
+        return t
+
+    A, B1, B2 = gen(1, m + 1, 1000003), gen(1, m + 1, 2000003), gen(2, m + 1, 3000017)
+    L, H = gen(1, m - 1, 4000037), gen(1, d, 5000011)
+    Av = A.view(m + 1, g1)
+    Av[2:m - 1:2] = Av[2].clone()
+    Av[m - 1] = Av[2]
+    Av[m] = 0
+    for Q, sz in ((B1, g1), (B2, g2)):
+        Qv = Q.view(m + 1, sz)
+        Qv[0] = 0
+        Qv[m] = 0
+        Qv[m - 2] = Qv[m - 3]
+    torch.cuda.synchronize()
+    return pkg.Params.from_device(curve, d, m, A, B1, B2, L, H)
+
+
+def make_input(torch, curve, k, seed):
+    """pinned host image of an input file: w[m+1] (w[0] = 1 in Montgomery form), ca, cb, cc [d+1], r"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import mnt753 as M
+    m = 1 << k
+    n = (m + 1) + 3 * m + 1
+    img = rand_fr(torch, n, seed, pinned=True)
+    r = M.MOD_A if curve == 0 else M.MOD_B
+    one = (M.R % r).to_bytes(FE, "little")
+    img[0] = torch.frombuffer(bytearray(one), dtype=torch.uint8)
+    return img
+
+
 def regroup_partials(blobs, pbytes):
     """blobs[r] = rank r's partial sums of every proof of the step, concatenated (what one all_gather delivers);
     returns, per proof, the rank-major concatenation b200_prove_combine expects."""

@@ -9,7 +9,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200groth16.so")
+# B200_LIB selects another build of the same library (kernel variants compiled with other switches, for timing runs)
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(HERE, "libb200groth16.so")
 
 MNT4753, MNT6753 = 0, 1
 CURVE_NAMES = {MNT4753: "MNT4753", MNT6753: "MNT6753"}

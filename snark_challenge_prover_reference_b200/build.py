@@ -11,8 +11,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libb200groth16.so")
+# B200_VARIANT=<name>: build into build_<name>/ and libb200groth16_<name>.so (kernel variants selected with
+# B200_NVCC_EXTRA, loaded with B200_LIB=<that .so>); the default build is untouched
+_VAR = os.environ.get("B200_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _VAR if _VAR else ""))
+LIB = os.path.join(HERE, "libb200groth16%s.so" % ("_" + _VAR if _VAR else ""))
 SOURCES = ["msm_g_mnt6g2.cu", "devops_g_mnt6g2.cu", "msm_g_mnt4g2.cu", "devops_g_mnt4g2.cu", "msm_g_mnt4g1.cu", "msm_g_mnt6g1.cu",
            "devops_g_mnt4g1.cu", "devops_g_mnt6g1.cu", "devops.cu", "msm.cu", "ntt.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
