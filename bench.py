@@ -459,7 +459,7 @@ def b200_arm(args):
     # here in isolation (same key, same scalars, one MSM at a time through b200_params_msm, CUDA events around the
     # accumulation launches on the MSM's stream). Bound: the INT32 multiplier (IMAD.WIDE / fmaheavy) pipe.
     imad = pkg.imad_peak()
-    peak = max(imad["mad_wide_mac32_per_s"], imad["carry_chain_mac32_per_s"])
+    peak = max(imad["mad_wide_mac32_per_s"], imad["carry_chain_mac32_per_s"], imad["montgomery_mul_mac32_per_s"])
     accum_mode = "affine" if pkg.batch_affine_enabled() else "xyzz"
     iso = {"g1": [], "g2": [], "a_merged": []}
     plans = {}
@@ -498,7 +498,9 @@ def b200_arm(args):
                     "traffic_algorithmic": plans[(0, False)]["windows"] * ((1 << k4) - 1) * 192.0,
                     "launches": len(iso["g1"]), "avg_launch_ms": statistics.mean(g1_big) if g1_big else None,
                     "a_query_equal_bases_merged_ms": [round(t, 2) for _, _, t, _ in iso["a_merged"]],
-                    "peak_source": "measured live by b200_imad_peak (independent IMAD.WIDE chains on all SMs, 50 ms runs)",
+                    "peak_source": "measured live by b200_imad_peak: best of three microbenchmarks (independent IMAD.WIDE chains, the multiplier's "
+                                   "carry-chain pattern, the generated Montgomery multiply in a register-resident loop), >= 50 ms runs on all SMs; "
+                                   "peak_nominal = 32 IMAD.WIDE/clk/SM x SMs x max SM clock",
                     "timing": "kernel timed alone with CUDA events on its stream (inside a proof 5 MSMs overlap)"}
         acc_ms_g2 = sum(t for _, _, t, _ in iso["g2"])
         g2_alg = sum((MAC32_PER_POINT["g2_fq2"] if c == 0 else MAC32_PER_POINT["g2_fq3"]) * n for c, n, _, _ in iso["g2"])

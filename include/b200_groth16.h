@@ -172,7 +172,8 @@ int b200_gen_points(int curve, int group, void *d_out_affine, size_t n, uint64_t
 /* IMAD roofline microbenchmark on every SM, runs of >= 50 ms each (shorter ones under-read: the clock is still
  * ramping). mac32_per_s[0] = independent IMAD.WIDE chains, [1] = the multiplier's (mad.lo.cc, madc.hi.cc) carry-chain
  * pattern, [2] = the NOMINAL rate 32 IMAD.WIDE / clk / SM x SMs x the device's maximum SM clock; ms[0..1] = the timed
- * runs, ms[2] = that clock in MHz. */
+ * runs, ms[2] = that clock in MHz; [3] = the generated Montgomery multiplication itself in a register-resident loop
+ * (the production instruction mix at the accumulation kernels' occupancy) and its run time. Arrays of 4. */
 int b200_imad_peak(double *mac32_per_s, double *ms);
 /* 1 when bucket accumulation currently uses batched affine additions, 0 for XYZZ mixed additions */
 int b200_msm_get_batch_affine(void);

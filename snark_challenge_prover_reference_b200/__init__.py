@@ -441,8 +441,8 @@ def batch_affine_enabled():
 
 
 def imad_peak():
-    v = (ctypes.c_double * 3)()
-    ms = (ctypes.c_double * 3)()
+    v = (ctypes.c_double * 4)()
+    ms = (ctypes.c_double * 4)()
     check(lib().b200_imad_peak(v, ms))
     return {"mad_wide_mac32_per_s": v[0], "carry_chain_mac32_per_s": v[1], "nominal_mac32_per_s": v[2],
-            "ms": [ms[0], ms[1]], "sm_clock_mhz": ms[2]}
+            "montgomery_mul_mac32_per_s": v[3], "ms": [ms[0], ms[1], ms[3]], "sm_clock_mhz": ms[2]}

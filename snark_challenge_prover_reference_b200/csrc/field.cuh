@@ -658,13 +658,14 @@ struct alignas(16) Fp {
     mul(r, vi, r3);
   }
   // r = a^-1; a != 0 (0 maps to 0). The reference uses an extended gcd (fp.tcc:641-685); the inverse is unique, so any
-  // algorithm gives the same canonical bytes. Device: bitwise binary gcd (validated on the GPU in round 1); host:
-  // batched binary gcd (30x fewer instructions; the device switches to it once it has been timed there).
+  // algorithm gives the same canonical bytes. Host and device: batched binary gcd (~10x fewer instructions than the
+  // bitwise one; it is what makes the shared inversion of the batch-affine accumulation cheap). -DB200_INV_BITWISE
+  // selects the bitwise routine on the device (round 1's default).
   B200_HD static void inv(Fp &r, const Fp &a) {
-#if defined(__CUDA_ARCH__) && !defined(B200_INV_BINGCD)
+#if defined(__CUDA_ARCH__) && defined(B200_INV_BITWISE)
     inv_binary(r, a);
 #else
-    inv_bingcd(r, a);  // -DB200_INV_BINGCD selects it on the device too (compiles for sm_100a; not yet timed there)
+    inv_bingcd(r, a);
 #endif
   }
   // a^(p-2) (Fermat): kept as an independent cross-check of the gcd-based inversions (tests)

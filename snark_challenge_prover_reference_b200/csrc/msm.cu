@@ -343,6 +343,7 @@ void msm_release_workspace() {
                    &ws.ntasks, &ws.task_off, &ws.task_bucket, &ws.task_len, &ws.task_len_sorted, &ws.partials,
                    &ws.scalar_out, &ws.fold_cnt, &ws.fold_off, &ws.fold_bucket, &ws.fold_partials,
                    &ws.aff_cnt, &ws.aff_off, &ws.aff_totals, &ws.aff_pts[0], &ws.aff_pts[1], &ws.aff_scratch,
+                   &ws.aff_pairs, &ws.aff_oflag[0], &ws.aff_oflag[1], &ws.base_flags,
                    &ws.merged_scalars};
   for (DevBuf *b : all) b->release();
   }
@@ -512,6 +513,57 @@ int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, ui
   return 0;
 }
 
+// ---- batch-affine bookkeeping kernels ---------------------------------------------------------------------------
+// base_is_O[i] = 1 when base i is the point at infinity (y == 0 on the wire, serialization.hpp:87-89)
+__global__ void msm_base_flags_kernel(const unsigned char *__restrict__ points, uint32_t n, uint32_t point_bytes,
+                                      uint8_t *__restrict__ flags) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint4 *y = reinterpret_cast<const uint4 *>(points + (size_t)i * point_bytes + point_bytes / 2);
+  uint32_t acc = 0;
+  for (uint32_t k = 0; k < point_bytes / 32; k++) {
+    const uint4 v = y[k];
+    acc |= v.x | v.y | v.z | v.w;
+  }
+  flags[i] = acc == 0 ? 1 : 0;
+}
+// Operand pairs of one round: output j of the round (bucket b = the last one with off_out[b] <= j, position i = j -
+// off_out[b]) adds inputs 2i and 2i+1 of list b (the second is missing for an odd leftover). Round 1 (entries !=
+// nullptr): an operand is the counting sort's entry (table index << 1 | negate), bit 31 set when that base is O;
+// later rounds: the index into the previous round's output << 1. One thread per output: a binary search instead of a
+// walk along the bucket, so that a bucket holding millions of entries (skewed scalars) costs nothing special.
+__global__ void __launch_bounds__(256) msm_affine_pairs_kernel(const uint32_t *__restrict__ cnt_in, const uint32_t *__restrict__ off_in,
+                                                               const uint32_t *__restrict__ off_out, uint32_t nbuckets,
+                                                               uint32_t total_out, const uint32_t *__restrict__ entries,
+                                                               const uint8_t *__restrict__ base_is_O, uint32_t n_bases,
+                                                               uint2 *__restrict__ pairs) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= total_out) return;
+  uint32_t lo = 0, hi = nbuckets;  // empty buckets share the offset of the next non-empty one: take the LAST b with off <= j
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (off_out[mid] <= j) lo = mid;
+    else hi = mid;
+  }
+  const uint32_t b = lo, i = j - off_out[b];
+  const uint32_t c = cnt_in[b], in = off_in[b] + 2 * i;
+  const bool second = 2 * i + 1 < c;
+  uint2 pr;
+  if (entries) {
+    pr.x = entries[in];
+    if (base_is_O[(pr.x >> 1) % n_bases]) pr.x |= 0x80000000u;
+    pr.y = 0xffffffffu;
+    if (second) {
+      pr.y = entries[in + 1];
+      if (base_is_O[(pr.y >> 1) % n_bases]) pr.y |= 0x80000000u;
+    }
+  } else {
+    pr.x = in << 1;
+    pr.y = second ? (in + 1) << 1 : 0xffffffffu;
+  }
+  pairs[j] = pr;
+}
+
 // Batch-affine accumulation bookkeeping: level 0 = the bucket counts/offsets of the counting sort; level r+1 halves every
 // list (ceil). All levels are computed up front so that the round kernels can be enqueued without host round trips.
 int msm_affine_levels(const uint32_t *counts, const uint32_t *offsets, uint32_t nbuckets, uint32_t max_count,
@@ -545,6 +597,37 @@ int msm_affine_levels(const uint32_t *counts, const uint32_t *offsets, uint32_t 
   }
   B200_CUDA_CHECK(cudaStreamSynchronize(st));
   for (int r = 0; r <= rounds; r++) totals[r] = (size_t)last[2 * r] + last[2 * r + 1];
+  return 0;
+}
+
+int msm_base_flags(const void *d_points, size_t n, size_t point_bytes, DevBuf &flags, cudaStream_t st) {
+  B200_CHECK(flags.reserve(n ? n : 1));
+  if (n == 0) return 0;
+  msm_base_flags_kernel<<<grid_for(n, 256), 256, 0, st>>>((const unsigned char *)d_points, (uint32_t)n, (uint32_t)point_bytes,
+                                                          flags.as<uint8_t>());
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
+// operand pairs of every round, one after the other in ws.aff_pairs (round r starts at pair_off[r]); `levels_ws` owns the
+// level arrays (aff_cnt / aff_off) and `entries` is the counting sort's list the first round reads
+int msm_affine_pairs(MsmWorkspace &ws, const uint32_t *cnt, const uint32_t *off, uint32_t nbuckets,
+                     const std::vector<size_t> &totals, const uint32_t *entries, const uint8_t *base_is_O, size_t n_bases,
+                     std::vector<size_t> &pair_off) {
+  cudaStream_t st = ws.stream;
+  const int rounds = (int)totals.size() - 1;
+  pair_off.assign(rounds + 2, 0);
+  for (int r = 1; r <= rounds; r++) pair_off[r + 1] = pair_off[r] + totals[r];
+  B200_CHECK(ws.aff_pairs.reserve((pair_off[rounds + 1] ? pair_off[rounds + 1] : 1) * sizeof(uint2)));
+  for (int r = 1; r <= rounds; r++) {
+    if (totals[r] == 0) continue;
+    msm_affine_pairs_kernel<<<grid_for(totals[r], 256), 256, 0, st>>>(
+        cnt + (size_t)(r - 1) * nbuckets, off + (size_t)(r - 1) * nbuckets, off + (size_t)r * nbuckets, nbuckets,
+        (uint32_t)totals[r], r == 1 ? entries : nullptr, base_is_O, (uint32_t)n_bases, ws.aff_pairs.as<uint2>() + pair_off[r]);
+    B200_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+  }
   return 0;
 }
 

@@ -89,152 +89,131 @@ __global__ void __launch_bounds__(128) msm_combine_kernel(const Proj<typename G:
   buckets[b] = acc;
 }
 
-// ---- batch-affine bucket accumulation (B200_BATCH_AFFINE=1) ------------------------------------------------------
+// ---- batch-affine bucket accumulation (b200_msm_set_batch_affine / B200_BATCH_AFFINE) ------------------------------
 // Every bucket's list is summed as a balanced tree: a round adds adjacent pairs of every list (an odd leftover is
 // carried over), ceil(log2(longest list)) rounds in all. All additions of a round are independent, so they are done
-// in AFFINE coordinates with Montgomery's simultaneous-inversion trick: one thread takes M consecutive outputs of the
-// round, multiplies their denominators together, inverts ONCE (binary gcd on the ALU pipe, Fp::inv_binary) and
-// unwinds. Cost per addition: 3 multiplications for the shared inversion + 3 for (lambda, x3, y3) = 6 instead of the 10
-// of the XYZZ mixed addition. Special cases are classified per pair: O + Q, P + O, P + P (tangent: denominator 2y,
-// numerator 3x^2 + a), P + (-P) = O. Points are kept in wire format ((0,0) = O).
+// in AFFINE coordinates with Montgomery's simultaneous-inversion trick: a thread takes M outputs of the round,
+// multiplies their denominators together, inverts ONCE (batched binary gcd, Fp::inv_bingcd: ~75 K ALU instructions,
+// no multiplier work) and unwinds. Cost per addition: 3 multiplications for the shared inversion + 3 for
+// (lambda, x3, y3) = 5M + 1S instead of the 8M + 2S of the XYZZ mixed addition (and 9M + 2S of the reference's
+// mixed_add, mnt4753_g1.cpp:265-313). Special cases are classified per pair: O + Q, P + O, P + P (tangent:
+// denominator 2y, numerator 3x^2 + a), P + (-P) = O. Points are kept in wire format ((0,0) = O) plus one O-flag byte
+// per point, so that the common path never has to look at a y coordinate to classify.
+//
+// Schedule (round 2 of the build): thread t of S takes outputs t, t + S, t + 2S, ... - consecutive threads work on
+// consecutive outputs, whose operands are consecutive in memory from the second round on (coalesced), and whose
+// prefix products pre[j] are written / read back coalesced. The operand pairs of every round come from a small
+// bookkeeping kernel (msm_affine_pairs_kernel), so the round kernel carries no bucket-walking state. While output k is
+// being computed, the operands of the thread's next output are prefetched into L2 (cp.async.bulk.prefetch): first-round
+// operands are gathers from a 7 GB table, and four dependent DRAM latencies per addition were what kept the round-1
+// kernel of the previous build at 57 % multiplier-pipe utilisation (profiles/r01_v3_summary.md 2).
 #ifndef B200_AFF_BLOCKS
-#define B200_AFF_BLOCKS 1
+#define B200_AFF_BLOCKS 3
 #endif
+#ifndef B200_AFF_MIN_M
+#define B200_AFF_MIN_M 32
+#endif
+constexpr uint32_t kAffNone = 0xffffffffu;
+
+template <class T>
+__device__ __forceinline__ void prefetch_l2(const T *p) {
+  // whole object, 16-byte granules (sizeof(Affine<F>) and sizeof(F) are multiples of 16, objects 16-byte aligned)
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "n"(sizeof(T)) : "memory");
+}
+
+// One operand of an addition. p points at the stored point (table entry or previous round's output), `neg` says the
+// operand is its negative (first round: negative digit), `inf` that it is O.
 template <class F>
-struct AffineSource {
-  const Affine<F> *table;    // round 0: pre-shifted bases or plain bases, indexed through `entries`
-  const uint32_t *entries;   // round 0: index << 1 | negate ; nullptr in later rounds
-  const Affine<F> *pts;      // later rounds: output of the previous round
+struct AffOperand {
+  const Affine<F> *p;
+  uint32_t neg, inf;
 };
-// streaming (evict-first) copies: the points, the prefix products and the round outputs pass through once, the L1/L2
-// capacity is needed for the threads' stack frames (the operands of every field operation live there)
-template <class T>
-__device__ __forceinline__ void load_streaming(T &dst, const T *src) {
-  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
-  const uint4 *s = reinterpret_cast<const uint4 *>(src);
-  uint4 *d = reinterpret_cast<uint4 *>(&dst);
-#pragma unroll
-  for (int k = 0; k < (int)(sizeof(T) / 16); k++) d[k] = __ldcs(s + k);
+template <class F>
+__device__ __forceinline__ AffOperand<F> aff_operand(const Affine<F> *src, const uint8_t *oflag_in, uint32_t v) {
+  AffOperand<F> o;
+  o.p = src + ((v & 0x7fffffffu) >> 1);
+  o.neg = v & 1u;
+  o.inf = oflag_in ? oflag_in[(v & 0x7fffffffu) >> 1] : (v >> 31);
+  return o;
 }
-template <class T>
-__device__ __forceinline__ void store_streaming(T *dst, const T &src) {
-  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
-  const uint4 *s = reinterpret_cast<const uint4 *>(&src);
-  uint4 *d = reinterpret_cast<uint4 *>(dst);
-#pragma unroll
-  for (int k = 0; k < (int)(sizeof(T) / 16); k++) __stcs(d + k, s[k]);
-}
-// One operand of a round: the point stays in GLOBAL memory (the field routines take generic pointers, so nothing is
-// copied to the stack) and a first-round entry's negation is carried as a flag. Every case below is arranged so
-// that no y coordinate ever has to be negated up front:
+// kind of one output: 0 copy first operand, 1 copy second, 2 result O, 3 chord, 4 tangent; den = the denominator of
+// lambda for kinds 3 and 4. Every case is arranged so that no y coordinate ever has to be negated up front:
 //   same flags     : lambda = (y2 - y1)/(x2 - x1), y3 = lambda (x1 - x3) - y1   - the sum of the stored points
 //   different flags: lambda = (y1 + y2)/(x2 - x1), y3 = lambda (x3 - x1) - y1   - P1 - P2 of the stored points
 // and the result is negated (y3 := y1 - ...) when the FIRST operand carried the flag.
 template <class F>
-struct AffineOperand {
-  const Affine<F> *p;
-  uint32_t neg;
-};
-template <class F>
-__device__ __forceinline__ AffineOperand<F> affine_operand(const AffineSource<F> &src, uint32_t idx) {
-  if (src.entries) {
-    const uint32_t e = src.entries[idx];
-    return AffineOperand<F>{src.table + (e >> 1), e & 1u};
-  }
-  return AffineOperand<F>{src.pts + idx, 0u};
-}
-// classification of one output of a round: 0 copy first operand, 1 copy second, 2 result O, 3 chord, 4 tangent;
-// den = the denominator of lambda for kinds 3 and 4
-template <class F>
-__device__ __forceinline__ int affine_classify(const AffineOperand<F> &a, const AffineOperand<F> &b, bool has_second,
-                                               F &den) {
+__device__ __forceinline__ int aff_classify(const AffOperand<F> &a, const AffOperand<F> &b, bool has_second, F &den) {
   if (!has_second) return 0;
-  if (F::is_zero(a.p->y)) return 1;
-  if (F::is_zero(b.p->y)) return 0;
-  if (F::eq(a.p->x, b.p->x)) {
-    const bool same_point = F::eq(a.p->y, b.p->y) == (a.neg == b.neg);
-    if (!same_point) return 2;
-    F::dbl(den, a.p->y);
-    return 4;
-  }
+  if (a.inf) return 1;
+  if (b.inf) return 0;
   F::sub(den, b.p->x, a.p->x);
-  return 3;
-}
-template <class F>
-__device__ __forceinline__ void affine_copy(Affine<F> *dst, const AffineOperand<F> &a) {
-  Affine<F> t;
-  load_streaming(t, a.p);
-  if (a.neg && !F::is_zero(t.y)) F::neg_ni(t.y, t.y);
-  store_streaming(dst, t);
+  if (!F::is_zero(den)) return 3;
+  const bool same_point = F::eq(a.p->y, b.p->y) == (a.neg == b.neg);
+  if (!same_point) return 2;
+  F::dbl(den, a.p->y);
+  return 4;
 }
 
 template <class G>
-__global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(AffineSource<typename G::F> src,
-                                                               const uint32_t *__restrict__ off_in,
-                                                               const uint32_t *__restrict__ cnt_in,
-                                                               const uint32_t *__restrict__ off_out, uint32_t nbuckets,
-                                                               uint32_t total_out, uint32_t M,
-                                                               Affine<typename G::F> *pts_out,
-                                                               typename G::F *scratch) {
+__global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(
+    const Affine<typename G::F> *__restrict__ src, const uint8_t *__restrict__ oflag_in, const uint2 *__restrict__ pairs,
+    uint32_t total_out, uint32_t S, Affine<typename G::F> *__restrict__ pts_out, uint8_t *__restrict__ oflag_out,
+    typename G::F *__restrict__ pre) {
   typedef typename G::F F;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t j0 = t * M;
-  if (j0 >= total_out) return;
-  const uint32_t jn = j0 + M < total_out ? j0 + M : total_out;
-  F *pre = scratch + (size_t)t * M;
-  // bucket of output j0: last b with off_out[b] <= j0 (empty buckets share the offset of the next non-empty one)
-  uint32_t lo = 0, hi = nbuckets;
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (off_out[mid] <= j0) lo = mid;
-    else hi = mid;
-  }
-  uint32_t b = lo, i = j0 - off_out[lo];
-  // NOTE: a variant of the backward loop that kept the per-output inverse in its own temporary (dinv = inv * prefix;
-  // lambda = num * dinv) was miscompiled by nvcc 12.9 for the MNT6753-G1 instantiation: the PTX passed the SAME stack
-  // slot for dinv and num. The ordering below needs no such temporary (tests run every MSM case in both accumulation
-  // modes).
-  F inv, den, lam, num, x3;  // the only field elements on the stack; inv holds the running product first
+  if (t >= S || t >= total_out) return;
+  // the only field elements on the stack; inv holds the running product first
+  F inv, den, lam, num, x3;
   F::set_one(inv);
   // ---- forward: running product of the denominators
-  for (uint32_t j = j0; j < jn; j++) {
-    while (i >= (cnt_in[b] + 1) / 2) {
-      b++;
-      i = 0;
+  uint32_t j = t;
+  uint2 nx = pairs[j];
+  for (;;) {
+    const uint2 pr = nx;
+    const uint32_t jn = j + S;
+    const bool more = jn < total_out && jn > j;
+    if (more) {
+      nx = pairs[jn];
+      if (nx.y != kAffNone) {
+        prefetch_l2(src + ((nx.x & 0x7fffffffu) >> 1));
+        prefetch_l2(src + ((nx.y & 0x7fffffffu) >> 1));
+      }
     }
-    const uint32_t c = cnt_in[b], base = off_in[b] + 2 * i;
-    const bool second = 2 * i + 1 < c;
-    const AffineOperand<F> q1 = affine_operand(src, base);
-    const AffineOperand<F> q2 = second ? affine_operand(src, base + 1) : q1;
-    const int kind = affine_classify(q1, q2, second, den);
+    const AffOperand<F> q1 = aff_operand(src, oflag_in, pr.x);
+    const AffOperand<F> q2 = pr.y != kAffNone ? aff_operand(src, oflag_in, pr.y) : q1;
+    const int kind = aff_classify(q1, q2, pr.y != kAffNone, den);
     if (kind >= 3) F::mul(inv, inv, den);
-    store_streaming(pre + (j - j0), inv);
-    i++;
+    pre[j] = inv;
+    if (!more) break;
+    j = jn;
   }
   F::inv(inv, inv);
-  // ---- backward: unwind the product, finish every addition
-  for (uint32_t j = jn; j-- > j0;) {
-    if (i == 0) {
-      do {
-        b--;
-      } while ((cnt_in[b] + 1) / 2 == 0);
-      i = (cnt_in[b] + 1) / 2;
+  // ---- backward: unwind the product, finish every addition (j is the thread's last output)
+  nx = pairs[j];
+  for (;;) {
+    const uint2 pr = nx;
+    const bool more = j >= S;
+    if (more) {
+      nx = pairs[j - S];
+      prefetch_l2(src + ((nx.x & 0x7fffffffu) >> 1));
+      if (nx.y != kAffNone) prefetch_l2(src + ((nx.y & 0x7fffffffu) >> 1));
+      if (j >= 2 * S) prefetch_l2(pre + (j - 2 * S));
     }
-    i--;
-    const uint32_t c = cnt_in[b], base = off_in[b] + 2 * i;
-    const bool second = 2 * i + 1 < c;
-    const AffineOperand<F> q1 = affine_operand(src, base);
-    const AffineOperand<F> q2 = second ? affine_operand(src, base + 1) : q1;
-    const int kind = affine_classify(q1, q2, second, den);
-    Affine<F> *out = pts_out + (off_out[b] + i);
-    if (kind == 0) {
-      affine_copy(out, q1);
-    } else if (kind == 1) {
-      affine_copy(out, q2);
+    const AffOperand<F> q1 = aff_operand(src, oflag_in, pr.x);
+    const AffOperand<F> q2 = pr.y != kAffNone ? aff_operand(src, oflag_in, pr.y) : q1;
+    const int kind = aff_classify(q1, q2, pr.y != kAffNone, den);
+    Affine<F> *out = pts_out + j;
+    if (kind <= 1) {
+      const AffOperand<F> &q = kind == 0 ? q1 : q2;
+      out->x = q.p->x;
+      if (q.neg && !q.inf) F::neg(out->y, q.p->y);
+      else out->y = q.p->y;
+      oflag_out[j] = (uint8_t)q.inf;
     } else if (kind == 2) {
       F::set_zero(x3);
-      store_streaming(&out->x, x3);
-      store_streaming(&out->y, x3);
+      out->x = x3;
+      out->y = x3;
+      oflag_out[j] = 1;
     } else {
       const bool same = kind == 4 || q1.neg == q2.neg;
       if (kind == 3) {
@@ -249,8 +228,11 @@ __global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(
         F::add(num, num, lam);  // 3 x^2 + a
       }
       // lambda = num * (inv * prefix) ; then drop this denominator from the running inverse
+      // (NOTE: a variant that kept the per-output inverse in its own temporary - dinv = inv * prefix; lambda = num * dinv -
+      // was miscompiled by nvcc 12.9 for the MNT6753-G1 instantiation: the PTX passed the SAME stack slot for dinv and
+      // num. This ordering needs no such temporary; the tests run every MSM case in both accumulation modes.)
       F::mul(num, num, inv);
-      if (j > j0) F::mul(lam, num, pre[j - j0 - 1]);
+      if (more) F::mul(lam, num, pre[j - S]);
       else lam = num;
       F::mul(inv, inv, den);
       F::sqr(x3, lam);
@@ -261,14 +243,20 @@ __global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(
       F::mul(num, lam, num);
       if (q1.neg) F::sub(out->y, q1.p->y, num);
       else F::sub(out->y, num, q1.p->y);
-      store_streaming(&out->x, x3);
+      out->x = x3;
+      oflag_out[j] = 0;
     }
+    if (!more) break;
+    j -= S;
   }
 }
 
 // bucket[b] = the single remaining point of list b (or O), converted to the projective form the reduction uses
 template <class G>
-__global__ void __launch_bounds__(128) msm_affine_finish_kernel(AffineSource<typename G::F> src,
+__global__ void __launch_bounds__(128) msm_affine_finish_kernel(const Affine<typename G::F> *__restrict__ src,
+                                                                const uint8_t *__restrict__ oflag_in,
+                                                                const uint32_t *__restrict__ entries,
+                                                                const uint8_t *__restrict__ base_is_O, uint32_t n_bases,
                                                                 const uint32_t *__restrict__ off_in,
                                                                 const uint32_t *__restrict__ cnt_in, uint32_t nbuckets,
                                                                 Proj<typename G::F> *__restrict__ buckets) {
@@ -276,14 +264,23 @@ __global__ void __launch_bounds__(128) msm_affine_finish_kernel(AffineSource<typ
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbuckets) return;
   Proj<F> out;
-  if (cnt_in[b] == 0) {
-    proj_set_zero(out);
-  } else {
-    Affine<F> p;
-    const AffineOperand<F> q = affine_operand(src, off_in[b]);
-    load_streaming(p, q.p);
-    if (q.neg && !F::is_zero(p.y)) F::neg_ni(p.y, p.y);
-    proj_from_affine(out, p);
+  proj_set_zero(out);
+  if (cnt_in[b] != 0) {
+    // no round ran at all (every list has <= 1 entry): the point still is a first-round entry
+    uint32_t idx = off_in[b], neg = 0, inf;
+    if (entries) {
+      const uint32_t e = entries[idx];
+      idx = e >> 1;
+      neg = e & 1u;
+      inf = base_is_O[idx % n_bases];
+    } else {
+      inf = oflag_in[idx];
+    }
+    if (!inf) {
+      Affine<F> p = src[idx];
+      if (neg) F::neg(p.y, p.y);
+      proj_from_affine(out, p);
+    }
   }
   buckets[b] = out;
 }
@@ -400,45 +397,55 @@ int msm_accumulate_xyzz(const void *d_points, const MsmPlan &plan, MsmWorkspace 
   return 0;
 }
 
-// Bucket accumulation, opt-in mode: rounds of batched affine additions (see msm_affine_round_kernel).
+// Bucket accumulation by rounds of batched affine additions (see msm_affine_round_kernel). n_bases = the MSM's n:
+// the first n entries of d_points are the bases themselves (window 0 of a table, or the plain query).
 template <class G>
-int msm_accumulate_batch_affine(const void *d_points, const MsmPlan &plan, MsmWorkspace &ws, MsmWorkspace &pw) {
+int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmPlan &plan, MsmWorkspace &ws, MsmWorkspace &pw) {
   typedef typename G::F F;
   cudaStream_t st = ws.stream;
   const size_t nbuckets = plan.nbuckets;
-  std::vector<size_t> totals;
+  std::vector<size_t> totals, pair_off;
+  B200_CHECK(msm_base_flags(d_points, n_bases, sizeof(Affine<F>), ws.base_flags, st));
   B200_CHECK(msm_affine_levels(pw.counts.as<uint32_t>(), pw.offsets.as<uint32_t>(), (uint32_t)nbuckets, plan.max_count, totals));
   const int rounds = (int)totals.size() - 1;
   const uint32_t *cnt = ws.aff_cnt.as<uint32_t>(), *off = ws.aff_off.as<uint32_t>();
-  AffineSource<F> src{(const Affine<F> *)d_points, pw.entries.as<uint32_t>(), nullptr};
+  B200_CHECK(msm_affine_pairs(ws, cnt, off, (uint32_t)nbuckets, totals, pw.entries.as<uint32_t>(), ws.base_flags.as<uint8_t>(),
+                              n_bases, pair_off));
+  static int wave = 0;  // resident threads of one full wave of the round kernel
+  if (!wave) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_affine_round_kernel<G>, 128, 0);
+    wave = (per_sm > 0 ? per_sm : 1) * sms * 128;
+  }
+  const Affine<F> *src = (const Affine<F> *)d_points;
+  const uint8_t *oflag_in = nullptr;
+  int done = 0;
   for (int r = 1; r <= rounds; r++) {
     const size_t total_out = totals[r];
     if (total_out == 0) break;
-    // one full wave of resident threads per round: M = outputs per thread (>= 24: the shared binary-gcd inversion
-    // costs as many instructions as ~48 additions, profiles/r01_v3_summary.md)
-    static int wave = 0;
-    if (!wave) {
-      int per_sm = 0, dev = 0, sms = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_affine_round_kernel<G>, 128, 0);
-      wave = (per_sm > 0 ? per_sm : 1) * sms * 128;
-    }
-    uint32_t M = (uint32_t)((total_out + wave - 1) / wave);
-    M = M < 24 ? 24 : M;
-    const size_t nthreads = (total_out + M - 1) / M;
-    DevBuf &outbuf = ws.aff_pts[r & 1];
+    // one wave of resident threads when the round is large; at least B200_AFF_MIN_M outputs per thread otherwise (the
+    // shared inversion costs as many instructions as ~9 additions)
+    size_t S = (size_t)wave;
+    if (total_out / S < B200_AFF_MIN_M) S = (total_out + B200_AFF_MIN_M - 1) / B200_AFF_MIN_M;
+    S = (S + 127) / 128 * 128;
+    DevBuf &outbuf = ws.aff_pts[r & 1], &oflag = ws.aff_oflag[r & 1];
     B200_CHECK(outbuf.reserve(total_out * sizeof(Affine<F>)));
-    B200_CHECK(ws.aff_scratch.reserve(nthreads * M * sizeof(F)));
-    msm_affine_round_kernel<G><<<grid_for(nthreads, 128), 128, 0, st>>>(
-        src, off + (size_t)(r - 1) * nbuckets, cnt + (size_t)(r - 1) * nbuckets, off + (size_t)r * nbuckets,
-        (uint32_t)nbuckets, (uint32_t)total_out, M, outbuf.as<Affine<F>>(), ws.aff_scratch.as<F>());
+    B200_CHECK(oflag.reserve(total_out));
+    B200_CHECK(ws.aff_scratch.reserve(total_out * sizeof(F)));
+    msm_affine_round_kernel<G><<<grid_for(S, 128), 128, 0, st>>>(src, oflag_in, ws.aff_pairs.as<uint2>() + pair_off[r],
+                                                               (uint32_t)total_out, (uint32_t)S, outbuf.as<Affine<F>>(),
+                                                               oflag.as<uint8_t>(), ws.aff_scratch.as<F>());
     B200_CUDA_CHECK(cudaGetLastError());
     note_launch();
-    src = AffineSource<F>{nullptr, nullptr, outbuf.as<Affine<F>>()};
+    src = outbuf.as<Affine<F>>();
+    oflag_in = oflag.as<uint8_t>();
+    done = r;
   }
   msm_affine_finish_kernel<G><<<grid_for(nbuckets, 128), 128, 0, st>>>(
-      src, off + (size_t)rounds * nbuckets, cnt + (size_t)rounds * nbuckets, (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
+      src, oflag_in, done == 0 ? pw.entries.as<uint32_t>() : nullptr, ws.base_flags.as<uint8_t>(), (uint32_t)n_bases,
+      off + (size_t)done * nbuckets, cnt + (size_t)done * nbuckets, (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
   return 0;
@@ -473,9 +480,10 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   stage->slot = msm_current_slot();
   for (int i = 0; i < 4; i++) stage->prep_ev[i] = share_slot >= 0 ? nullptr : ws.tm_ev[i];
 
-  if (msm_use_batch_affine()) {
+  // (batch-affine operand words keep bit 31 for the O flag: entry indices must stay below 2^30)
+  if (msm_use_batch_affine() && (size_t)plan.W * n < ((size_t)1 << 30)) {
     B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
-    B200_CHECK(msm_accumulate_batch_affine<G>(d_points, plan, ws, pw));
+    B200_CHECK(msm_accumulate_batch_affine<G>(d_points, n, plan, ws, pw));
   } else {
     B200_CUDA_CHECK(cudaStreamWaitEvent(ws.acc_stream, pw.prep_done, 0));
     B200_CUDA_CHECK(cudaEventRecord(stage->ta, ws.acc_stream));

@@ -39,6 +39,7 @@ struct MsmWorkspace {
   DevBuf ntasks, task_off, task_bucket, task_len, task_len_sorted, partials;
   DevBuf scalar_out, fold_cnt, fold_off, fold_bucket, fold_partials;  // fold_* hold two ping-pong halves
   DevBuf aff_cnt, aff_off, aff_totals, aff_pts[2], aff_scratch;        // batch-affine accumulation (msm_affine_*)
+  DevBuf aff_pairs, aff_oflag[2], base_flags;                          // operand pairs of all rounds, O flags per round
   DevBuf merged_scalars;                                               // scalars after equal-base merging (MsmDedup)
   // Two streams per MSM: `stream` (HIGH priority) carries the short, latency-bound kernels - digits, counting sort,
   // task lists, fold/combine, bucket reduction, tree sums; `acc_stream` (LOW priority) carries the long accumulation
@@ -106,6 +107,10 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan, cons
 int msm_make_plan(size_t n, bool merged, MsmPlan &plan);
 int msm_affine_levels(const uint32_t *counts, const uint32_t *offsets, uint32_t nbuckets, uint32_t max_count,
                       std::vector<size_t> &totals);
+int msm_base_flags(const void *d_points, size_t n, size_t point_bytes, DevBuf &flags, cudaStream_t st);
+int msm_affine_pairs(MsmWorkspace &ws, const uint32_t *cnt, const uint32_t *off, uint32_t nbuckets,
+                     const std::vector<size_t> &totals, const uint32_t *entries, const uint8_t *base_is_O, size_t n_bases,
+                     std::vector<size_t> &pair_off);
 bool msm_use_batch_affine();
 constexpr uint32_t kFoldWidth = 32;  // a bucket with more task sums than this is folded in parallel first
 int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, uint32_t *cnt_out, uint32_t *off_out,
