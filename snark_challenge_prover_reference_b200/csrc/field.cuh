@@ -661,7 +661,9 @@ struct alignas(16) Fp {
   // algorithm gives the same canonical bytes. Host and device: batched binary gcd (~10x fewer instructions than the
   // bitwise one; it is what makes the shared inversion of the batch-affine accumulation cheap). -DB200_INV_BITWISE
   // selects the bitwise routine on the device (round 1's default).
-  B200_HD static void inv(Fp &r, const Fp &a) {
+  // (out of line on the device: its ~1 KB of scratch arrays and their live ranges then stay out of the calling kernel's
+  // register allocation)
+  B200_HD static B200_NOINLINE void inv(Fp &r, const Fp &a) {
 #if defined(__CUDA_ARCH__) && defined(B200_INV_BITWISE)
     inv_binary(r, a);
 #else

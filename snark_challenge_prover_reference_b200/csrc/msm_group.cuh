@@ -11,6 +11,38 @@
 
 namespace b200 {
 
+// L2 prefetch of a whole object: one prefetch per 128-byte line (objects are 64-byte aligned multiples of 64 bytes, or
+// 32-byte aligned field elements). A per-thread instruction: cp.async.bulk.prefetch would be cheaper per byte, but it
+// takes warp-uniform operands, and with 32 different addresses the compiler serialises it over the lanes (measured:
+// 9.7 % of the round kernel's instructions).
+template <class T>
+__device__ __forceinline__ void prefetch_l2(const T *p) {
+  const char *c = reinterpret_cast<const char *>(p);
+#pragma unroll
+  for (int off = 0; off < (int)sizeof(T); off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+  if (sizeof(T) % 128 != 0 && sizeof(T) % 64 != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + sizeof(T) - 1));
+}
+// streaming (evict-first) copies: the points, the prefix products and the round outputs pass through the caches once;
+// the L1 / L2 capacity is needed for the threads' stack frames (the operands of every field operation live there).
+// Without the hint the 40 GB that stream through one round evict the 70 MB of frames from the L2, and every field
+// operation then waits on DRAM (measured: L2 hit rate 46 %, 23 % of the warps' time in long-scoreboard stalls).
+template <class T>
+__device__ __forceinline__ void load_streaming(T &dst, const T *src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  uint4 *d = reinterpret_cast<uint4 *>(&dst);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 16); k++) d[k] = __ldcs(s + k);
+}
+template <class T>
+__device__ __forceinline__ void store_streaming(T *dst, const T &src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  const uint4 *s = reinterpret_cast<const uint4 *>(&src);
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 16); k++) __stcs(d + k, s[k]);
+}
+
 // One thread sums one task (a piece of <= T entries of one bucket's list) by mixed addition.
 template <class G>
 __global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : (G::F::kDegree == 2 ? 4 : 1)) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
@@ -32,7 +64,8 @@ __global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : (G::F::kDegree =
   xyzz_set_zero(acc);
   for (uint32_t k = 0; k < len; k++) {
     uint32_t e = entries[start + k];
-    Affine<F> q = points[e >> 1];
+    Affine<F> q;
+    load_streaming(q, points + (e >> 1));  // table gathers pass through once: keep the L2 for the stack frames
     if (affine_is_zero(q)) continue;
     if (e & 1) F::neg(q.y, q.y);
     xyzz_madd<G>(acc, q);
@@ -115,42 +148,40 @@ __global__ void __launch_bounds__(128) msm_combine_kernel(const Proj<typename G:
 #endif
 constexpr uint32_t kAffNone = 0xffffffffu;
 
-template <class T>
-__device__ __forceinline__ void prefetch_l2(const T *p) {
-  // whole object, 16-byte granules (sizeof(Affine<F>) and sizeof(F) are multiples of 16, objects 16-byte aligned)
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "n"(sizeof(T)) : "memory");
-}
-
-// One operand of an addition. p points at the stored point (table entry or previous round's output), `neg` says the
+// One operand of an addition: index of the stored point (table entry or previous round's output), `neg` says the
 // operand is its negative (first round: negative digit), `inf` that it is O.
-template <class F>
 struct AffOperand {
-  const Affine<F> *p;
-  uint32_t neg, inf;
+  uint32_t idx, neg, inf;
 };
-template <class F>
-__device__ __forceinline__ AffOperand<F> aff_operand(const Affine<F> *src, const uint8_t *oflag_in, uint32_t v) {
-  AffOperand<F> o;
-  o.p = src + ((v & 0x7fffffffu) >> 1);
+__device__ __forceinline__ AffOperand aff_operand(const uint8_t *oflag_in, uint32_t v) {
+  AffOperand o;
+  o.idx = (v & 0x7fffffffu) >> 1;
   o.neg = v & 1u;
-  o.inf = oflag_in ? oflag_in[(v & 0x7fffffffu) >> 1] : (v >> 31);
+  o.inf = oflag_in ? oflag_in[o.idx] : (v >> 31);
   return o;
 }
 // kind of one output: 0 copy first operand, 1 copy second, 2 result O, 3 chord, 4 tangent; den = the denominator of
-// lambda for kinds 3 and 4. Every case is arranged so that no y coordinate ever has to be negated up front:
+// lambda for kinds 3 and 4. p1 / p2 are local copies of the operands (x only is enough unless the x's are equal: `ys`
+// says whether the y coordinates have been loaded, and they are fetched here when needed).
+// Every case is arranged so that no y coordinate ever has to be negated up front:
 //   same flags     : lambda = (y2 - y1)/(x2 - x1), y3 = lambda (x1 - x3) - y1   - the sum of the stored points
 //   different flags: lambda = (y1 + y2)/(x2 - x1), y3 = lambda (x3 - x1) - y1   - P1 - P2 of the stored points
 // and the result is negated (y3 := y1 - ...) when the FIRST operand carried the flag.
 template <class F>
-__device__ __forceinline__ int aff_classify(const AffOperand<F> &a, const AffOperand<F> &b, bool has_second, F &den) {
+__device__ __forceinline__ int aff_classify(const Affine<F> *src, const AffOperand &a, const AffOperand &b, bool has_second,
+                                            Affine<F> &p1, Affine<F> &p2, bool ys, F &den) {
   if (!has_second) return 0;
   if (a.inf) return 1;
   if (b.inf) return 0;
-  F::sub(den, b.p->x, a.p->x);
+  F::sub(den, p2.x, p1.x);
   if (!F::is_zero(den)) return 3;
-  const bool same_point = F::eq(a.p->y, b.p->y) == (a.neg == b.neg);
+  if (!ys) {
+    load_streaming(p1.y, &src[a.idx].y);
+    load_streaming(p2.y, &src[b.idx].y);
+  }
+  const bool same_point = F::eq(p1.y, p2.y) == (a.neg == b.neg);
   if (!same_point) return 2;
-  F::dbl(den, a.p->y);
+  F::dbl(den, p1.y);
   return 4;
 }
 
@@ -162,8 +193,9 @@ __global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(
   typedef typename G::F F;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= S || t >= total_out) return;
-  // the only field elements on the stack; inv holds the running product first
-  F inv, den, lam, num, x3;
+  // the field elements on the stack; inv holds the running product first; p1 / p2 are the operands of the current output
+  F inv, den, lam, num;
+  Affine<F> p1, p2;
   F::set_one(inv);
   // ---- forward: running product of the denominators
   uint32_t j = t;
@@ -175,15 +207,20 @@ __global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(
     if (more) {
       nx = pairs[jn];
       if (nx.y != kAffNone) {
-        prefetch_l2(src + ((nx.x & 0x7fffffffu) >> 1));
-        prefetch_l2(src + ((nx.y & 0x7fffffffu) >> 1));
+        prefetch_l2(&src[(nx.x & 0x7fffffffu) >> 1].x);
+        prefetch_l2(&src[(nx.y & 0x7fffffffu) >> 1].x);
       }
     }
-    const AffOperand<F> q1 = aff_operand(src, oflag_in, pr.x);
-    const AffOperand<F> q2 = pr.y != kAffNone ? aff_operand(src, oflag_in, pr.y) : q1;
-    const int kind = aff_classify(q1, q2, pr.y != kAffNone, den);
+    const bool has2 = pr.y != kAffNone;
+    const AffOperand q1 = aff_operand(oflag_in, pr.x);
+    const AffOperand q2 = has2 ? aff_operand(oflag_in, pr.y) : q1;
+    if (has2 && !q1.inf && !q2.inf) {
+      load_streaming(p1.x, &src[q1.idx].x);
+      load_streaming(p2.x, &src[q2.idx].x);
+    }
+    const int kind = aff_classify(src, q1, q2, has2, p1, p2, false, den);
     if (kind >= 3) F::mul(inv, inv, den);
-    pre[j] = inv;
+    store_streaming(pre + j, inv);
     if (!more) break;
     j = jn;
   }
@@ -199,51 +236,57 @@ __global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(
       if (nx.y != kAffNone) prefetch_l2(src + ((nx.y & 0x7fffffffu) >> 1));
       if (j >= 2 * S) prefetch_l2(pre + (j - 2 * S));
     }
-    const AffOperand<F> q1 = aff_operand(src, oflag_in, pr.x);
-    const AffOperand<F> q2 = pr.y != kAffNone ? aff_operand(src, oflag_in, pr.y) : q1;
-    const int kind = aff_classify(q1, q2, pr.y != kAffNone, den);
+    const bool has2 = pr.y != kAffNone;
+    const AffOperand q1 = aff_operand(oflag_in, pr.x);
+    const AffOperand q2 = has2 ? aff_operand(oflag_in, pr.y) : q1;
+    // all operand loads of this output are issued together (one memory latency), then everything is local
+    load_streaming(p1, src + q1.idx);
+    if (has2) load_streaming(p2, src + q2.idx);
+    if (more) load_streaming(lam, pre + (j - S));
+    const int kind = aff_classify(src, q1, q2, has2, p1, p2, true, den);
     Affine<F> *out = pts_out + j;
     if (kind <= 1) {
-      const AffOperand<F> &q = kind == 0 ? q1 : q2;
-      out->x = q.p->x;
-      if (q.neg && !q.inf) F::neg(out->y, q.p->y);
-      else out->y = q.p->y;
+      const AffOperand &q = kind == 0 ? q1 : q2;
+      Affine<F> &pq = kind == 0 ? p1 : p2;
+      if (q.neg && !q.inf) F::neg(pq.y, pq.y);
+      store_streaming(out, pq);
       oflag_out[j] = (uint8_t)q.inf;
     } else if (kind == 2) {
-      F::set_zero(x3);
-      out->x = x3;
-      out->y = x3;
+      F::set_zero(p1.x);
+      F::set_zero(p1.y);
+      store_streaming(out, p1);
       oflag_out[j] = 1;
     } else {
       const bool same = kind == 4 || q1.neg == q2.neg;
       if (kind == 3) {
-        if (same) F::sub(num, q2.p->y, q1.p->y);
-        else F::add(num, q1.p->y, q2.p->y);
+        if (same) F::sub(num, p2.y, p1.y);
+        else F::add(num, p1.y, p2.y);
       } else {
-        F::sqr(num, q1.p->x);
-        F::add(lam, num, num);
-        F::add(num, lam, num);
-        F::set_one(lam);
-        G::mul_by_a(lam, lam);
-        F::add(num, num, lam);  // 3 x^2 + a
+        F::sqr(num, p1.x);
+        F::add(p2.y, num, num);
+        F::add(num, p2.y, num);
+        F::set_one(p2.y);
+        G::mul_by_a(p2.y, p2.y);
+        F::add(num, num, p2.y);  // 3 x^2 + a   (p2.y is free: P2 == P1 here)
       }
       // lambda = num * (inv * prefix) ; then drop this denominator from the running inverse
       // (NOTE: a variant that kept the per-output inverse in its own temporary - dinv = inv * prefix; lambda = num * dinv -
       // was miscompiled by nvcc 12.9 for the MNT6753-G1 instantiation: the PTX passed the SAME stack slot for dinv and
       // num. This ordering needs no such temporary; the tests run every MSM case in both accumulation modes.)
       F::mul(num, num, inv);
-      if (more) F::mul(lam, num, pre[j - S]);
+      if (more) F::mul(lam, num, lam);  // lam held pre[j - S]
       else lam = num;
       F::mul(inv, inv, den);
-      F::sqr(x3, lam);
-      F::sub(x3, x3, q1.p->x);
-      F::sub(x3, x3, q2.p->x);
-      if (same) F::sub(num, q1.p->x, x3);
-      else F::sub(num, x3, q1.p->x);
+      F::sqr(den, lam);                 // den is free from here on: x3 is built in it
+      F::sub(den, den, p1.x);
+      F::sub(den, den, p2.x);
+      if (same) F::sub(num, p1.x, den);
+      else F::sub(num, den, p1.x);
       F::mul(num, lam, num);
-      if (q1.neg) F::sub(out->y, q1.p->y, num);
-      else F::sub(out->y, num, q1.p->y);
-      out->x = x3;
+      if (q1.neg) F::sub(p1.y, p1.y, num);
+      else F::sub(p1.y, num, p1.y);
+      p1.x = den;
+      store_streaming(out, p1);
       oflag_out[j] = 0;
     }
     if (!more) break;
