@@ -280,6 +280,43 @@ def step_plan(world, mode=None):
     return "dedicated", list(range(world - 1)), world - 1
 
 
+def rank_jobs(rank, world, mode=None):
+    """this rank's share of a step: [(proof index, rank within that proof's group, size of the group)]"""
+    mode, big_ranks, small_rank = step_plan(world, mode)
+    jobs = []
+    if rank in big_ranks:
+        jobs.append((0, big_ranks.index(rank), len(big_ranks)))
+    if small_rank is None:
+        jobs.append((1, rank, world))
+    elif rank == small_rank:
+        jobs.append((1, 0, 1))
+    return jobs
+
+
+def pack_rank_blob(jobs, outs, slot):
+    """what one rank contributes to the step's all_gather: per proof a fixed-size slot holding its partial sums (or,
+    for a proof it ran whole, the finished proof), zeros where it took no part"""
+    blob = bytearray(sum(slot))
+    for (i, _, _), o in zip(jobs, outs):
+        off = sum(slot[:i])
+        blob[off:off + len(o)] = o
+    return blob
+
+
+def combine_step(pkg, blobs, world, slot, pbytes, proof_len, r_fr, mode=None):
+    """rank 0: the gathered blobs -> the step's two proofs"""
+    _, big_ranks, small_rank = step_plan(world, mode)
+    parts = regroup_partials(blobs, slot)
+    big = b"".join(parts[0][r * slot[0]:r * slot[0] + pbytes[0]] for r in big_ranks)
+    proofs = [pkg.prove_combine(0, big, len(big_ranks), r_fr[0])]
+    if small_rank is None:
+        small = b"".join(parts[1][r * slot[1]:r * slot[1] + pbytes[1]] for r in range(world))
+        proofs.append(pkg.prove_combine(1, small, world, r_fr[1]))
+    else:
+        proofs.append(parts[1][small_rank * slot[1]:small_rank * slot[1] + proof_len[1]])
+    return proofs
+
+
 def ncu_traffic(csv_name, kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the first launch of a kernel in a committed
     `ncu --page raw --csv` export under profiles/ (row 0 names, row 1 units, then one row per launch)."""
@@ -326,14 +363,7 @@ def b200_arm(args):
     shapes = ((0, k4), (1, k6))
     files = ensure_synth(k4, k6, wait_only=local != 0)
     mode, big_ranks, small_rank = step_plan(world)
-    # which proofs this rank takes part in: (index into shapes, rank within the proof's group, size of that group)
-    my_jobs = []
-    if rank in big_ranks:
-        my_jobs.append((0, big_ranks.index(rank), len(big_ranks)))
-    if small_rank is None:
-        my_jobs.append((1, rank, world))
-    elif rank == small_rank:
-        my_jobs.append((1, 0, 1))
+    my_jobs = rank_jobs(rank, world)  # (index into shapes, rank within the proof's group, size of that group)
 
     # ---- key load (B::read_params) + key-only preprocessing, outside every timed region like the reference's own key
     # loading (main.cpp:200-203); both are reported
@@ -366,24 +396,13 @@ def b200_arm(args):
         else:
             jobs = [(keys[i], inputs[i], r, w) if w > 1 else (keys[i], inputs[i]) for i, r, w in my_jobs]
             outs, tms = pkg.prove_batch(jobs, timings=True) if jobs else ([], [])
-            blob = bytearray(sum(slot))
-            for (i, _, _), o in zip(my_jobs, outs):
-                off = sum(slot[:i])
-                blob[off:off + len(o)] = o
-            mine = torch.frombuffer(blob, dtype=torch.uint8).to(dev)
+            mine = torch.frombuffer(pack_rank_blob(my_jobs, outs, slot), dtype=torch.uint8).to(dev)
             allp = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allp, mine)
             proofs = []
             if rank == 0:
                 blobs = [bytes(t.cpu().numpy().tobytes()) for t in allp]
-                parts = regroup_partials(blobs, slot)
-                big = b"".join(parts[0][r * slot[0]:r * slot[0] + pbytes[0]] for r in big_ranks)
-                proofs.append(pkg.prove_combine(0, big, len(big_ranks), r_fr[0]))
-                if small_rank is None:
-                    small = b"".join(parts[1][r * slot[1]:r * slot[1] + pbytes[1]] for r in range(world))
-                    proofs.append(pkg.prove_combine(1, small, world, r_fr[1]))
-                else:
-                    proofs.append(parts[1][small_rank * slot[1]:small_rank * slot[1] + proof_len[1]])
+                proofs = combine_step(pkg, blobs, world, slot, pbytes, proof_len, r_fr)
         if timings is not None:
             wall = time.perf_counter() - t0
             for (i, _, _), tm in zip(my_jobs, tms):

@@ -275,21 +275,13 @@ struct alignas(16) Fp {
     uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
     load_limbs(x, a);
     load_limbs(y, b);
-    // Default: interleaved CIOS (1152 IMAD.WIDE). -DB200_MUL_KARATSUBA selects the one-level Karatsuba product +
-    // half-width Montgomery reduction (1008 IMAD.WIDE, ~330 more IADD3 on the ALU pipe). Measured on B200 (round 1):
-    // 12 % fewer multiplier-pipe instructions but the longer carry chains and +16 registers drop the fmaheavy
-    // pipe from 94 % to 84 % busy at 8 warps/SM - no net gain, so it stays an option.
-#if defined(B200_MUL_KARATSUBA)
-    if (P::kTag == 'A')
-      fp_mulk_ptx_A(z, x, y);
-    else
-      fp_mulk_ptx_B(z, x, y);
-#else
+    // Interleaved CIOS, 1152 IMAD.WIDE. (A one-level Karatsuba product with half-width reduction was generated and
+    // measured in round 1 - 12 % fewer multiplier instructions, but longer carry chains and +16 registers drop the
+    // fmaheavy pipe from 94 % to 84 % busy - and removed in round 2; tools/gen_fp_ptx.py --experimental still emits it.)
     if (P::kTag == 'A')
       fp_mul_ptx_A(z, x, y);
     else
       fp_mul_ptx_B(z, x, y);
-#endif
     store_limbs(r, z);
   }
 #endif
@@ -300,29 +292,9 @@ struct alignas(16) Fp {
     host_mul(r, a, b);
 #endif
   }
-#if defined(__CUDACC__) && defined(B200_SQR_DEDICATED)
-  // -DB200_SQR_DEDICATED: squarings use the generated 876-MAC squaring (276 off-diagonal products doubled + 24 squares
-  // + Montgomery reduction of the 48-limb value) instead of the 1152-MAC multiply. Validated against Python integers
-  // through the PTX interpreter (tests/test_ptx_model.py); NOT yet timed on the GPU (round 1 ran out of GPU budget;
-  // the Karatsuba variant showed that fewer multiplier instructions do not automatically mean less time), so it is
-  // off by default.
-  static __device__ __noinline__ void sqr_dev(uint32_t *r, const uint32_t *a) {
-    uint32_t x[kLimbs], z[kLimbs];
-    load_limbs(x, a);
-    if (P::kTag == 'A')
-      fp_sqr_ptx_A(z, x);
-    else
-      fp_sqr_ptx_B(z, x);
-    store_limbs(r, z);
-  }
-#endif
-  B200_HD static B200_INLINE void sqr(Fp &r, const Fp &a) {
-#if defined(__CUDA_ARCH__) && defined(B200_SQR_DEDICATED)
-    sqr_dev(r.l, a.l);
-#else
-    mul(r, a, a);
-#endif
-  }
+  // (a dedicated 876-MAC squaring was generated, validated and timed in round 2: G1 accumulation 49.5 -> 49.0 ms, G2
+  // 160.7 -> 162.0 ms - noise, so squarings stay multiplications; tools/gen_fp_ptx.py --experimental still emits it)
+  B200_HD static B200_INLINE void sqr(Fp &r, const Fp &a) { mul(r, a, a); }
 
   // out-of-line add / sub / small-constant multiply for the tower fields (keeps Fq2/Fq3 code a short list of calls:
   // with the ~100-instruction carry chains inlined ~40 times the G2 kernels no longer fit the instruction cache)

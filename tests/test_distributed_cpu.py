@@ -109,3 +109,49 @@ def test_two_rank_step_with_both_curves_in_one_gather():
     port = 29850 + (os.getpid() % 100)
     mp.spawn(_worker_step, args=(world, port, ret), nprocs=world, join=True)
     assert ret.get("ok") is True
+
+
+def _worker_dedicated(rank, world, port, ret):
+    """bench.py's plan from 4 GPUs on (forced here at world 2): the small proof runs WHOLE on the last rank, the other
+    ranks share the large one; one all_gather of fixed-size slots; rank 0 combines."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import snark_challenge_prover_reference_b200 as b200
+    O = util.load_oracle()
+    cases = [(0, 5), (1, 5)]
+    pbytes = [b200.partial_bytes(c) for c, _ in cases]
+    proof_len = [b200.proof_bytes(c) for c, _ in cases]
+    slot = [max(a, b) for a, b in zip(pbytes, proof_len)]
+    jobs = bench.rank_jobs(rank, world, "dedicated")
+    outs, r_fr = [], [util.golden(c, k)[1][-96:] for c, k in cases]
+    for i, r, w in jobs:
+        curve, k = cases[i]
+        if i == 0:
+            outs.append(_oracle_partials(b200, O, curve, k, r, w)[0])
+        else:
+            params, inp, _ = util.golden(curve, k)
+            outs.append(util.orc_prove(O, curve, params, inp))
+    mine = torch.frombuffer(bench.pack_rank_blob(jobs, outs, slot), dtype=torch.uint8)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        blobs = [t.numpy().tobytes() for t in gathered]
+        proofs = bench.combine_step(b200, blobs, world, slot, pbytes, proof_len, r_fr, "dedicated")
+        ret["ok"] = proofs == [util.golden(c, k)[2] for c, k in cases]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_with_dedicated_small_proof_rank():
+    import bench
+    assert bench.step_plan(8)[:1] + bench.step_plan(8)[2:] == ("dedicated", 7) and bench.step_plan(8)[1] == list(range(7))
+    assert bench.step_plan(2) == ("shard", [0, 1], None) and bench.step_plan(1) == ("shard", [0], None)
+    assert bench.rank_jobs(7, 8) == [(1, 0, 1)] and bench.rank_jobs(3, 8) == [(0, 3, 7)] and bench.rank_jobs(1, 2) == [(0, 1, 2), (1, 1, 2)]
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29950 + (os.getpid() % 40)
+    mp.spawn(_worker_dedicated, args=(world, port, ret), nprocs=world, join=True)
+    assert ret.get("ok") is True
