@@ -213,6 +213,39 @@ struct alignas(16) Fp {
 #pragma unroll
     for (int k = 0; k < kLimbs / 4; k++) r4[k] = make_uint4(z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
   }
+  // streaming variant: the limbs come from GLOBAL memory with the evict-first hint (data that passes through once)
+  static __device__ __forceinline__ void load_limbs_cs(uint32_t (&x)[kLimbs], const uint32_t *a) {
+    const uint4 *a4 = reinterpret_cast<const uint4 *>(a);
+#pragma unroll
+    for (int k = 0; k < kLimbs / 4; k++) {
+      const uint4 v = __ldcs(a4 + k);
+      x[4 * k] = v.x;
+      x[4 * k + 1] = v.y;
+      x[4 * k + 2] = v.z;
+      x[4 * k + 3] = v.w;
+    }
+  }
+  // r = a +/- b with operands read in place; GA / GB: that operand lives in global memory and is streamed
+  template <bool SUB, bool GA, bool GB>
+  static __device__ __noinline__ void addsub_dev_g(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
+    if (GA) load_limbs_cs(x, a);
+    else load_limbs(x, a);
+    if (GB) load_limbs_cs(y, b);
+    else load_limbs(y, b);
+    if (SUB) {
+      if (P::kTag == 'A') fp_sub_ptx_A(z, x, y);
+      else fp_sub_ptx_B(z, x, y);
+    } else {
+      if (P::kTag == 'A') fp_add_ptx_A(z, x, y);
+      else fp_add_ptx_B(z, x, y);
+    }
+    store_limbs(r, z);
+  }
+  template <bool GA, bool GB>
+  static __device__ __forceinline__ void sub_g(Fp &r, const Fp &a, const Fp &b) { addsub_dev_g<true, GA, GB>(r.l, a.l, b.l); }
+  template <bool GA, bool GB>
+  static __device__ __forceinline__ void add_g(Fp &r, const Fp &a, const Fp &b) { addsub_dev_g<false, GA, GB>(r.l, a.l, b.l); }
   static __device__ __noinline__ void add_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
     uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
     load_limbs(x, a);
@@ -271,10 +304,13 @@ struct alignas(16) Fp {
 #if defined(__CUDACC__)
   // out-of-line device multiply: operands come from (local/shared/global) memory, limbs live in registers only
   // inside the body. One copy per modulus per module keeps the instruction footprint inside the 32 KB L1.5 I-cache.
-  static __device__ __noinline__ void mul_dev(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+  // b_streamed != 0: b lives in global memory and is read with the evict-first hint (a run-time flag, not a second
+  // copy of the body)
+  static __device__ __noinline__ void mul_dev(uint32_t *r, const uint32_t *a, const uint32_t *b, int b_streamed = 0) {
     uint32_t x[kLimbs], y[kLimbs], z[kLimbs];
     load_limbs(x, a);
-    load_limbs(y, b);
+    if (b_streamed) load_limbs_cs(y, b);
+    else load_limbs(y, b);
     // Interleaved CIOS, 1152 IMAD.WIDE. (A one-level Karatsuba product with half-width reduction was generated and
     // measured in round 1 - 12 % fewer multiplier instructions, but longer carry chains and +16 registers drop the
     // fmaheavy pipe from 94 % to 84 % busy - and removed in round 2; tools/gen_fp_ptx.py --experimental still emits it.)
@@ -292,6 +328,10 @@ struct alignas(16) Fp {
     host_mul(r, a, b);
 #endif
   }
+#if defined(__CUDACC__)
+  // r = a * b with b streamed from global memory
+  static __device__ __forceinline__ void mul_bg(Fp &r, const Fp &a, const Fp &b) { mul_dev(r.l, a.l, b.l, 1); }
+#endif
   // (a dedicated 876-MAC squaring was generated, validated and timed in round 2: G1 accumulation 49.5 -> 49.0 ms, G2
   // 160.7 -> 162.0 ms - noise, so squarings stay multiplications; tools/gen_fp_ptx.py --experimental still emits it)
   B200_HD static B200_INLINE void sqr(Fp &r, const Fp &a) { mul(r, a, a); }

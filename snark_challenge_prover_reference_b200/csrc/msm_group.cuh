@@ -294,6 +294,140 @@ __global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(
   }
 }
 
+// ---- the same round for groups over the BASE field (G1), with the thread's three live field elements in SHARED
+// memory. In the generic kernel above every field operation fetches its operands from the stack frame; 384-512 threads
+// x 1.8 KB do not fit the L1, so a quarter of the warps' time went into long-scoreboard stalls in front of every
+// multiplication (profiles/r02_summary.md). Three temporaries per thread - the running inverse and two scratch values -
+// are all a G1 addition needs when the operands are read in place from global memory (streaming loads inside the
+// add / sub routines, prefetched into L2 one output ahead) and x3 is stored as soon as it exists:
+//   B = x2 - x1 [den]            A = y2 -/+ y1 ; A *= inv ; A *= pre[j-S] [lambda] ; inv *= B
+//   B = A^2 - x1 - x2 [x3] -> out.x ;  B = x1 - B ; B *= A ; A = B - y1 -> out.y
+// Layout: slot s of thread t at word ((s * 128 + t) * 28): a 112-byte stride makes the 128-bit accesses of a
+// quarter-warp hit 8 different bank groups. 3 x 128 x 112 B = 43 KB per block, 4 blocks per SM.
+#ifndef B200_AFF_G1_BLOCKS
+#define B200_AFF_G1_BLOCKS 4
+#endif
+constexpr int kAffSlotStride = 112;  // bytes
+constexpr size_t kAffG1Smem = 3 * 128 * kAffSlotStride;
+
+template <class G>
+__global__ void __launch_bounds__(128, B200_AFF_G1_BLOCKS) msm_affine_round_g1_kernel(
+    const Affine<typename G::F> *__restrict__ src, const uint8_t *__restrict__ oflag_in, const uint2 *__restrict__ pairs,
+    uint32_t total_out, uint32_t S, Affine<typename G::F> *__restrict__ pts_out, uint8_t *__restrict__ oflag_out,
+    typename G::F *__restrict__ pre) {
+  typedef typename G::F F;
+  static_assert(F::kDegree == 1, "base-field groups only");
+  extern __shared__ uint4 aff_smem[];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S || t >= total_out) return;
+  char *sm = reinterpret_cast<char *>(aff_smem);
+  F &inv = *reinterpret_cast<F *>(sm + (0 * 128 + threadIdx.x) * kAffSlotStride);
+  F &A = *reinterpret_cast<F *>(sm + (1 * 128 + threadIdx.x) * kAffSlotStride);
+  F &B = *reinterpret_cast<F *>(sm + (2 * 128 + threadIdx.x) * kAffSlotStride);
+  F::set_one(inv);
+  // classification of one output into B (= den); 0 copy first, 1 copy second, 2 O, 3 chord, 4 tangent
+  auto classify = [&](const AffOperand &q1, const AffOperand &q2, bool has2) -> int {
+    if (!has2) return 0;
+    if (q1.inf) return 1;
+    if (q2.inf) return 0;
+    F::template sub_g<true, true>(B, src[q2.idx].x, src[q1.idx].x);
+    if (!F::is_zero(B)) return 3;
+    const bool same_point = F::eq(src[q1.idx].y, src[q2.idx].y) == (q1.neg == q2.neg);
+    if (!same_point) return 2;
+    F::template add_g<true, true>(B, src[q1.idx].y, src[q1.idx].y);
+    return 4;
+  };
+  // ---- forward: running product of the denominators
+  uint32_t j = t;
+  uint2 nx = pairs[j];
+  for (;;) {
+    const uint2 pr = nx;
+    const uint32_t jn = j + S;
+    const bool more = jn < total_out && jn > j;
+    if (more) {
+      nx = pairs[jn];
+      if (nx.y != kAffNone) {
+        prefetch_l2(&src[(nx.x & 0x7fffffffu) >> 1].x);
+        prefetch_l2(&src[(nx.y & 0x7fffffffu) >> 1].x);
+      }
+    }
+    const bool has2 = pr.y != kAffNone;
+    const AffOperand q1 = aff_operand(oflag_in, pr.x);
+    const AffOperand q2 = has2 ? aff_operand(oflag_in, pr.y) : q1;
+    const int kind = classify(q1, q2, has2);
+    if (kind >= 3) F::mul(inv, inv, B);
+    store_streaming(pre + j, inv);
+    if (!more) break;
+    j = jn;
+  }
+  F::inv(inv, inv);
+  // ---- backward
+  nx = pairs[j];
+  for (;;) {
+    const uint2 pr = nx;
+    const bool more = j >= S;
+    if (more) {
+      nx = pairs[j - S];
+      prefetch_l2(src + ((nx.x & 0x7fffffffu) >> 1));
+      if (nx.y != kAffNone) prefetch_l2(src + ((nx.y & 0x7fffffffu) >> 1));
+      if (j >= 2 * S) prefetch_l2(pre + (j - 2 * S));
+    }
+    const bool has2 = pr.y != kAffNone;
+    const AffOperand q1 = aff_operand(oflag_in, pr.x);
+    const AffOperand q2 = has2 ? aff_operand(oflag_in, pr.y) : q1;
+    const Affine<F> &p1 = src[q1.idx], &p2 = src[q2.idx];
+    const int kind = classify(q1, q2, has2);
+    Affine<F> *out = pts_out + j;
+    if (kind <= 1) {
+      const AffOperand &q = kind == 0 ? q1 : q2;
+      const Affine<F> &pq = kind == 0 ? p1 : p2;
+      load_streaming(A, &pq.x);
+      store_streaming(&out->x, A);
+      load_streaming(A, &pq.y);
+      if (q.neg && !q.inf) F::neg(A, A);
+      store_streaming(&out->y, A);
+      oflag_out[j] = (uint8_t)q.inf;
+    } else if (kind == 2) {
+      F::set_zero(A);
+      store_streaming(&out->x, A);
+      store_streaming(&out->y, A);
+      oflag_out[j] = 1;
+    } else {
+      const bool same = kind == 4 || q1.neg == q2.neg;
+      if (kind == 3) {
+        if (same) F::template sub_g<true, true>(A, p2.y, p1.y);
+        else F::template add_g<true, true>(A, p1.y, p2.y);
+      } else {
+        // 3 x^2 + a ; inv must survive, B holds den = 2y: build the numerator in A with the output slot as scratch
+        F &T = out->x;  // (global scratch: the tangent case is rare - a duplicated base meeting itself)
+        load_streaming(A, &p1.x);
+        F::sqr(A, A);
+        F::add(T, A, A);
+        F::add(A, T, A);
+        F::set_one(T);
+        G::mul_by_a(T, T);
+        F::add(A, A, T);
+      }
+      F::mul(A, A, inv);                       // num * inv
+      if (more) F::mul_bg(A, A, pre[j - S]);   // lambda
+      F::mul(inv, inv, B);                     // drop this denominator from the running inverse
+      F::sqr(B, A);
+      F::template sub_g<false, true>(B, B, p1.x);
+      F::template sub_g<false, true>(B, B, p2.x);  // x3
+      store_streaming(&out->x, B);
+      if (same) F::template sub_g<true, false>(B, p1.x, B);
+      else F::template sub_g<false, true>(B, B, p1.x);
+      F::mul(B, A, B);
+      if (q1.neg) F::template sub_g<true, false>(A, p1.y, B);
+      else F::template sub_g<false, true>(A, B, p1.y);
+      store_streaming(&out->y, A);
+      oflag_out[j] = 0;
+    }
+    if (!more) break;
+    j -= S;
+  }
+}
+
 // bucket[b] = the single remaining point of list b (or O), converted to the projective form the reduction uses
 template <class G>
 __global__ void __launch_bounds__(128) msm_affine_finish_kernel(const Affine<typename G::F> *__restrict__ src,
@@ -440,6 +574,24 @@ int msm_accumulate_xyzz(const void *d_points, const MsmPlan &plan, MsmWorkspace 
   return 0;
 }
 
+// which round kernel a group uses: base-field groups take the shared-memory one (-DB200_AFF_G1_GENERIC: the generic one)
+template <class G, int DEG = G::F::kDegree>
+struct AffineRound {
+  typedef typename G::F F;
+  typedef void (*Kernel)(const Affine<F> *, const uint8_t *, const uint2 *, uint32_t, uint32_t, Affine<F> *, uint8_t *, F *);
+  static constexpr size_t kSmem = 0;
+  static Kernel kernel() { return msm_affine_round_kernel<G>; }
+};
+#if !defined(B200_AFF_G1_GENERIC)
+template <class G>
+struct AffineRound<G, 1> {
+  typedef typename G::F F;
+  typedef void (*Kernel)(const Affine<F> *, const uint8_t *, const uint2 *, uint32_t, uint32_t, Affine<F> *, uint8_t *, F *);
+  static constexpr size_t kSmem = kAffG1Smem;
+  static Kernel kernel() { return msm_affine_round_g1_kernel<G>; }
+};
+#endif
+
 // Bucket accumulation by rounds of batched affine additions (see msm_affine_round_kernel). n_bases = the MSM's n:
 // the first n entries of d_points are the bases themselves (window 0 of a table, or the plain query).
 template <class G>
@@ -459,7 +611,10 @@ int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmP
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_affine_round_kernel<G>, 128, 0);
+    if (AffineRound<G>::kSmem)
+      B200_CUDA_CHECK(cudaFuncSetAttribute(AffineRound<G>::kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)AffineRound<G>::kSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, AffineRound<G>::kernel(), 128, AffineRound<G>::kSmem);
     wave = (per_sm > 0 ? per_sm : 1) * sms * 128;
   }
   const Affine<F> *src = (const Affine<F> *)d_points;
@@ -477,7 +632,7 @@ int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmP
     B200_CHECK(outbuf.reserve(total_out * sizeof(Affine<F>)));
     B200_CHECK(oflag.reserve(total_out));
     B200_CHECK(ws.aff_scratch.reserve(total_out * sizeof(F)));
-    msm_affine_round_kernel<G><<<grid_for(S, 128), 128, 0, st>>>(src, oflag_in, ws.aff_pairs.as<uint2>() + pair_off[r],
+    AffineRound<G>::kernel()<<<grid_for(S, 128), 128, AffineRound<G>::kSmem, st>>>(src, oflag_in, ws.aff_pairs.as<uint2>() + pair_off[r],
                                                                (uint32_t)total_out, (uint32_t)S, outbuf.as<Affine<F>>(),
                                                                oflag.as<uint8_t>(), ws.aff_scratch.as<F>());
     B200_CUDA_CHECK(cudaGetLastError());
