@@ -317,6 +317,34 @@ def combine_step(pkg, blobs, world, slot, pbytes, proof_len, r_fr, mode=None):
     return proofs
 
 
+def drop_in_run(files, curve_name="MNT4753"):
+    """What a user of the reference's `cuda_prover_piecewise` sees: the driver binaries built over the `B::` bundle
+    (the reference's own UNMODIFIED cuda_prover_piecewise.cu -> oracle/_ref/piecewise_b200, and this repo's
+    csrc/host/prover_main.cpp -> bin/cuda_prover_piecewise) run as separate processes on the step's files; their own
+    'Total time from input to output' (key load + table build excluded, like main.cpp:203,270) and the proof's sha256."""
+    out = {}
+    exes = {"reference_driver_over_b200_bundle": os.path.join(REF_DIR, "piecewise_b200"),
+            "repo_driver": os.path.join(ROOT, "snark_challenge_prover_reference_b200", "bin", "cuda_prover_piecewise")}
+    for name, exe in exes.items():
+        if not os.path.exists(exe):
+            out[name] = {"unavailable": os.path.relpath(exe, ROOT) + " not built"}
+            continue
+        dst = os.path.join(files, "%s-output-%s" % (curve_name, name))
+        t0 = time.time()
+        r = subprocess.run([exe, curve_name, "compute", os.path.join(files, curve_name + "-parameters"),
+                            os.path.join(files, curve_name + "-input"), dst], capture_output=True, text=True)
+        wall = time.time() - t0
+        if r.returncode != 0 or not os.path.exists(dst):
+            out[name] = {"failed": (r.stderr or r.stdout)[-300:]}
+            continue
+        m = re.search(r"Total time from input to output: : (\d+) ms", r.stdout)
+        lp = re.search(r"load params: (\d+) ms", r.stdout)
+        out[name] = {"input_to_output_ms": float(m.group(1)) if m else None,
+                     "load_params_ms": float(lp.group(1)) if lp else None,
+                     "process_wall_s": wall, "sha256": sha256_file(dst)}
+    return out
+
+
 def ncu_traffic(csv_name, kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the first launch of a kernel in a committed
     `ncu --page raw --csv` export under profiles/ (row 0 names, row 1 units, then one row per launch)."""
@@ -364,6 +392,8 @@ def b200_arm(args):
     files = ensure_synth(k4, k6, wait_only=local != 0)
     mode, big_ranks, small_rank = step_plan(world)
     my_jobs = rank_jobs(rank, world)  # (index into shapes, rank within the proof's group, size of that group)
+    # the drop-in path, measured before this process takes its own 100 GB of HBM (separate processes, N = 1 only)
+    drop_in = drop_in_run(files) if world == 1 and not args.no_cpu_baseline else None
 
     # ---- key load (B::read_params) + key-only preprocessing, outside every timed region like the reference's own key
     # loading (main.cpp:200-203); both are reported
@@ -472,6 +502,10 @@ def b200_arm(args):
         parity["sha256_equal_to_reference_main_full_size"] = None
         parity["reference_run"] = "no reference output for these files on this box (run `bench.py --impl reference` first)"
     parity["proof_sha256"] = mine_sha
+    if drop_in:
+        for name, res in drop_in.items():
+            if "sha256" in res:
+                res["sha256_equal_to_b200_prove"] = res.pop("sha256") == mine_sha["MNT4753"]
 
     # ---- roofline of the dominant kernel: the G1 bucket accumulation (4 of the 5 MSMs of each proof). Inside a proof the
     # five MSMs run concurrently on five streams, so per-kernel event times overlap; the kernel is therefore timed
@@ -479,7 +513,13 @@ def b200_arm(args):
     # accumulation launches on the MSM's stream). Bound: the INT32 multiplier (IMAD.WIDE / fmaheavy) pipe.
     imad = pkg.imad_peak()
     peak = max(imad["mad_wide_mac32_per_s"], imad["carry_chain_mac32_per_s"], imad["montgomery_mul_mac32_per_s"])
-    accum_mode = "affine" if pkg.batch_affine_enabled() else "xyzz"
+    lib_mode = pkg.batch_affine_mode()
+
+    def accum_of(kind, entries):
+        """which accumulation kernel the library picks (msm_affine_wins in msm.cu)"""
+        if lib_mode != "auto":
+            return lib_mode
+        return "affine" if kind == "g2_fq2" and entries >= (8 << 20) else "xyzz"
     iso = {"g1": [], "g2": [], "a_merged": []}
     plans = {}
     if world == 1:
@@ -499,7 +539,9 @@ def b200_arm(args):
     if world == 1:
         acc_ms_g1 = sum(t for _, _, t, _ in iso["g1"])
         g1_alg = sum(MAC32_PER_POINT["g1"] * n for _, n, _, _ in iso["g1"])
-        g1_issued = sum(plans[(c, False)]["windows"] * ISSUED_MULS[accum_mode]["g1"] * IMAD_PER_MUL * n for c, n, _, _ in iso["g1"])
+        accum_mode = accum_of("g1", plans[(0, False)]["windows"] << k4)
+        g1_issued = sum(plans[(c, False)]["windows"] * ISSUED_MULS[accum_of("g1", plans[(c, False)]["windows"] * n)]["g1"] * IMAD_PER_MUL * n
+                        for c, n, _, _ in iso["g1"])
         g1_big = [t for c, _, t, _ in iso["g1"] if c == 0]
         tr = ncu_traffic("prof_accumulate_g1_r02_raw.csv", "Mnt4G1")
         roofline = {"bound": "imad", "bound_note": "INT32 multiplier (IMAD.WIDE / fmaheavy) pipe; neither HBM nor tensor bound, SURVEY.md 8d",
@@ -523,10 +565,12 @@ def b200_arm(args):
                     "timing": "kernel timed alone with CUDA events on its stream (inside a proof 5 MSMs overlap)"}
         acc_ms_g2 = sum(t for _, _, t, _ in iso["g2"])
         g2_alg = sum((MAC32_PER_POINT["g2_fq2"] if c == 0 else MAC32_PER_POINT["g2_fq3"]) * n for c, n, _, _ in iso["g2"])
-        g2_issued = sum(plans[(c, True)]["windows"] * ISSUED_MULS[accum_mode]["g2_fq2" if c == 0 else "g2_fq3"] * IMAD_PER_MUL * n
+        g2_kind = lambda c: "g2_fq2" if c == 0 else "g2_fq3"
+        g2_issued = sum(plans[(c, True)]["windows"] * ISSUED_MULS[accum_of(g2_kind(c), plans[(c, True)]["windows"] * n)][g2_kind(c)] * IMAD_PER_MUL * n
                         for c, n, _, _ in iso["g2"])
+        g2_mode = accum_of("g2_fq2", plans[(0, True)]["windows"] << k4)
         tr2 = ncu_traffic("prof_accumulate_g2_r02_raw.csv", "Mnt4G2")
-        roofline_g2 = {"kernel": "G2 bucket accumulation (%s)" % accum_mode, "achieved": g2_issued / (acc_ms_g2 / 1e3) / 1e12,
+        roofline_g2 = {"kernel": "G2 bucket accumulation (MNT4753: %s)" % g2_mode, "achieved": g2_issued / (acc_ms_g2 / 1e3) / 1e12,
                        "peak": peak / 1e12, "unit": "TMAC32/s", "frac": g2_issued / (acc_ms_g2 / 1e3) / peak,
                        "frac_algorithmic": g2_alg / (acc_ms_g2 / 1e3) / peak,
                        "launch_ms": [round(t, 2) for _, _, t, _ in iso["g2"]],
@@ -586,7 +630,7 @@ def b200_arm(args):
                        "l2": "inputs larger than L2: each step streams >1.6 GB of bases and 416 MB of scalars",
                        "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys",
                        "multi_gpu": {"mode": mode, "mnt4753_ranks": big_ranks, "mnt6753_rank": small_rank},
-                       "accumulation": accum_mode,
+                       "accumulation": lib_mode + " (auto = batched affine additions for large G2/Fq2 MSMs, XYZZ mixed additions otherwise)",
                        "key_preprocess": "pre-shifted base tables 2^(start_j)*P_i per MSM window, built once per key, "
                                          "outside the timed region (see key_load); see no_tables"},
             "key_load": {"from_file_ms": load_ms, "precompute_s": preprocess_s,
@@ -600,6 +644,8 @@ def b200_arm(args):
             "roofline_ntt": roofline_ntt, "proof_pair_latency_s": ms_dev / args.steps / 1e3,
             "proof_latency_s": {n: v["latency_s"] for n, v in per_curve.items()},
             "per_curve": per_curve, "parity": parity,
+            "drop_in": {"MNT4753": drop_in, "note": "the B:: bundle path driven by cuda_prover_piecewise (asynchronous multiexps resolved at "
+                        "G1_scale / G1_add / groth16_output_write), full size, separate processes"} if drop_in else None,
             "msm_phase_ms_per_step": {g: {k: v / args.steps for k, v in ph.items()} for g, ph in phases.items()},
             "imad_peak": imad}
     if world == 1:

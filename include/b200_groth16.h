@@ -76,8 +76,9 @@ int b200_msm_g1(int curve, const void *d_scalars, const void *d_points, size_t n
 int b200_msm_g2(int curve, const void *d_scalars, const void *d_points, size_t n, void *h_out_proj);
 /* tuning hook: force the Pippenger window width (0 = automatic) */
 int b200_msm_set_window(int c);
-/* Bucket accumulation of every following MSM: 0 = XYZZ mixed additions (default), 1 = batched affine additions
- * with simultaneous inversion. Same results bit for bit; the environment variable B200_BATCH_AFFINE=1 selects 1. */
+/* Bucket accumulation of every following MSM: 0 = XYZZ mixed additions, 1 = batched affine additions with
+ * simultaneous inversion, 2 = automatic (default: batched affine where it measured faster - large G2/Fq2 MSMs).
+ * Same results bit for bit; the environment variable B200_BATCH_AFFINE=0|1|2 sets the initial mode. */
 int b200_msm_set_batch_affine(int on);
 
 /* ---- O(1) group / field helpers on HOST buffers (serial tail of the prover) --------------------------------- */
@@ -122,6 +123,16 @@ int b200_set_precompute(int on);
  * pre-shifted base table when precomputation is enabled and n is the query's length. Result: projective, host memory.
  * B::multiexp_G1 / B::multiexp_G2 on vectors obtained from B::params_* bind to this. */
 int b200_params_msm(b200_params *p, int which, const void *d_scalars, size_t n, void *h_out_proj);
+/* The same MSM, asynchronously: returns as soon as the GPU work is enqueued (each outstanding call takes the next of
+ * five workspaces / streams, so consecutive calls overlap on the device like the five MSMs of b200_prove);
+ * b200_msm_wait blocks until h_out_proj - which must stay valid until then - holds the result, and frees the handle.
+ * This is what lets the reference's UNMODIFIED driver (cuda_prover_piecewise.cu:71-81 issues its five multiexps back
+ * to back and first looks at a result at :85-87) overlap them: B::multiexp_* return a pending point that is resolved
+ * when B::G1_scale / G1_add / groth16_output_write first read it. */
+typedef struct b200_msm_pending b200_msm_pending;
+int b200_params_msm_async(b200_params *p, int which, const void *d_scalars, size_t n, void *h_out_proj,
+                          b200_msm_pending **out);
+int b200_msm_wait(b200_msm_pending *pending);
 size_t b200_params_d(const b200_params *p);
 size_t b200_params_m(const b200_params *p);
 const void *b200_params_query(const b200_params *p, int which); /* 0 A, 1 B1, 2 B2, 3 L, 4 H (device pointers) */
@@ -175,7 +186,7 @@ int b200_gen_points(int curve, int group, void *d_out_affine, size_t n, uint64_t
  * runs, ms[2] = that clock in MHz; [3] = the generated Montgomery multiplication itself in a register-resident loop
  * (the production instruction mix at the accumulation kernels' occupancy) and its run time. Arrays of 4. */
 int b200_imad_peak(double *mac32_per_s, double *ms);
-/* 1 when bucket accumulation currently uses batched affine additions, 0 for XYZZ mixed additions */
+/* the current mode (0, 1 or 2, see b200_msm_set_batch_affine) */
 int b200_msm_get_batch_affine(void);
 /* number of CUDA kernels this library has launched so far (bench.py: gpu_launches) */
 unsigned long long b200_launch_count(void);

@@ -115,6 +115,8 @@ _SIGNATURES = {
     "b200_params_precompute_ms": (ctypes.c_double, [_vp]),
     "b200_set_precompute": (_i, [_i]),
     "b200_params_msm": (_i, [_vp, _i, _vp, _sz, _vp]),
+    "b200_params_msm_async": (_i, [_vp, _i, _vp, _sz, _vp, ctypes.POINTER(_vp)]),
+    "b200_msm_wait": (_i, [_vp]),
     "b200_params_d": (_sz, [_vp]),
     "b200_params_m": (_sz, [_vp]),
     "b200_params_query": (_vp, [_vp, _i]),
@@ -427,17 +429,18 @@ def prove_timeline(begin=False):
     return {name: [round(out[i * 3 + k], 2) for k in range(3)] for i, name in enumerate(("B2", "A", "B1", "L", "H"))}
 
 
-def set_batch_affine(on):
-    """Select the bucket accumulation of the MSMs: batched affine additions (True) or XYZZ mixed additions."""
-    check(lib().b200_msm_set_batch_affine(1 if on else 0))
+def set_batch_affine(mode):
+    """Select the bucket accumulation of the MSMs: 0 / False XYZZ mixed additions, 1 / True batched affine additions,
+    2 automatic (the library's default)."""
+    check(lib().b200_msm_set_batch_affine(int(mode)))
 
 
 def set_precompute(on):
     check(lib().b200_set_precompute(1 if on else 0))
 
 
-def batch_affine_enabled():
-    return bool(lib().b200_msm_get_batch_affine())
+def batch_affine_mode():
+    return {0: "xyzz", 1: "affine", 2: "auto"}[lib().b200_msm_get_batch_affine()]
 
 
 def imad_peak():

@@ -345,7 +345,7 @@ int b200_msm_set_batch_affine(int on) {
   msm_set_batch_affine(on);
   return 0;
 }
-int b200_msm_get_batch_affine(void) { return msm_use_batch_affine() ? 1 : 0; }
+int b200_msm_get_batch_affine(void) { return msm_accum_mode(); }
 int b200_msm_set_window(int c) {
   msm_set_window(c);
   return 0;
@@ -655,6 +655,42 @@ int b200_params_msm(b200_params *p, int which, const void *d_scalars, size_t n, 
     return 0;
   }
   return msm_dispatch(p->curve, group, d_scalars, p->q[which], n, h_out);
+}
+
+struct b200_msm_pending {
+  MsmTail tail;
+};
+int b200_params_msm_async(b200_params *p, int which, const void *d_scalars, size_t n, void *h_out, b200_msm_pending **out) {
+  B200_CHECK(require_device());
+  if (which < 0 || which > 4) return set_error(-1, "bad query index %d", which);
+  const size_t ns[5] = {p->m + 1, p->m + 1, p->m + 1, p->m - 1, p->d};  // A, B1, B2, L, H
+  const int job_of_query[5] = {0, 1, 2, 4, 3};
+  const int group = which == 2 ? 2 : 1;
+  static thread_local int next_slot = 0;  // round robin over the calling thread's five workspaces
+  msm_select_slot(next_slot);
+  next_slot = (next_slot + 1) % kMsmSlots;
+  std::unique_ptr<b200_msm_pending> h(new b200_msm_pending());
+  int rc;
+  if (use_precompute() && n == ns[which]) {
+    B200_CHECK(b200_params_precompute(p, 0, 1));
+    const int j = job_of_query[which];
+    rc = msm_table_dispatch_deferred(p->curve, group, d_scalars, p->pre.table[j].p, n, p->pre.plan[j], h_out, h->tail, -1,
+                                     &p->pre.dedup[j]);
+  } else {
+    rc = msm_dispatch_deferred(p->curve, group, d_scalars, p->q[which], n, h_out, h->tail);
+  }
+  msm_select_slot(0);
+  if (rc) return rc;
+  *out = h.release();
+  return 0;
+}
+int b200_msm_wait(b200_msm_pending *pending) {
+  if (!pending) return 0;
+  std::unique_ptr<b200_msm_pending> h(pending);
+  std::string err;
+  const int rc = h->tail(err);
+  if (rc) return set_error(rc, "%s", err.c_str());
+  return 0;
 }
 
 // Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like

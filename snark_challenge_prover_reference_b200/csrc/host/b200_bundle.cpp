@@ -79,7 +79,23 @@ BUNDLE void B::init_public_params() {
   B200_OK(b200_set_device(dev ? atoi(dev) : 0));
 }
 
+BUNDLE void B::G1::resolve() {
+  if (pending) {
+    b200_msm_pending *h = (b200_msm_pending *)pending;
+    pending = nullptr;
+    B200_OK(b200_msm_wait(h));
+  }
+}
+BUNDLE void B::G2::resolve() {
+  if (pending) {
+    b200_msm_pending *h = (b200_msm_pending *)pending;
+    pending = nullptr;
+    B200_OK(b200_msm_wait(h));
+  }
+}
+
 BUNDLE void B::print_G1(G1 *a) {
+  a->resolve();
   unsigned char xy[2 * 96];
   B200_OK(b200_g1_to_affine(CURVE, a->bytes, xy));
   printf("(");
@@ -87,6 +103,7 @@ BUNDLE void B::print_G1(G1 *a) {
   printf(")  [affine, Montgomery limbs]\n");
 }
 BUNDLE void B::print_G2(G2 *a) {
+  a->resolve();
   const size_t deg = CURVE == 0 ? 2 : 3;
   std::vector<unsigned char> xy(2 * deg * 96);
   B200_OK(b200_g2_to_affine(CURVE, a->bytes, xy.data()));
@@ -102,11 +119,14 @@ BUNDLE typename B::evaluation_domain *B::get_evaluation_domain(size_t d) {
 }
 
 BUNDLE typename B::G1 *B::G1_add(G1 *a, G1 *b) {
+  a->resolve();
+  b->resolve();
   G1 *r = new G1();
   B200_OK(b200_g1_add(CURVE, a->bytes, b->bytes, r->bytes));
   return r;
 }
 BUNDLE typename B::G1 *B::G1_scale(field *a, G1 *b) {
+  b->resolve();
   G1 *r = new G1();
   B200_OK(b200_g1_scale(CURVE, a->bytes, b->bytes, r->bytes));
   return r;
@@ -148,13 +168,16 @@ BUNDLE size_t B::domain_get_m(evaluation_domain *domain) { return b200_domain_si
 
 BUNDLE typename B::G1 *B::multiexp_G1(vector_Fr *scalar_start, vector_G1 *g_start, size_t length) {
   G1 *r = new G1();
-  // goes through the key so that the pre-shifted base table is used when `length` is the whole query
-  B200_OK(b200_params_msm(g_start->owner->h, g_start->query, scalar_start->data->at(scalar_start->offset), length, r->bytes));
+  // goes through the key so that the pre-shifted base table is used when `length` is the whole query; asynchronous: the
+  // result is pending until first read
+  B200_OK(b200_params_msm_async(g_start->owner->h, g_start->query, scalar_start->data->at(scalar_start->offset), length,
+                                r->bytes, (b200_msm_pending **)&r->pending));
   return r;
 }
 BUNDLE typename B::G2 *B::multiexp_G2(vector_Fr *scalar_start, vector_G2 *g_start, size_t length) {
   G2 *r = new G2();
-  B200_OK(b200_params_msm(g_start->owner->h, g_start->query, scalar_start->data->at(scalar_start->offset), length, r->bytes));
+  B200_OK(b200_params_msm_async(g_start->owner->h, g_start->query, scalar_start->data->at(scalar_start->offset), length,
+                                r->bytes, (b200_msm_pending **)&r->pending));
   return r;
 }
 
@@ -233,6 +256,9 @@ BUNDLE void B::delete_evaluation_domain(evaluation_domain *a) { delete a; }
 
 BUNDLE void B::groth16_output_write(G1 *A, G2 *Bp, G1 *C, const char *output_path) {
   // A (G1) | B (G2) | C (G1), affine, O -> zero bytes  (main.cpp:94-100, serialization.hpp:43-67)
+  A->resolve();
+  Bp->resolve();
+  C->resolve();
   const size_t deg = CURVE == 0 ? 2 : 3;
   std::vector<unsigned char> out(2 * 96 + 2 * deg * 96 + 2 * 96);
   B200_OK(b200_g1_to_affine(CURVE, A->bytes, out.data()));

@@ -40,11 +40,20 @@ public:
   struct field {
     unsigned char bytes[96];  // Fr, Montgomery form
   };
+  // Group elements live in host memory. One returned by multiexp_* may still be PENDING: the GPU work is enqueued, the
+  // bytes arrive when the element is first read (resolve()), so the reference's driver - which issues its five
+  // multiexps back to back (cuda_prover_piecewise.cu:71-81) - overlaps them without being changed.
   struct G1 {
-    unsigned char bytes[3 * 96];  // projective (X:Y:Z) over Fq, host memory
+    unsigned char bytes[3 * 96];  // projective (X:Y:Z) over Fq
+    void *pending = nullptr;      // b200_msm_pending*
+    void resolve();
+    ~G1() { resolve(); }
   };
   struct G2 {
     unsigned char bytes[3 * 96 * (CURVE == 0 ? 2 : 3)];  // projective over Fq2 / Fq3
+    void *pending = nullptr;
+    void resolve();
+    ~G2() { resolve(); }
   };
   struct evaluation_domain {
     std::shared_ptr<b200_host::domain_box> box;

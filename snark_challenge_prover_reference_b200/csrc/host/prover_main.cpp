@@ -57,24 +57,25 @@ static int prove(const char *params_path, const char *input_path, const char *ou
   typename B::vector_G2 *qB2 = B::params_B2(params);
   t = clk::now();
   typename B::G1 *At = B::multiexp_G1(w, qA, m + 1);
-  printf("A G1 multiexp: %.1f ms\n", since_ms(t));
+  printf("A G1 multiexp issued: %.1f ms\n", since_ms(t));
   t = clk::now();
   typename B::G1 *Bt1 = B::multiexp_G1(w, qB1, m + 1);
-  printf("B G1 multiexp: %.1f ms\n", since_ms(t));
+  printf("B G1 multiexp issued: %.1f ms\n", since_ms(t));
   t = clk::now();
   typename B::G2 *Bt2 = B::multiexp_G2(w, qB2, m + 1);
-  printf("B G2 multiexp: %.1f ms\n", since_ms(t));
+  printf("B G2 multiexp issued: %.1f ms\n", since_ms(t));
   t = clk::now();
   typename B::G1 *Ht = B::multiexp_G1(h, qH, d);
-  printf("H G1 multiexp: %.1f ms\n", since_ms(t));
+  printf("H G1 multiexp issued: %.1f ms\n", since_ms(t));
   t = clk::now();
   typename B::G1 *Lt = B::multiexp_G1(w2, qL, m - 1);
-  printf("L G1 multiexp: %.1f ms\n", since_ms(t));
+  printf("L G1 multiexp issued: %.1f ms\n", since_ms(t));
 
   typename B::field *r = B::input_r(input);
   typename B::G1 *rB = B::G1_scale(r, Bt1);
   typename B::G1 *LrB = B::G1_add(Lt, rB);
   typename B::G1 *C = B::G1_add(Ht, LrB);
+  // (the five multiexps above are asynchronous: their results are first read by G1_scale / G1_add / the writer)
   B::groth16_output_write(At, Bt2, C, output_path);
   printf("Total time from input to output: : %.0f ms\n", since_ms(t_main));
 

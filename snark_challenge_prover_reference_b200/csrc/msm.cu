@@ -31,14 +31,26 @@ std::atomic<double> g_msm_phase_total[2][5];
 static std::atomic<int> g_forced_window{0};
 // B200_BATCH_AFFINE=1: bucket accumulation by rounds of batched affine additions (experimental, see msm_group.cuh)
 static std::atomic<int> g_batch_affine{-1};  // -1: take B200_BATCH_AFFINE from the environment on first use
-bool msm_use_batch_affine() {
+// 0 = XYZZ mixed additions, 1 = batched affine additions, 2 = automatic (default): batched affine where it is the faster
+// one on this hardware - see msm_affine_wins()
+int msm_accum_mode() {
   if (g_batch_affine < 0) {
     const char *e = getenv("B200_BATCH_AFFINE");
-    g_batch_affine = (e && e[0] == '1') ? 1 : 0;
+    g_batch_affine = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }
-  return g_batch_affine == 1;
+  return g_batch_affine;
 }
-void msm_set_batch_affine(int on) { g_batch_affine = on ? 1 : 0; }
+bool msm_use_batch_affine() { return msm_accum_mode() == 1; }
+void msm_set_batch_affine(int on) { g_batch_affine = on < 0 || on > 2 ? 2 : on; }
+// Measured on B200 (profiles/r02_summary.md): the batch-affine rounds beat the XYZZ kernel for G2 over Fq2 once a bucket
+// set holds millions of entries (2^20 points: 145 vs 157 ms); for G1 the two are within 1 %, and for small MSMs the
+// ~7 dependent rounds (one inversion latency each) lose to the single XYZZ launch (2^15 points: 9.3 vs 2.8 ms).
+bool msm_affine_wins(int degree, size_t entries) { return degree == 2 && entries >= ((size_t)8 << 20); }
+// B200_AFF_SPLIT=0: every batch-affine round as ONE region of equal per-thread batches (for A/B timing of the tail fill)
+bool msm_affine_split_tail() {
+  static const bool on = !(getenv("B200_AFF_SPLIT") && getenv("B200_AFF_SPLIT")[0] == '0');
+  return on;
+}
 void msm_set_window(int c) { g_forced_window = c; }
 void msm_phase_totals(double *out10, int reset) {
   for (int g = 0; g < 2; g++)

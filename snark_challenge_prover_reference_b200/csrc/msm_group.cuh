@@ -44,8 +44,13 @@ __device__ __forceinline__ void store_streaming(T *dst, const T &src) {
 }
 
 // One thread sums one task (a piece of <= T entries of one bucket's list) by mixed addition.
+// (G2 over Fq3: 2 blocks per SM cost nothing - the kernel needs 255 registers either way - and double the warps that
+// hide each other's latency; round 1 ran it at 1.)
+#ifndef B200_ACC_BLOCKS_FQ3
+#define B200_ACC_BLOCKS_FQ3 2
+#endif
 template <class G>
-__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : (G::F::kDegree == 2 ? 4 : 1)) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
+__global__ void __launch_bounds__(128, G::F::kDegree == 3 ? B200_ACC_BLOCKS_FQ3 : 4) msm_accumulate_kernel(const Affine<typename G::F> *__restrict__ points,
                                                              const uint32_t *__restrict__ entries,
                                                              const uint32_t *__restrict__ offsets,
                                                              const uint32_t *__restrict__ task_off,
@@ -147,6 +152,25 @@ __global__ void __launch_bounds__(128) msm_combine_kernel(const Proj<typename G:
 #define B200_AFF_MIN_M 32
 #endif
 constexpr uint32_t kAffNone = 0xffffffffu;
+// A round's outputs are cut into up to three REGIONS handled by consecutive block ranges of one launch. Inside a
+// region thread t takes outputs first + t, first + t + S, ... The first region is one full wave of resident threads
+// with most of the outputs (long per-thread batches: the shared inversion is amortised over ~200 additions); the
+// following, much shorter regions are scheduled as the first one's blocks retire and fill the tail that a single
+// wave of equal batches leaves on a 148-SM chip (measured: 13.4 of 16 warps resident on average, 16 % of the pipe lost).
+struct AffRegions {
+  uint32_t first[3], count[3], stride[3], block0[3];  // block0: first block of the region
+  int n;
+};
+__device__ __forceinline__ bool aff_my_region(const AffRegions &rg, uint32_t &first, uint32_t &count, uint32_t &S, uint32_t &t) {
+  int r = 0;
+  if (rg.n > 1 && blockIdx.x >= rg.block0[1]) r = 1;
+  if (rg.n > 2 && blockIdx.x >= rg.block0[2]) r = 2;
+  first = rg.first[r];
+  count = rg.count[r];
+  S = rg.stride[r];
+  t = (blockIdx.x - rg.block0[r]) * blockDim.x + threadIdx.x;
+  return t < S && t < count;
+}
 
 // One operand of an addition: index of the stored point (table entry or previous round's output), `neg` says the
 // operand is its negative (first round: negative digit), `inf` that it is O.
@@ -188,11 +212,15 @@ __device__ __forceinline__ int aff_classify(const Affine<F> *src, const AffOpera
 template <class G>
 __global__ void __launch_bounds__(128, B200_AFF_BLOCKS) msm_affine_round_kernel(
     const Affine<typename G::F> *__restrict__ src, const uint8_t *__restrict__ oflag_in, const uint2 *__restrict__ pairs,
-    uint32_t total_out, uint32_t S, Affine<typename G::F> *__restrict__ pts_out, uint8_t *__restrict__ oflag_out,
+    AffRegions rg, Affine<typename G::F> *__restrict__ pts_out, uint8_t *__restrict__ oflag_out,
     typename G::F *__restrict__ pre) {
   typedef typename G::F F;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= S || t >= total_out) return;
+  uint32_t first, total_out, S, t;
+  if (!aff_my_region(rg, first, total_out, S, t)) return;
+  pairs += first;
+  pts_out += first;
+  oflag_out += first;
+  pre += first;
   // the field elements on the stack; inv holds the running product first; p1 / p2 are the operands of the current output
   F inv, den, lam, num;
   Affine<F> p1, p2;
@@ -313,13 +341,17 @@ constexpr size_t kAffG1Smem = 3 * 128 * kAffSlotStride;
 template <class G>
 __global__ void __launch_bounds__(128, B200_AFF_G1_BLOCKS) msm_affine_round_g1_kernel(
     const Affine<typename G::F> *__restrict__ src, const uint8_t *__restrict__ oflag_in, const uint2 *__restrict__ pairs,
-    uint32_t total_out, uint32_t S, Affine<typename G::F> *__restrict__ pts_out, uint8_t *__restrict__ oflag_out,
+    AffRegions rg, Affine<typename G::F> *__restrict__ pts_out, uint8_t *__restrict__ oflag_out,
     typename G::F *__restrict__ pre) {
   typedef typename G::F F;
   static_assert(F::kDegree == 1, "base-field groups only");
   extern __shared__ uint4 aff_smem[];
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= S || t >= total_out) return;
+  uint32_t first, total_out, S, t;
+  if (!aff_my_region(rg, first, total_out, S, t)) return;
+  pairs += first;
+  pts_out += first;
+  oflag_out += first;
+  pre += first;
   char *sm = reinterpret_cast<char *>(aff_smem);
   F &inv = *reinterpret_cast<F *>(sm + (0 * 128 + threadIdx.x) * kAffSlotStride);
   F &A = *reinterpret_cast<F *>(sm + (1 * 128 + threadIdx.x) * kAffSlotStride);
@@ -578,7 +610,7 @@ int msm_accumulate_xyzz(const void *d_points, const MsmPlan &plan, MsmWorkspace 
 template <class G, int DEG = G::F::kDegree>
 struct AffineRound {
   typedef typename G::F F;
-  typedef void (*Kernel)(const Affine<F> *, const uint8_t *, const uint2 *, uint32_t, uint32_t, Affine<F> *, uint8_t *, F *);
+  typedef void (*Kernel)(const Affine<F> *, const uint8_t *, const uint2 *, AffRegions, Affine<F> *, uint8_t *, F *);
   static constexpr size_t kSmem = 0;
   static Kernel kernel() { return msm_affine_round_kernel<G>; }
 };
@@ -586,7 +618,7 @@ struct AffineRound {
 template <class G>
 struct AffineRound<G, 1> {
   typedef typename G::F F;
-  typedef void (*Kernel)(const Affine<F> *, const uint8_t *, const uint2 *, uint32_t, uint32_t, Affine<F> *, uint8_t *, F *);
+  typedef void (*Kernel)(const Affine<F> *, const uint8_t *, const uint2 *, AffRegions, Affine<F> *, uint8_t *, F *);
   static constexpr size_t kSmem = kAffG1Smem;
   static Kernel kernel() { return msm_affine_round_g1_kernel<G>; }
 };
@@ -623,18 +655,37 @@ int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmP
   for (int r = 1; r <= rounds; r++) {
     const size_t total_out = totals[r];
     if (total_out == 0) break;
-    // one wave of resident threads when the round is large; at least B200_AFF_MIN_M outputs per thread otherwise (the
-    // shared inversion costs as many instructions as ~9 additions)
-    size_t S = (size_t)wave;
-    if (total_out / S < B200_AFF_MIN_M) S = (total_out + B200_AFF_MIN_M - 1) / B200_AFF_MIN_M;
-    S = (S + 127) / 128 * 128;
+    // regions (see AffRegions): a round with >= 64 outputs per resident thread is cut 80 % / 20 %, each part one wave;
+    // smaller rounds are one region with at least B200_AFF_MIN_M outputs per thread (the shared inversion costs as
+    // many instructions as ~15 additions)
+    AffRegions rg;
+    unsigned blocks = 0;
+    auto add_region = [&](int r, size_t first, size_t count, size_t S) {
+      S = (S + 127) / 128 * 128;
+      rg.first[r] = (uint32_t)first;
+      rg.count[r] = (uint32_t)count;
+      rg.stride[r] = (uint32_t)S;
+      rg.block0[r] = blocks;
+      blocks += (unsigned)(S / 128);
+      rg.n = r + 1;
+    };
+    rg.n = 0;
+    if (msm_affine_split_tail() && total_out / (size_t)wave >= 64) {
+      const size_t nA = total_out / 5 * 4;
+      add_region(0, 0, nA, (size_t)wave);
+      add_region(1, nA, total_out - nA, (size_t)wave);
+    } else {
+      size_t S = (size_t)wave;
+      if (total_out / S < B200_AFF_MIN_M) S = (total_out + B200_AFF_MIN_M - 1) / B200_AFF_MIN_M;
+      add_region(0, 0, total_out, S);
+    }
     DevBuf &outbuf = ws.aff_pts[r & 1], &oflag = ws.aff_oflag[r & 1];
     B200_CHECK(outbuf.reserve(total_out * sizeof(Affine<F>)));
     B200_CHECK(oflag.reserve(total_out));
     B200_CHECK(ws.aff_scratch.reserve(total_out * sizeof(F)));
-    AffineRound<G>::kernel()<<<grid_for(S, 128), 128, AffineRound<G>::kSmem, st>>>(src, oflag_in, ws.aff_pairs.as<uint2>() + pair_off[r],
-                                                               (uint32_t)total_out, (uint32_t)S, outbuf.as<Affine<F>>(),
-                                                               oflag.as<uint8_t>(), ws.aff_scratch.as<F>());
+    AffineRound<G>::kernel()<<<blocks, 128, AffineRound<G>::kSmem, st>>>(src, oflag_in, ws.aff_pairs.as<uint2>() + pair_off[r], rg,
+                                                                     outbuf.as<Affine<F>>(), oflag.as<uint8_t>(),
+                                                                     ws.aff_scratch.as<F>());
     B200_CUDA_CHECK(cudaGetLastError());
     note_launch();
     src = outbuf.as<Affine<F>>();
@@ -679,7 +730,10 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   for (int i = 0; i < 4; i++) stage->prep_ev[i] = share_slot >= 0 ? nullptr : ws.tm_ev[i];
 
   // (batch-affine operand words keep bit 31 for the O flag: entry indices must stay below 2^30)
-  if (msm_use_batch_affine() && (size_t)plan.W * n < ((size_t)1 << 30)) {
+  const int accum_mode = msm_accum_mode();
+  const bool affine = (accum_mode == 1 || (accum_mode == 2 && msm_affine_wins(F::kDegree, (size_t)plan.W * n))) &&
+                      (size_t)plan.W * n < ((size_t)1 << 30);
+  if (affine) {
     B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
     B200_CHECK(msm_accumulate_batch_affine<G>(d_points, n, plan, ws, pw));
   } else {

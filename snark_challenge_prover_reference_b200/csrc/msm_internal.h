@@ -112,6 +112,9 @@ int msm_affine_pairs(MsmWorkspace &ws, const uint32_t *cnt, const uint32_t *off,
                      const std::vector<size_t> &totals, const uint32_t *entries, const uint8_t *base_is_O, size_t n_bases,
                      std::vector<size_t> &pair_off);
 bool msm_use_batch_affine();
+int msm_accum_mode();
+bool msm_affine_wins(int degree, size_t entries);
+bool msm_affine_split_tail();
 constexpr uint32_t kFoldWidth = 32;  // a bucket with more task sums than this is folded in parallel first
 int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, uint32_t *cnt_out, uint32_t *off_out,
                    size_t &total_out);

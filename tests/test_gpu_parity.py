@@ -193,7 +193,7 @@ def accum(request, b200):
     """Run the test under both bucket-accumulation modes of the MSM (the results must be identical bit for bit)."""
     b200.set_batch_affine(request.param)
     yield request.param
-    b200.set_batch_affine(0)
+    b200.set_batch_affine(2)  # the library's default: automatic
 
 
 @pytest.mark.parametrize("curve", [0, 1])
