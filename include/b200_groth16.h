@@ -108,6 +108,13 @@ int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_par
  * (zeros for keys that were not loaded from a file). */
 int b200_params_from_file(int curve, const char *path, b200_params **out);
 int b200_params_load_ms(const b200_params *p, double *out3);
+/* The same chunked pinned-read + asynchronous copy for any byte range of a file: d_dst[0, bytes) = file[offset, +bytes).
+ * B::read_input binds to it (libsnark/main.cpp:63-83 reads the witness element by element). */
+int b200_file_to_device(const char *path, size_t file_offset, void *d_dst, size_t bytes);
+/* The evaluation domain of size d+1 that every key owns (built when the key is loaded, i.e. outside the reference's
+ * timed region). Borrowed: valid until b200_params_destroy. B::get_evaluation_domain hands it out when the size matches,
+ * so the driver's witness map does not rebuild the twiddle tables inside the timed region. */
+b200_domain *b200_params_domain(const b200_params *p);
 /* adopt caller-owned device arrays (synthetic keys built on the device) */
 int b200_params_from_device(int curve, size_t d, size_t m, const void *d_A, const void *d_B1, const void *d_B2,
                             const void *d_L, const void *d_H, b200_params **out);

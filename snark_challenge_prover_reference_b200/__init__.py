@@ -109,6 +109,8 @@ _SIGNATURES = {
     "b200_params_from_host": (_i, [_i, _vp, _sz, ctypes.POINTER(_vp)]),
     "b200_params_from_file": (_i, [_i, ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "b200_params_load_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_double)]),
+    "b200_file_to_device": (_i, [ctypes.c_char_p, _sz, _vp, _sz]),
+    "b200_params_domain": (_vp, [_vp]),
     "b200_params_from_device": (_i, [_i, _sz, _sz, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     "b200_params_destroy": (_i, [_vp]),
     "b200_params_precompute": (_i, [_vp, _i, _i]),

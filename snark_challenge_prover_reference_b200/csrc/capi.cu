@@ -149,6 +149,11 @@ struct b200_params {
   Precomputed pre;
 };
 
+// B200_SHARE_PREP=0: every MSM of a proof extracts and sorts its own digits (A/B timing and tests of the sharing)
+static bool share_prep_enabled() {
+  static const bool on = !(getenv("B200_SHARE_PREP") && getenv("B200_SHARE_PREP")[0] == '0');
+  return on;
+}
 static std::atomic<int> g_use_precompute{-1};  // -1: read B200_PRECOMPUTE from the environment (default on)
 static bool use_precompute() {
   if (g_use_precompute < 0) {
@@ -486,6 +491,63 @@ int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_par
   *out = p;
   return 0;
 }
+// file (positioned at the first byte to copy) -> device, `bytes` bytes: two pinned staging buffers, chunk k's
+// host->device copy runs while chunk k+1 is being read
+static int stream_file_to_device(FILE *f, const char *path, void *d_dst, size_t bytes, double &read_ms, double &wait_ms) {
+  constexpr size_t kChunk = (size_t)64 << 20;
+  struct Stage {
+    void *h = nullptr;
+    cudaEvent_t done = nullptr;
+    ~Stage() {
+      if (h) cudaFreeHost(h);
+      if (done) cudaEventDestroy(done);
+    }
+  } stage[2];
+  cudaStream_t copy_stream = nullptr;
+  B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  struct StreamCloser {
+    cudaStream_t s;
+    ~StreamCloser() { cudaStreamDestroy(s); }
+  } sc{copy_stream};
+  const size_t chunk = bytes < kChunk ? (bytes ? bytes : 16) : kChunk;
+  for (int i = 0; i < 2; i++) {
+    B200_CUDA_CHECK(cudaMallocHost(&stage[i].h, chunk));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&stage[i].done, cudaEventDisableTiming));
+  }
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += chunk, k ^= 1) {
+    const size_t n = bytes - off < chunk ? bytes - off : chunk;
+    double a = now_ms();
+    B200_CUDA_CHECK(cudaEventSynchronize(stage[k].done));  // the copy that last used this buffer (no-op the first time)
+    double b = now_ms();
+    if (fread(stage[k].h, 1, n, f) != n) return set_error(-4, "short read on %s", path);
+    double c = now_ms();
+    wait_ms += b - a;
+    read_ms += c - b;
+    B200_CUDA_CHECK(cudaMemcpyAsync((char *)d_dst + off, stage[k].h, n, cudaMemcpyHostToDevice, copy_stream));
+    B200_CUDA_CHECK(cudaEventRecord(stage[k].done, copy_stream));
+  }
+  double a = now_ms();
+  B200_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+  wait_ms += now_ms() - a;
+  return 0;
+}
+
+int b200_file_to_device(const char *path, size_t file_offset, void *d_dst, size_t bytes) {
+  B200_CHECK(require_device());
+  FILE *f = fopen(path, "rb");
+  if (!f) return set_error(-4, "cannot open %s", path);
+  struct Closer {
+    FILE *f;
+    ~Closer() { fclose(f); }
+  } closer{f};
+  if (fseek(f, (long)file_offset, SEEK_SET) != 0) return set_error(-4, "cannot seek in %s", path);
+  double r = 0, w = 0;
+  return stream_file_to_device(f, path, d_dst, bytes, r, w);
+}
+
+b200_domain *b200_params_domain(const b200_params *p) { return p ? p->dom : nullptr; }
+
 int b200_params_from_file(int curve, const char *path, b200_params **out) {
   B200_CHECK(require_device());
   if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
@@ -513,46 +575,8 @@ int b200_params_from_file(int curve, const char *path, b200_params **out) {
   p->m = m;
   p->dom = nullptr;
   B200_CHECK(p->owned.alloc(body));
-  // two pinned staging buffers; chunk k's copy runs while chunk k+1 is being read
-  constexpr size_t kChunk = (size_t)64 << 20;
-  struct Stage {
-    void *h = nullptr;
-    cudaEvent_t done = nullptr;
-    ~Stage() {
-      if (h) cudaFreeHost(h);
-      if (done) cudaEventDestroy(done);
-    }
-  } stage[2];
-  cudaStream_t copy_stream = nullptr;
-  B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-  struct StreamCloser {
-    cudaStream_t s;
-    ~StreamCloser() { cudaStreamDestroy(s); }
-  } sc{copy_stream};
-  const size_t chunk = body < kChunk ? (body ? body : 16) : kChunk;
-  for (int i = 0; i < 2; i++) {
-    B200_CUDA_CHECK(cudaMallocHost(&stage[i].h, chunk));
-    B200_CUDA_CHECK(cudaEventCreateWithFlags(&stage[i].done, cudaEventDisableTiming));
-  }
   double read_ms = 0, wait_ms = 0;
-  int k = 0;
-  for (size_t off = 0; off < body; off += chunk, k ^= 1) {
-    const size_t n = body - off < chunk ? body - off : chunk;
-    double a = now_ms();
-    B200_CUDA_CHECK(cudaEventSynchronize(stage[k].done));  // the copy that last used this buffer (no-op the first time)
-    double b = now_ms();
-    if (fread(stage[k].h, 1, n, f) != n) return set_error(-4, "short read on %s", path);
-    double c = now_ms();
-    wait_ms += b - a;
-    read_ms += c - b;
-    B200_CUDA_CHECK(cudaMemcpyAsync((char *)p->owned.p + off, stage[k].h, n, cudaMemcpyHostToDevice, copy_stream));
-    B200_CUDA_CHECK(cudaEventRecord(stage[k].done, copy_stream));
-  }
-  {
-    double a = now_ms();
-    B200_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
-    wait_ms += now_ms() - a;
-  }
+  B200_CHECK(stream_file_to_device(f, path, p->owned.p, body, read_ms, wait_ms));
   params_set_queries(p.get());
   int rc = params_finish(p.get());
   if (rc) {
@@ -601,6 +625,31 @@ size_t b200_params_d(const b200_params *p) { return p->d; }
 size_t b200_params_m(const b200_params *p) { return p->m; }
 const void *b200_params_query(const b200_params *p, int which) { return (which >= 0 && which < 5) ? p->q[which] : nullptr; }
 
+// Slice [lo, hi) of query qi (0 A, 1 B1, 2 B2, 3 L, 4 H) that rank `rank` of `world` sums: contiguous ranges like
+// multi_exp's chunks (multiexp.tcc:417-431; the last rank takes the remainder). The four w-driven queries are cut so
+// that a rank's scalars are ONE range of w - A / B1 / B2 take points [lo1, hi1) of m+1, and L, whose point i belongs to
+// w[i + 2] (main.cpp:247-250), takes points [lo1 - 2, hi1 - 2) clipped to [0, m-1) - so the four MSMs of a rank share
+// one digit extraction and one counting sort at every world size.
+static void query_slice(size_t d, size_t m, int qi, int rank, int world, size_t &lo, size_t &hi) {
+  if (qi == 4) {
+    const size_t one = d / (size_t)world;
+    lo = (size_t)rank * one;
+    hi = rank == world - 1 ? d : lo + one;
+    return;
+  }
+  const size_t n1 = m + 1, one = n1 / (size_t)world;
+  const size_t lo1 = (size_t)rank * one, hi1 = rank == world - 1 ? n1 : lo1 + one;
+  if (qi != 3) {
+    lo = lo1;
+    hi = hi1;
+    return;
+  }
+  lo = lo1 >= 2 ? lo1 - 2 : 0;
+  hi = hi1 >= 2 ? hi1 - 2 : 0;
+  if (hi > m - 1) hi = m - 1;
+  if (lo > hi) lo = hi;
+}
+
 // Build (once per key and slicing) the tables of pre-shifted bases for this rank's slice of the five queries.
 int b200_params_precompute(b200_params *p, int rank, int world) {
   B200_CHECK(require_device());
@@ -608,14 +657,13 @@ int b200_params_precompute(b200_params *p, int rank, int world) {
   if (p->pre.rank == rank && p->pre.world == world) return 0;
   double t0 = now_ms();
   const size_t d = p->d, m = p->m;
-  const size_t ns[5] = {m + 1, m + 1, m + 1, m - 1, d};   // A, B1, B2, L, H (order of p->q)
   const int jobq[5] = {0, 1, 2, 4, 3};                     // job order A, B1, B2, H, L -> query index
   p->pre.rank = p->pre.world = -1;
   for (int j = 0; j < 5; j++) {
     const int qi = jobq[j];
     const int group = qi == 2 ? 2 : 1;
-    const size_t n = ns[qi], one = n / (size_t)world;
-    const size_t lo = (size_t)rank * one, hi = (rank == world - 1) ? n : lo + one;
+    size_t lo, hi;
+    query_slice(d, m, qi, rank, world, lo, hi);
     const char *pts = (const char *)p->q[qi] + lo * affine_bytes(p->curve, group);
     p->pre.plan[j] = MsmPlan();
     if (hi > lo) B200_CHECK(msm_precompute_dispatch(p->curve, group, pts, hi - lo, p->pre.plan[j], p->pre.table[j]));
@@ -648,7 +696,7 @@ int b200_params_msm(b200_params *p, int which, const void *d_scalars, size_t n, 
     MsmTail tail;
     msm_select_slot(0);
     B200_CHECK(msm_table_dispatch_deferred(p->curve, group, d_scalars, p->pre.table[j].p, n, p->pre.plan[j], h_out, tail,
-                                           -1, &p->pre.dedup[j]));
+                                           MsmShare(), &p->pre.dedup[j]));
     std::string err;
     const int rc = tail(err);
     if (rc) return set_error(rc, "%s", err.c_str());
@@ -674,7 +722,7 @@ int b200_params_msm_async(b200_params *p, int which, const void *d_scalars, size
   if (use_precompute() && n == ns[which]) {
     B200_CHECK(b200_params_precompute(p, 0, 1));
     const int j = job_of_query[which];
-    rc = msm_table_dispatch_deferred(p->curve, group, d_scalars, p->pre.table[j].p, n, p->pre.plan[j], h_out, h->tail, -1,
+    rc = msm_table_dispatch_deferred(p->curve, group, d_scalars, p->pre.table[j].p, n, p->pre.plan[j], h_out, h->tail, MsmShare(),
                                      &p->pre.dedup[j]);
   } else {
     rc = msm_dispatch_deferred(p->curve, group, d_scalars, p->q[which], n, h_out, h->tail);
@@ -707,10 +755,8 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   // compute_H, under the MSMs that are already running (truly asynchronous when the image is in pinned memory)
   // (a rank of a sharded proof only needs the part of w its slices of A/B1/B2 (w[i]) and L (w[i+2]) read)
   {
-    const size_t n1 = m + 1, n3 = m - 1, one1 = n1 / (size_t)world, one3 = n3 / (size_t)world;
-    const size_t lo1 = (size_t)rank * one1, hi1 = rank == world - 1 ? n1 : lo1 + one1;
-    const size_t lo3 = (size_t)rank * one3 + 2, hi3 = (rank == world - 1 ? n3 : (size_t)rank * one3 + one3) + 2;
-    const size_t lo = std::min(lo1, lo3), hi = std::max(hi1, hi3);
+    size_t lo, hi;
+    query_slice(d, m, 0, rank, world, lo, hi);  // covers L's scalars w[lo3 + 2 .. hi3 + 2) too (query_slice)
     B200_CUDA_CHECK(cudaMemcpy((char *)p->w.p + lo * 96, in + lo * 96, (hi - lo) * 96, cudaMemcpyDefault));
   }
   double t1 = now_ms();
@@ -756,16 +802,29 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     }
     unsigned char *o = partials + outoff[j];
     const Job &J = jobs[j];
-    size_t one = J.n / (size_t)world;
-    size_t lo = (size_t)rank * one, hi = (rank == world - 1) ? J.n : lo + one;
+    const int jobq[5] = {0, 1, 2, 4, 3};  // job -> query index
+    size_t lo, hi;
+    query_slice(d, m, jobq[j], rank, world, lo, hi);
     double a = now_ms();
     MsmTail tail;
     msm_select_slot(jj);
     // A and B1 (slots 1, 2) run over the same scalars and window plan as B2 (slot 0): they reuse its digits, counting
     // sort and task list
     // (not when this query's equal bases are merged: its scalars then differ from w)
+    // L (slot 3) does too: its points are the same scalars shifted by 2 (main.cpp:247-250), so B2's entry list is
+    // re-indexed for it instead of being rebuilt (MsmShare)
     const bool merges = use_precompute() && p->pre.dedup[j].merged > 0;
-    const int share = (jj == 1 || jj == 2) && !merges && p->pre.plan[j].c == p->pre.plan[2].c ? 0 : -1;
+    MsmShare share;
+    if (use_precompute() && !merges && hi > lo && p->pre.plan[j].c == p->pre.plan[2].c && share_prep_enabled()) {
+      size_t lo1, hi1;
+      query_slice(d, m, 2, rank, world, lo1, hi1);
+      if (jj == 1 || jj == 2) share.slot = 0;
+      if (jj == 3 && hi1 > lo1) {
+        share.slot = 0;
+        share.n_src = (uint32_t)(hi1 - lo1);
+        share.shift = (uint32_t)(lo + 2 - lo1);
+      }
+    }
     if (use_precompute())
       rc_all = msm_table_dispatch_deferred(curve, J.group, J.scalars + lo * 96, p->pre.table[j].p, hi - lo,
                                            p->pre.plan[j], o, tail, share, &p->pre.dedup[j]);

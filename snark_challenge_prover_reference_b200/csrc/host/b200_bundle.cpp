@@ -1,4 +1,4 @@
-// `B::` over the C ABI (include/b200_groth16.h). Host code only: files are read with one bulk read each, vectors are
+// `B::` over the C ABI (include/b200_groth16.h). Host code only: files stream through pinned staging buffers, vectors are
 // handles to device memory, the O(1) group operations of the prover tail run on the host inside the library.
 // Reference counterpart: libsnark/prover_reference_functions.cpp (libff-backed, CPU).
 //
@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 
 #include "b200_groth16.h"
@@ -38,26 +39,29 @@ struct params_box {
 };
 struct domain_box {
   b200_domain *h = nullptr;
-  ~domain_box() { b200_domain_destroy(h); }
+  std::shared_ptr<params_box> borrowed_from;  // set: h is the key's own domain (b200_params_domain), not owned here
+  ~domain_box() {
+    if (!borrowed_from) b200_domain_destroy(h);
+  }
 };
-
-static std::vector<unsigned char> slurp(const char *path) {
-  FILE *f = fopen(path, "rb");
-  if (!f) {
-    fprintf(stderr, "b200 prover: cannot open %s\n", path);
-    exit(1);
-  }
-  fseek(f, 0, SEEK_END);
-  long n = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  std::vector<unsigned char> buf((size_t)n);
-  if (n > 0 && fread(buf.data(), 1, (size_t)n, f) != (size_t)n) {
-    fprintf(stderr, "b200 prover: short read on %s\n", path);
-    exit(1);
-  }
-  fclose(f);
-  return buf;
+// keys loaded by this process, by curve: B::get_evaluation_domain(d) carries no key, so the size is looked up here and
+// the key's own, already built domain is handed out (its twiddle tables were made at key-load time)
+static std::vector<std::weak_ptr<params_box>> &loaded_keys(int curve) {
+  static std::vector<std::weak_ptr<params_box>> keys[2];
+  return keys[curve];
 }
+// B200_BUNDLE_TIMING=1: print the reference prover's two timing lines (main.cpp:201,270) from inside the bundle - the
+// reference's own driver prints nothing - so that a caller of the unmodified cuda_prover_piecewise can be timed
+static bool timing_on() {
+  static const bool on = getenv("B200_BUNDLE_TIMING") && getenv("B200_BUNDLE_TIMING")[0] == '1';
+  return on;
+}
+static double now_ms() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+}
+static double g_input_t0 = 0;
 
 static void print_hex_elems(const unsigned char *p, size_t count) {
   for (size_t e = 0; e < count; e++) {
@@ -114,6 +118,14 @@ BUNDLE void B::print_G2(G2 *a) {
 
 BUNDLE typename B::evaluation_domain *B::get_evaluation_domain(size_t d) {
   auto box = std::make_shared<domain_box>();
+  for (auto &w : loaded_keys(CURVE)) {
+    std::shared_ptr<params_box> key = w.lock();
+    if (key && b200_params_d(key->h) + 1 == d) {
+      box->h = b200_params_domain(key->h);
+      box->borrowed_from = key;
+      return new evaluation_domain{box};
+    }
+  }
   B200_OK(b200_domain_create(CURVE, d, &box->h));
   return new evaluation_domain{box};
 }
@@ -184,25 +196,38 @@ BUNDLE typename B::G2 *B::multiexp_G2(vector_Fr *scalar_start, vector_G2 *g_star
 BUNDLE typename B::groth16_input *B::read_input(const char *path, groth16_params *params) {
   // file layout: w[m+1], ca[d+1], cb[d+1], cc[d+1], r  (libsnark/main.cpp:63-83)
   const size_t d = params->d, m = params->m;
-  std::vector<unsigned char> img = slurp(path);
+  g_input_t0 = now_ms();
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    fprintf(stderr, "b200 prover: cannot open %s\n", path);
+    exit(1);
+  }
+  fseek(f, 0, SEEK_END);
+  const size_t have = (size_t)ftell(f);
   const size_t need = B200_FE_BYTES * ((m + 1) + 3 * (d + 1) + 1);
-  if (img.size() != need) {
-    fprintf(stderr, "b200 prover: %s has %zu bytes, expected %zu\n", path, img.size(), need);
+  if (have != need) {
+    fprintf(stderr, "b200 prover: %s has %zu bytes, expected %zu\n", path, have, need);
     exit(1);
   }
   groth16_input *in = new groth16_input();
-  const unsigned char *p = img.data();
+  // the four vectors go from the file to HBM through pinned staging buffers, copies overlapping the reads
+  size_t off = 0;
   auto upload = [&](size_t count) {
     auto mem = std::make_shared<device_mem>(count * B200_FE_BYTES);
-    B200_OK(b200_memcpy_h2d(mem->ptr, p, count * B200_FE_BYTES));
-    p += count * B200_FE_BYTES;
+    B200_OK(b200_file_to_device(path, off, mem->ptr, count * B200_FE_BYTES));
+    off += count * B200_FE_BYTES;
     return mem;
   };
   in->w = upload(m + 1);
   in->ca = upload(d + 1);
   in->cb = upload(d + 1);
   in->cc = upload(d + 1);
-  memcpy(in->r.bytes, p, B200_FE_BYTES);
+  fseek(f, (long)off, SEEK_SET);
+  if (fread(in->r.bytes, 1, B200_FE_BYTES, f) != B200_FE_BYTES) {
+    fprintf(stderr, "b200 prover: short read on %s\n", path);
+    exit(1);
+  }
+  fclose(f);
   return in;
 }
 
@@ -213,6 +238,7 @@ BUNDLE typename B::vector_Fr *B::input_cc(groth16_input *input) { return new vec
 BUNDLE typename B::field *B::input_r(groth16_input *input) { return new field(input->r); }
 
 BUNDLE typename B::groth16_params *B::read_params(const char *path) {
+  const double t0 = now_ms();
   auto box = std::make_shared<params_box>();
   B200_OK(b200_params_from_file(CURVE, path, &box->h));  // chunked reads into pinned memory, asynchronous H2D
   // key-only preprocessing (pre-shifted base tables), part of loading the key like the reference's own parsing
@@ -224,6 +250,8 @@ BUNDLE typename B::groth16_params *B::read_params(const char *path) {
   p->d = b200_params_d(box->h);
   p->m = b200_params_m(box->h);
   p->box = box;
+  loaded_keys(CURVE).push_back(box);
+  if (timing_on()) printf("load params: %.0f ms\n", now_ms() - t0);
   return p;
 }
 BUNDLE size_t B::params_d(groth16_params *params) { return params->d; }
@@ -270,6 +298,7 @@ BUNDLE void B::groth16_output_write(G1 *A, G2 *Bp, G1 *C, const char *output_pat
     exit(1);
   }
   fclose(f);
+  if (timing_on() && g_input_t0 > 0) printf("Total time from input to output: : %.0f ms\n", now_ms() - g_input_t0);
 }
 
 template class b200_groth16_bundle<0>;

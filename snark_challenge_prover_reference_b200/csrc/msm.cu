@@ -46,9 +46,11 @@ void msm_set_batch_affine(int on) { g_batch_affine = on < 0 || on > 2 ? 2 : on; 
 // set holds millions of entries (2^20 points: 145 vs 157 ms); for G1 the two are within 1 %, and for small MSMs the
 // ~7 dependent rounds (one inversion latency each) lose to the single XYZZ launch (2^15 points: 9.3 vs 2.8 ms).
 bool msm_affine_wins(int degree, size_t entries) { return degree == 2 && entries >= ((size_t)8 << 20); }
-// B200_AFF_SPLIT=0: every batch-affine round as ONE region of equal per-thread batches (for A/B timing of the tail fill)
+// B200_AFF_SPLIT=1: cut large batch-affine rounds into an 80 % and a 20 % region (see AffRegions) to fill the tail of the
+// single wave. Measured on B200 and left off: the second region's shorter batches pay more per addition for the shared
+// inversion than the tail costs (G1 2^20: 52.9 vs 49.2 ms, G2: 149.5 vs 145.2 ms).
 bool msm_affine_split_tail() {
-  static const bool on = !(getenv("B200_AFF_SPLIT") && getenv("B200_AFF_SPLIT")[0] == '0');
+  static const bool on = getenv("B200_AFF_SPLIT") && getenv("B200_AFF_SPLIT")[0] == '1';
   return on;
 }
 void msm_set_window(int c) { g_forced_window = c; }
@@ -214,6 +216,28 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const int32_t *__restr
   uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);
   uint32_t e = merged ? (uint32_t)idx : i;
   entries[pos] = (e << 1) | (d < 0 ? 1u : 0u);
+}
+
+// re-index a producer's entry list for a consumer whose points are numbered with an offset (see MsmShare)
+__global__ void __launch_bounds__(256) msm_share_entries_kernel(const uint32_t *__restrict__ src, size_t total, uint32_t n_src,
+                                                                uint32_t n_dst, uint32_t shift, uint32_t *__restrict__ dst) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  const uint32_t e = src[k];
+  uint32_t out = kSkipEntry;
+  if (e != kSkipEntry) {
+    const uint32_t idx = e >> 1, j = idx / n_src, s = idx - j * n_src;
+    if (s >= shift && s - shift < n_dst) out = ((j * n_dst + (s - shift)) << 1) | (e & 1u);
+  }
+  dst[k] = out;
+}
+int msm_share_entries(const uint32_t *src_entries, size_t total, uint32_t n_src, uint32_t n_dst, uint32_t shift,
+                      uint32_t *dst_entries, cudaStream_t st) {
+  if (total == 0) return 0;
+  msm_share_entries_kernel<<<grid_for(total, 256), 256, 0, st>>>(src_entries, total, n_src, n_dst, shift, dst_entries);
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  return 0;
 }
 
 // ---- folding of task sums for skewed inputs (a bucket with more than kFoldWidth task sums) ----------------------
@@ -562,13 +586,13 @@ __global__ void __launch_bounds__(256) msm_affine_pairs_kernel(const uint32_t *_
   const bool second = 2 * i + 1 < c;
   uint2 pr;
   if (entries) {
-    pr.x = entries[in];
-    if (base_is_O[(pr.x >> 1) % n_bases]) pr.x |= 0x80000000u;
-    pr.y = 0xffffffffu;
-    if (second) {
-      pr.y = entries[in + 1];
-      if (base_is_O[(pr.y >> 1) % n_bases]) pr.y |= 0x80000000u;
-    }
+    // a dropped entry of a shared list (kSkipEntry) becomes an operand that is O
+    auto operand = [&](uint32_t e) -> uint32_t {
+      if (e == kSkipEntry) return 0x80000000u;
+      return base_is_O[(e >> 1) % n_bases] ? (e | 0x80000000u) : e;
+    };
+    pr.x = operand(entries[in]);
+    pr.y = second ? operand(entries[in + 1]) : 0xffffffffu;
   } else {
     pr.x = in << 1;
     pr.y = second ? (in + 1) << 1 : 0xffffffffu;
@@ -664,7 +688,7 @@ int msm_dispatch_deferred(int curve, int group, const void *d_scalars, const voi
 
 #define B200_DECL_G(name)                                                                                   \
   int msm_precompute_##name(const void *, size_t, MsmPlan &, DevBuf &);                                     \
-  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, MsmTail &, int, const MsmDedup *);
+  int msm_run_table_deferred_##name(const void *, const void *, size_t, const MsmPlan &, void *, MsmTail &, MsmShare, const MsmDedup *);
 B200_DECL_G(mnt4g1) B200_DECL_G(mnt4g2) B200_DECL_G(mnt6g1) B200_DECL_G(mnt6g2)
 #undef B200_DECL_G
 
@@ -676,12 +700,12 @@ int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
-                                const MsmPlan &plan, void *h_out, MsmTail &tail, int share_slot,
+                                const MsmPlan &plan, void *h_out, MsmTail &tail, MsmShare share,
                                 const MsmDedup *dedup) {
-  if (curve == 0 && group == 1) return msm_run_table_deferred_mnt4g1(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
-  if (curve == 0 && group == 2) return msm_run_table_deferred_mnt4g2(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
-  if (curve == 1 && group == 1) return msm_run_table_deferred_mnt6g1(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
-  if (curve == 1 && group == 2) return msm_run_table_deferred_mnt6g2(d_scalars, d_table, n, plan, h_out, tail, share_slot, dedup);
+  if (curve == 0 && group == 1) return msm_run_table_deferred_mnt4g1(d_scalars, d_table, n, plan, h_out, tail, share, dedup);
+  if (curve == 0 && group == 2) return msm_run_table_deferred_mnt4g2(d_scalars, d_table, n, plan, h_out, tail, share, dedup);
+  if (curve == 1 && group == 1) return msm_run_table_deferred_mnt6g1(d_scalars, d_table, n, plan, h_out, tail, share, dedup);
+  if (curve == 1 && group == 2) return msm_run_table_deferred_mnt6g2(d_scalars, d_table, n, plan, h_out, tail, share, dedup);
   return set_error(-1, "msm: bad curve/group %d/%d", curve, group);
 }
 

@@ -7,7 +7,7 @@ int msm_run_deferred_mnt4g2(const void *s, const void *p, size_t n, void *out, M
 }
 int msm_precompute_mnt4g2(const void *p, size_t n, MsmPlan &plan, DevBuf &table) { return msm_precompute<Mnt4G2>(p, n, plan, table); }
 int msm_run_table_deferred_mnt4g2(const void *s, const void *t, size_t n, const MsmPlan &plan, void *out,
-                                  MsmTail &tail, int share_slot, const MsmDedup *dedup) {
-  return msm_run_table_deferred<Mnt4G2>(s, t, n, plan, out, tail, share_slot, dedup);
+                                  MsmTail &tail, MsmShare share, const MsmDedup *dedup) {
+  return msm_run_table_deferred<Mnt4G2>(s, t, n, plan, out, tail, share, dedup);
 }
 }  // namespace b200

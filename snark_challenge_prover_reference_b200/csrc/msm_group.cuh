@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(128, G::F::kDegree == 3 ? B200_ACC_BLOCKS_FQ3 
   xyzz_set_zero(acc);
   for (uint32_t k = 0; k < len; k++) {
     uint32_t e = entries[start + k];
+    if (e == kSkipEntry) continue;  // dropped when a shared entry list was re-indexed for this query (MsmShare)
     Affine<F> q;
     load_streaming(q, points + (e >> 1));  // table gathers pass through once: keep the L2 for the stack frames
     if (affine_is_zero(q)) continue;
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(128) msm_affine_finish_kernel(const Affine<typ
       const uint32_t e = entries[idx];
       idx = e >> 1;
       neg = e & 1u;
-      inf = base_is_O[idx % n_bases];
+      inf = e == kSkipEntry ? 1u : base_is_O[idx % n_bases];
     } else {
       inf = oflag_in[idx];
     }
@@ -547,7 +548,8 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 // per-bucket combine of the task sums. `pw` owns the entry lists / task arrays (this MSM's workspace or the one it
 // shares its scalar preparation with). Nothing here waits on the host.
 template <class G>
-int msm_accumulate_xyzz(const void *d_points, const MsmPlan &plan, MsmWorkspace &ws, MsmWorkspace &pw) {
+int msm_accumulate_xyzz(const void *d_points, const MsmPlan &plan, MsmWorkspace &ws, MsmWorkspace &pw,
+                        const uint32_t *entries) {
   typedef typename G::F F;
   cudaStream_t st = ws.stream;
   const size_t nbuckets = plan.nbuckets;
@@ -557,7 +559,7 @@ int msm_accumulate_xyzz(const void *d_points, const MsmPlan &plan, MsmWorkspace 
   B200_CUDA_CHECK(cudaStreamWaitEvent(ws.acc_stream, pw.prep_done, 0));
   if (plan.ntasks) {
     msm_accumulate_kernel<G><<<grid_for(plan.ntasks, 128), 128, 0, ws.acc_stream>>>(
-        (const Affine<F> *)d_points, pw.entries.as<uint32_t>(), pw.offsets.as<uint32_t>(), pw.task_off.as<uint32_t>(),
+        (const Affine<F> *)d_points, entries, pw.offsets.as<uint32_t>(), pw.task_off.as<uint32_t>(),
         pw.task_bucket.as<uint32_t>(), pw.task_len_sorted.as<uint32_t>(), pw.order.as<uint32_t>(),
         (uint32_t)plan.ntasks, plan.task_len, ws.partials.as<Proj<F>>());
     B200_CUDA_CHECK(cudaGetLastError());
@@ -627,7 +629,8 @@ struct AffineRound<G, 1> {
 // Bucket accumulation by rounds of batched affine additions (see msm_affine_round_kernel). n_bases = the MSM's n:
 // the first n entries of d_points are the bases themselves (window 0 of a table, or the plain query).
 template <class G>
-int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmPlan &plan, MsmWorkspace &ws, MsmWorkspace &pw) {
+int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmPlan &plan, MsmWorkspace &ws, MsmWorkspace &pw,
+                                const uint32_t *entries) {
   typedef typename G::F F;
   cudaStream_t st = ws.stream;
   const size_t nbuckets = plan.nbuckets;
@@ -636,8 +639,7 @@ int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmP
   B200_CHECK(msm_affine_levels(pw.counts.as<uint32_t>(), pw.offsets.as<uint32_t>(), (uint32_t)nbuckets, plan.max_count, totals));
   const int rounds = (int)totals.size() - 1;
   const uint32_t *cnt = ws.aff_cnt.as<uint32_t>(), *off = ws.aff_off.as<uint32_t>();
-  B200_CHECK(msm_affine_pairs(ws, cnt, off, (uint32_t)nbuckets, totals, pw.entries.as<uint32_t>(), ws.base_flags.as<uint8_t>(),
-                              n_bases, pair_off));
+  B200_CHECK(msm_affine_pairs(ws, cnt, off, (uint32_t)nbuckets, totals, entries, ws.base_flags.as<uint8_t>(), n_bases, pair_off));
   static int wave = 0;  // resident threads of one full wave of the round kernel
   if (!wave) {
     int per_sm = 0, dev = 0, sms = 0;
@@ -693,7 +695,7 @@ int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmP
     done = r;
   }
   msm_affine_finish_kernel<G><<<grid_for(nbuckets, 128), 128, 0, st>>>(
-      src, oflag_in, done == 0 ? pw.entries.as<uint32_t>() : nullptr, ws.base_flags.as<uint8_t>(), (uint32_t)n_bases,
+      src, oflag_in, done == 0 ? entries : nullptr, ws.base_flags.as<uint8_t>(), (uint32_t)n_bases,
       off + (size_t)done * nbuckets, cnt + (size_t)done * nbuckets, (uint32_t)nbuckets, ws.buckets.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
@@ -706,7 +708,8 @@ int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmP
 // scalars and window plan instead of repeating it (this MSM then only waits for that slot's prep_done event).
 template <class G>
 int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan &plan, MsmWorkspace::Staging *&stage,
-                  int share_slot = -1, const MsmDedup *dedup = nullptr) {
+                  MsmShare share = MsmShare(), const MsmDedup *dedup = nullptr) {
+  const int share_slot = share.slot;
   typedef typename G::F F;
   typedef typename G::ScalarPrime FrP;
   MsmWorkspace &ws = msm_workspace();
@@ -720,6 +723,15 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
     B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan, dedup));
   }
   MsmWorkspace &pw = *prep_ws;  // owner of entries / offsets / task arrays
+  const uint32_t *entries = pw.entries.as<uint32_t>();
+  if (share_slot >= 0 && share.n_src) {
+    // same buckets, other point numbering: this MSM's own copy of the producer's entry list, re-indexed
+    const size_t total = (size_t)plan.W * share.n_src;
+    B200_CHECK(ws.entries.reserve(total * sizeof(uint32_t)));
+    B200_CHECK(msm_share_entries(entries, total, share.n_src, (uint32_t)n, share.shift, ws.entries.as<uint32_t>(), st));
+    if (ws.acc_stream != st) B200_CUDA_CHECK(cudaStreamSynchronize(st));  // (split-stream experiment only)
+    entries = ws.entries.as<uint32_t>();
+  }
   const int W = plan.merged ? 1 : plan.W;  // number of independent bucket sets to reduce
   const uint32_t nb = plan.nb;
   const size_t nbuckets = plan.nbuckets;
@@ -735,11 +747,11 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
                       (size_t)plan.W * n < ((size_t)1 << 30);
   if (affine) {
     B200_CUDA_CHECK(cudaEventRecord(stage->ta, st));
-    B200_CHECK(msm_accumulate_batch_affine<G>(d_points, n, plan, ws, pw));
+    B200_CHECK(msm_accumulate_batch_affine<G>(d_points, n, plan, ws, pw, entries));
   } else {
     B200_CUDA_CHECK(cudaStreamWaitEvent(ws.acc_stream, pw.prep_done, 0));
     B200_CUDA_CHECK(cudaEventRecord(stage->ta, ws.acc_stream));
-    B200_CHECK(msm_accumulate_xyzz<G>(d_points, plan, ws, pw));
+    B200_CHECK(msm_accumulate_xyzz<G>(d_points, plan, ws, pw, entries));
   }
 
   // ---- bucket reduction (enqueued, not awaited): chunks of K buckets, then tree sum per bucket set
@@ -953,7 +965,7 @@ int msm_precompute(const void *d_points, size_t n, MsmPlan &plan, DevBuf &table)
 // MSM over a table built by msm_precompute (plan must be the table's plan).
 template <class G>
 int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n, const MsmPlan &table_plan, void *h_out,
-                           MsmTail &tail, int share_slot, const MsmDedup *dedup) {
+                           MsmTail &tail, MsmShare share, const MsmDedup *dedup) {
   typedef typename G::F F;
   if (n == 0) {
     Proj<F> zero;
@@ -964,7 +976,7 @@ int msm_run_table_deferred(const void *d_scalars, const void *d_table, size_t n,
   }
   auto plan = std::make_shared<MsmPlan>(table_plan);
   MsmWorkspace::Staging *stage = nullptr;
-  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage, share_slot, dedup));
+  B200_CHECK(msm_gpu_phase<G>(d_scalars, d_table, n, *plan, stage, share, dedup));
   tail = msm_make_tail<G>(plan, stage, h_out);
   return 0;
 }

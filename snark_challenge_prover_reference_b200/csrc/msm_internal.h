@@ -76,6 +76,19 @@ int msm_current_slot();
 // scalars: copies, compute_H). Default: the legacy default stream.
 void msm_set_input_stream(cudaStream_t st);
 
+// Reuse of another MSM's scalar-side preparation (digits, counting sort, task lists): `slot` = the workspace that made
+// it for the SAME window plan (-1: prepare on its own). When the consumer's points are numbered differently - the L
+// query reads w[i + 2], i.e. its point i belongs to the producer's scalar i + 2 - the producer's entries are re-indexed
+// into the consumer's own entry buffer: entry (window j, scalar s) -> j * n + (s - shift), dropped (kSkipEntry) when
+// s < shift or s - shift >= n. n_src = the producer's n (0: same numbering, entries are used in place).
+struct MsmShare {
+  int slot = -1;
+  uint32_t n_src = 0, shift = 0;
+};
+constexpr uint32_t kSkipEntry = 0xffffffffu;
+int msm_share_entries(const uint32_t *src_entries, size_t total, uint32_t n_src, uint32_t n_dst, uint32_t shift,
+                      uint32_t *dst_entries, cudaStream_t st);
+
 struct MsmPlan {
   int c = 0, W = 0;
   bool merged = false;          // all windows share one bucket set (entries index a table of pre-shifted bases)
@@ -121,7 +134,7 @@ int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, ui
 // pre-shifted base tables (merged buckets), see msm_group.cuh
 int msm_precompute_dispatch(int curve, int group, const void *d_points, size_t n, MsmPlan &plan, DevBuf &table);
 int msm_table_dispatch_deferred(int curve, int group, const void *d_scalars, const void *d_table, size_t n,
-                                const MsmPlan &plan, void *h_out, MsmTail &tail, int share_slot = -1,
+                                const MsmPlan &plan, void *h_out, MsmTail &tail, MsmShare share = MsmShare(),
                                 const MsmDedup *dedup = nullptr);
 
 }  // namespace b200
