@@ -178,6 +178,20 @@ typedef struct {
 } b200_proof_job;
 int b200_prove_batch(b200_proof_job *jobs, int count);
 
+/* ---- complete Groth16 proof terms ------------------------------------------------------------
+ * The challenge's prover stops at A = sum w_i A_i, B = sum w_i B_i (G2), C = H + L + r*B1 (main.cpp:227-253). A complete
+ * r1cs_gg_ppzksnark proof (r1cs_gg_ppzksnark.tcc:457-470, and the `debug` sketch main.cpp:295-343) adds the key's
+ * alpha / beta / delta elements and the second randomiser s:
+ *     A' = alpha_g1 + A + r*delta_g1      B' = beta_g2 + B + s*delta_g2      C' = C + s*A' + r*beta_g1
+ * (C already holds r*B1, which is what remains of r*B1' - r*s*delta_g1). O(1) host group operations on top of the
+ * five MSMs. h_proof / h_out: A | B | C in wire format; h_extras: alpha_g1 | beta_g1 | delta_g1 (G1) | beta_g2 |
+ * delta_g2 (G2) in wire format (the proving-key elements the challenge's parameter file leaves out). */
+int b200_groth16_finalize(int curve, const void *h_proof, const void *h_r_fr, const void *h_s_fr, const void *h_extras,
+                          void *h_out, size_t *out_bytes);
+/* b200_prove followed by b200_groth16_finalize (r = the input image's last element, as in main.cpp:218) */
+int b200_prove_full(b200_params *p, const void *h_input, size_t input_bytes, const void *h_s_fr, const void *h_extras,
+                    void *h_out, size_t *out_bytes);
+
 /* ---- test / bench hooks: element-wise application of the device primitives the kernels are built from ------- */
 /* op: 0 add 1 sub 2 mul 3 sqr 4 from_mont 5 to_mont 6 inv ; tag: 0 = modulus A, 1 = modulus B */
 int b200_dev_fp_op(int tag, int op, const void *d_a, const void *d_b, void *d_r, size_t n);

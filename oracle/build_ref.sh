@@ -47,6 +47,7 @@ build() { # name, sources...
 build main "$R/libsnark/main.cpp" &
 build generate_parameters "$R/libsnark/generate_parameters.cpp" &
 build gen_params_any "$HERE/gen_params_any.cpp" &
+build groth16_tool "$HERE/groth16_tool.cpp" &
 # host-only build of the reference's own piecewise driver: its six cuda-fixnum includes are satisfied by empty
 # stub headers (it calls none of them), and -x c++ treats the .cu as plain C++.
 for h in array/fixnum_array.h fixnum/warp_fixnum.cu functions/modexp.cu functions/multi_modexp.cu \

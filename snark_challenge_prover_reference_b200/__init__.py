@@ -124,6 +124,8 @@ _SIGNATURES = {
     "b200_params_query": (_vp, [_vp, _i]),
     "b200_prove": (_i, [_vp, _vp, _sz, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
     "b200_prove_partial": (_i, [_vp, _vp, _sz, _i, _i, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
+    "b200_groth16_finalize": (_i, [_i, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_sz)]),
+    "b200_prove_full": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, ctypes.POINTER(_sz)]),
     "b200_prove_combine": (_i, [_i, _vp, _i, _vp, _vp, ctypes.POINTER(_sz)]),
     "b200_dev_fp_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
     "b200_dev_fqe_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
@@ -355,6 +357,15 @@ class Params:
                                ctypes.byref(tm)))
         return (out.raw[:n.value], tm.as_dict()) if timings else out.raw[:n.value]
 
+    def prove_full(self, input_image, s_fr, extras):
+        """one proof with the complete Groth16 terms (b200_prove_full)"""
+        out = ctypes.create_string_buffer(proof_bytes(self.curve))
+        n = ctypes.c_size_t()
+        sb, eb = ctypes.create_string_buffer(bytes(s_fr), len(s_fr)), ctypes.create_string_buffer(bytes(extras), len(extras))
+        check(lib().b200_prove_full(self.h, _ptr(input_image), _len(input_image), ctypes.addressof(sb), ctypes.addressof(eb),
+                                    ctypes.addressof(out), ctypes.byref(n)))
+        return out.raw[:n.value]
+
     def prove_partial(self, input_image, rank, world):
         out = ctypes.create_string_buffer(partial_bytes(self.curve))
         n = ctypes.c_size_t()
@@ -377,6 +388,15 @@ def prove_combine(curve, partials_all, world, r_fr):
     rb = ctypes.create_string_buffer(bytes(r_fr), FE)
     check(lib().b200_prove_combine(curve, ctypes.addressof(pb), world, ctypes.addressof(rb), ctypes.addressof(out),
                                    ctypes.byref(n)))
+    return out.raw[:n.value]
+
+
+def groth16_finalize(curve, proof, r_fr, s_fr, extras):
+    """challenge proof (A | B | C) -> complete Groth16 proof with the alpha / beta / delta / s terms (host only)"""
+    out = ctypes.create_string_buffer(proof_bytes(curve))
+    n = ctypes.c_size_t()
+    bufs = [ctypes.create_string_buffer(bytes(x), len(x)) for x in (proof, r_fr, s_fr, extras)]
+    check(lib().b200_groth16_finalize(curve, *[ctypes.addressof(b) for b in bufs], ctypes.addressof(out), ctypes.byref(n)))
     return out.raw[:n.value]
 
 

@@ -918,6 +918,52 @@ int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_
   return 0;
 }
 
+// ---- complete Groth16 proof terms: r1cs_gg_ppzksnark.tcc:457-470 / main.cpp:307-314
+int b200_groth16_finalize(int curve, const void *h_proof, const void *h_r_fr, const void *h_s_fr, const void *h_extras,
+                          void *h_out, size_t *out_bytes) {
+  if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
+  if (!h_proof || !h_r_fr || !h_s_fr || !h_extras || !h_out) return set_error(-1, "groth16_finalize: null argument");
+  const size_t g1a = affine_bytes(curve, 1), g2a = affine_bytes(curve, 2), g1p = proj_bytes(curve, 1), g2p = proj_bytes(curve, 2);
+  const unsigned char *pr = (const unsigned char *)h_proof, *ex = (const unsigned char *)h_extras;
+  std::vector<unsigned char> A(g1p), B(g2p), C(g1p), alpha(g1p), beta1(g1p), delta1(g1p), beta2(g2p), delta2(g2p), t1(g1p), t2(g2p);
+  B200_CHECK(b200_g1_from_affine(curve, pr, A.data()));
+  B200_CHECK(b200_g2_from_affine(curve, pr + g1a, B.data()));
+  B200_CHECK(b200_g1_from_affine(curve, pr + g1a + g2a, C.data()));
+  B200_CHECK(b200_g1_from_affine(curve, ex, alpha.data()));
+  B200_CHECK(b200_g1_from_affine(curve, ex + g1a, beta1.data()));
+  B200_CHECK(b200_g1_from_affine(curve, ex + 2 * g1a, delta1.data()));
+  B200_CHECK(b200_g2_from_affine(curve, ex + 3 * g1a, beta2.data()));
+  B200_CHECK(b200_g2_from_affine(curve, ex + 3 * g1a + g2a, delta2.data()));
+  // A' = alpha + A + r*delta
+  B200_CHECK(b200_g1_scale(curve, h_r_fr, delta1.data(), t1.data()));
+  B200_CHECK(b200_g1_add(curve, alpha.data(), A.data(), A.data()));
+  B200_CHECK(b200_g1_add(curve, A.data(), t1.data(), A.data()));
+  // B' = beta + B + s*delta
+  B200_CHECK(b200_g2_scale(curve, h_s_fr, delta2.data(), t2.data()));
+  B200_CHECK(b200_g2_add(curve, beta2.data(), B.data(), B.data()));
+  B200_CHECK(b200_g2_add(curve, B.data(), t2.data(), B.data()));
+  // C' = C + s*A' + r*beta_g1
+  B200_CHECK(b200_g1_scale(curve, h_s_fr, A.data(), t1.data()));
+  B200_CHECK(b200_g1_add(curve, C.data(), t1.data(), C.data()));
+  B200_CHECK(b200_g1_scale(curve, h_r_fr, beta1.data(), t1.data()));
+  B200_CHECK(b200_g1_add(curve, C.data(), t1.data(), C.data()));
+  unsigned char *o = (unsigned char *)h_out;
+  B200_CHECK(b200_g1_to_affine(curve, A.data(), o));
+  B200_CHECK(b200_g2_to_affine(curve, B.data(), o + g1a));
+  B200_CHECK(b200_g1_to_affine(curve, C.data(), o + g1a + g2a));
+  if (out_bytes) *out_bytes = 2 * g1a + g2a;
+  return 0;
+}
+int b200_prove_full(b200_params *p, const void *h_input, size_t input_bytes, const void *h_s_fr, const void *h_extras,
+                    void *h_out, size_t *out_bytes) {
+  std::vector<unsigned char> abc(2 * affine_bytes(p->curve, 1) + affine_bytes(p->curve, 2));
+  size_t n = 0;
+  B200_CHECK(b200_prove(p, h_input, input_bytes, abc.data(), &n, nullptr));
+  unsigned char r[96];  // the input image may live in host or device memory
+  B200_CUDA_CHECK(cudaMemcpy(r, (const unsigned char *)h_input + input_bytes - 96, 96, cudaMemcpyDefault));
+  return b200_groth16_finalize(p->curve, abc.data(), r, h_s_fr, h_extras, h_out, out_bytes);
+}
+
 // ---- several proofs in flight at once -------------------------------------------------------------------------------
 // A persistent host thread per extra job: the MSM workspaces and streams are thread_local, so a worker keeps its
 // own set for the life of the process and its proof runs beside the caller's on the same GPU. The MNT6753 proof
