@@ -192,6 +192,15 @@ int b200_groth16_finalize(int curve, const void *h_proof, const void *h_r_fr, co
 int b200_prove_full(b200_params *p, const void *h_input, size_t input_bytes, const void *h_s_fr, const void *h_extras,
                     void *h_out, size_t *out_bytes);
 
+/* ---- key generation: fixed-base batch exponentiation ------------------------------------------
+ * out[i] = scalars[i] * g for one base and n scalars - libff::batch_exp over get_window_table / windowed_exp
+ * (multiexp.tcc:547-645), the inner loop of r1cs_gg_ppzksnark_generator (r1cs_gg_ppzksnark.tcc:289-342).
+ * h_base_affine: g in affine wire format (HOST); d_scalars: n Fr elements (Montgomery, as everywhere); d_out_affine: n
+ * affine wire-format points, i.e. exactly what a query of a parameter file holds. window: 0 = automatic, else the
+ * window width in bits. ms3 (optional): milliseconds of {table build, exponentiation, conversion to affine}. */
+int b200_batch_exp(int curve, int group, const void *h_base_affine, const void *d_scalars, size_t n, void *d_out_affine,
+                   int window, double *ms3);
+
 /* ---- test / bench hooks: element-wise application of the device primitives the kernels are built from ------- */
 /* op: 0 add 1 sub 2 mul 3 sqr 4 from_mont 5 to_mont 6 inv ; tag: 0 = modulus A, 1 = modulus B */
 int b200_dev_fp_op(int tag, int op, const void *d_a, const void *d_b, void *d_r, size_t n);

@@ -131,6 +131,7 @@ _SIGNATURES = {
     "b200_dev_fqe_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
     "b200_dev_group_op": (_i, [_i, _i, _i, _vp, _vp, _vp, _sz]),
     "b200_gen_points": (_i, [_i, _i, _vp, _sz, _u64]),
+    "b200_batch_exp": (_i, [_i, _i, _vp, _vp, _sz, _vp, _i, ctypes.POINTER(ctypes.c_double)]),
     "b200_imad_peak": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -389,6 +390,14 @@ def prove_combine(curve, partials_all, world, r_fr):
     check(lib().b200_prove_combine(curve, ctypes.addressof(pb), world, ctypes.addressof(rb), ctypes.addressof(out),
                                    ctypes.byref(n)))
     return out.raw[:n.value]
+
+
+def batch_exp(curve, group, base_affine, d_scalars, n, d_out, window=0):
+    """out[i] = scalars[i] * base (fixed-base windowed exponentiation, libff::batch_exp); returns phase times in ms"""
+    ms = (ctypes.c_double * 3)()
+    b = ctypes.create_string_buffer(bytes(base_affine), len(base_affine))
+    check(lib().b200_batch_exp(curve, group, ctypes.addressof(b), _ptr(d_scalars), n, _ptr(d_out), window, ms))
+    return {"table": ms[0], "exp": ms[1], "to_affine": ms[2]}
 
 
 def groth16_finalize(curve, proof, r_fr, s_fr, extras):

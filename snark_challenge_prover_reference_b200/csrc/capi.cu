@@ -420,6 +420,14 @@ int b200_gen_points(int curve, int group, void *d_out, size_t n, uint64_t first)
   B200_CHECK(require_device());
   return gen_points(curve, group, d_out, n, first);
 }
+int b200_batch_exp(int curve, int group, const void *h_base_affine, const void *d_scalars, size_t n, void *d_out_affine,
+                   int window, double *ms3) {
+  B200_CHECK(require_device());
+  if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
+  if (group != 1 && group != 2) return set_error(-1, "bad group %d", group);
+  if (!h_base_affine || (n && (!d_scalars || !d_out_affine))) return set_error(-1, "batch_exp: null argument");
+  return batch_exp(curve, group, h_base_affine, d_scalars, n, d_out_affine, window, ms3);
+}
 int b200_imad_peak(double *mac32_per_s, double *ms) {
   B200_CHECK(require_device());
   return imad_peak(mac32_per_s, ms);

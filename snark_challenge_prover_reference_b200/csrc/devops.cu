@@ -219,6 +219,17 @@ int dev_group_op(int curve, int group, int op, const void *p, const void *q, voi
   if (curve == 1 && group == 2) return group_op_mnt6g2(op, p, q, r, n);
   return set_error(-1, "dev_group_op: bad curve/group");
 }
+int batch_exp_mnt4g1(const void *, const void *, size_t, void *, int, double *);
+int batch_exp_mnt4g2(const void *, const void *, size_t, void *, int, double *);
+int batch_exp_mnt6g1(const void *, const void *, size_t, void *, int, double *);
+int batch_exp_mnt6g2(const void *, const void *, size_t, void *, int, double *);
+int batch_exp(int curve, int group, const void *h_base, const void *d_scalars, size_t n, void *d_out, int window, double *ms3) {
+  if (curve == 0 && group == 1) return batch_exp_mnt4g1(h_base, d_scalars, n, d_out, window, ms3);
+  if (curve == 0 && group == 2) return batch_exp_mnt4g2(h_base, d_scalars, n, d_out, window, ms3);
+  if (curve == 1 && group == 1) return batch_exp_mnt6g1(h_base, d_scalars, n, d_out, window, ms3);
+  if (curve == 1 && group == 2) return batch_exp_mnt6g2(h_base, d_scalars, n, d_out, window, ms3);
+  return set_error(-1, "batch_exp: bad curve/group");
+}
 int gen_points(int curve, int group, void *out, size_t n, uint64_t first) {
   if (n == 0) return 0;
   if (curve == 0 && group == 1) return gen_points_mnt4g1(out, n, first);

@@ -568,3 +568,30 @@ def test_host_synth_key_matches_device_generator(b200, dev, curve, group, tmp_pa
     got = b200.from_device(out)
     lo, hi = (0, n) if group == 1 else (1, m - 2)   # B2 carries O at 0 and m and a duplicate pair at m-2
     assert got[lo * ab:hi * ab] == q[name][lo * ab:hi * ab]
+
+
+# ------------------------------------------------------------------------------------------------ key generation: batch_exp
+@pytest.mark.parametrize("curve,group,window", [(0, 1, 0), (0, 1, 16), (0, 2, 11), (1, 1, 0), (1, 2, 7)])
+def test_batch_exp_vs_oracle(b200, oracle, dev, curve, group, window):
+    """SURVEY.md 8(f) row 4: fixed-base windowed exponentiation (libff::batch_exp, multiexp.tcc:547-645) - out[i] =
+    s_i * g, affine wire format - against the oracle's scalar multiplication, including scalars 0, 1, r-1 and a base
+    that is not the generator."""
+    import torch
+    c = util.curve_obj(curve)
+    rng = random.Random(9300 + 10 * curve + group + window)
+    n = 150
+    scalars = [rng.randrange(c.r) for _ in range(n)]
+    scalars[0], scalars[1], scalars[2], scalars[3] = 0, 1, c.r - 1, 1 << 752
+    sc = b"".join(util.fe_bytes(M.to_mont(s, c.r)) for s in scalars)
+    ab = b200.affine_bytes(curve, group)
+    G = b200.g_from_affine(curve, group, util.generator_affine(curve, group))
+    k = util.fe_bytes(M.to_mont(rng.randrange(2, c.r), c.r))
+    base_proj = util.orc_group(oracle, curve, group, 3, G, k)
+    base = util.orc_to_affine(oracle, curve, group, base_proj)
+    out = torch.empty(n * ab, dtype=torch.uint8, device=dev)
+    ms = b200.batch_exp(curve, group, base, b200.to_device(sc), n, out, window)
+    assert all(v >= 0 for v in ms.values())
+    got = b200.from_device(out)
+    for i in range(n):
+        exp = util.orc_to_affine(oracle, curve, group, util.orc_group(oracle, curve, group, 3, base_proj, sc[i * FE:(i + 1) * FE]))
+        assert got[i * ab:(i + 1) * ab] == exp, (curve, group, window, i)
