@@ -5,7 +5,7 @@ import torch
 import snark_challenge_prover_reference_b200 as b
 import bench
 curve, k = int(sys.argv[1]), int(sys.argv[2])
-reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 tables = (sys.argv[4] != "0") if len(sys.argv) > 4 else True
 b.check(b.lib().b200_set_device(0))
 dev = torch.device("cuda", 0)
