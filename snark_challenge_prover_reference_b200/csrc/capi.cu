@@ -500,43 +500,66 @@ int b200_params_from_host(int curve, const void *h_image, size_t bytes, b200_par
   return 0;
 }
 // file (positioned at the first byte to copy) -> device, `bytes` bytes: two pinned staging buffers, chunk k's
-// host->device copy runs while chunk k+1 is being read
-static int stream_file_to_device(FILE *f, const char *path, void *d_dst, size_t bytes, double &read_ms, double &wait_ms) {
-  constexpr size_t kChunk = (size_t)64 << 20;
-  struct Stage {
-    void *h = nullptr;
-    cudaEvent_t done = nullptr;
-    ~Stage() {
-      if (h) cudaFreeHost(h);
-      if (done) cudaEventDestroy(done);
+// host->device copy runs while chunk k+1 is being read. The buffers, their events and the copy stream are made once per
+// device and kept (pinning 128 MB costs ~100 ms - more than copying a 100 MB vector).
+namespace {
+struct StagePool {
+  static constexpr size_t kChunk = (size_t)64 << 20;
+  void *h[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr;
+  int device = -1;
+  std::mutex mu;
+  int ensure() {
+    int dev = 0;
+    B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (device == dev) return 0;
+    release();
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      B200_CUDA_CHECK(cudaMallocHost(&h[i], kChunk));
+      B200_CUDA_CHECK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
     }
-  } stage[2];
-  cudaStream_t copy_stream = nullptr;
-  B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-  struct StreamCloser {
-    cudaStream_t s;
-    ~StreamCloser() { cudaStreamDestroy(s); }
-  } sc{copy_stream};
-  const size_t chunk = bytes < kChunk ? (bytes ? bytes : 16) : kChunk;
-  for (int i = 0; i < 2; i++) {
-    B200_CUDA_CHECK(cudaMallocHost(&stage[i].h, chunk));
-    B200_CUDA_CHECK(cudaEventCreateWithFlags(&stage[i].done, cudaEventDisableTiming));
+    device = dev;
+    return 0;
   }
+  void release() {
+    for (int i = 0; i < 2; i++) {
+      if (h[i]) cudaFreeHost(h[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+      h[i] = nullptr;
+      done[i] = nullptr;
+    }
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+    device = -1;
+  }
+};
+StagePool &stage_pool() {
+  static StagePool *pool = new StagePool();  // leaked on purpose: outlives static destruction of the CUDA runtime
+  return *pool;
+}
+}  // namespace
+static int stream_file_to_device(FILE *f, const char *path, void *d_dst, size_t bytes, double &read_ms, double &wait_ms) {
+  StagePool &sp = stage_pool();
+  std::lock_guard<std::mutex> g(sp.mu);
+  B200_CHECK(sp.ensure());
+  const size_t chunk = StagePool::kChunk;
   int k = 0;
   for (size_t off = 0; off < bytes; off += chunk, k ^= 1) {
     const size_t n = bytes - off < chunk ? bytes - off : chunk;
     double a = now_ms();
-    B200_CUDA_CHECK(cudaEventSynchronize(stage[k].done));  // the copy that last used this buffer (no-op the first time)
+    B200_CUDA_CHECK(cudaEventSynchronize(sp.done[k]));  // the copy that last used this buffer (no-op the first time)
     double b = now_ms();
-    if (fread(stage[k].h, 1, n, f) != n) return set_error(-4, "short read on %s", path);
+    if (fread(sp.h[k], 1, n, f) != n) return set_error(-4, "short read on %s", path);
     double c = now_ms();
     wait_ms += b - a;
     read_ms += c - b;
-    B200_CUDA_CHECK(cudaMemcpyAsync((char *)d_dst + off, stage[k].h, n, cudaMemcpyHostToDevice, copy_stream));
-    B200_CUDA_CHECK(cudaEventRecord(stage[k].done, copy_stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync((char *)d_dst + off, sp.h[k], n, cudaMemcpyHostToDevice, sp.stream));
+    B200_CUDA_CHECK(cudaEventRecord(sp.done[k], sp.stream));
   }
   double a = now_ms();
-  B200_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+  B200_CUDA_CHECK(cudaStreamSynchronize(sp.stream));
   wait_ms += now_ms() - a;
   return 0;
 }
