@@ -476,10 +476,18 @@ def b200_arm(args):
     pkg.set_precompute(True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    # bytes this rank moves per e2e step: its slice of w (b200_prove_partial uploads only what its MSM slices read) plus
+    # ca, cb, cc in full (compute_H is replicated); back come the partial sums or the finished proof
+    def slice_len(n, r, w):
+        one = n // w
+        return n - r * one if r == w - 1 else one
+    my_h2d = sum(FE * (slice_len((1 << shapes[i][1]) + 1, r, w) + 3 * (1 << shapes[i][1]) + 1) for i, r, w in my_jobs)
+    my_d2h = sum(pbytes[i] if w > 1 else proof_len[i] for i, _, w in my_jobs)
+    h2d_list, d2h_list = [my_h2d], [my_d2h]
     if world > 1:
-        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        lt = torch.tensor([launches, my_h2d, my_d2h], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
-        launches = int(lt.item())
+        launches, h2d_list, d2h_list = int(lt[0].item()), [int(lt[1].item())], [int(lt[2].item())]
 
     if rank != 0:
         if world > 1:
@@ -489,8 +497,8 @@ def b200_arm(args):
     assert proofs_dev == proofs_nt, "table and table-free MSM paths disagree"
     value = constraints * args.steps / (ms_dev / 1e3)
     e2e = constraints * args.steps / (ms_e2e / 1e3)
-    h2d = sum(h.numel() for h in host_inputs.values())
-    d2h = sum(pbytes[i] if w > 1 else proof_len[i] for i, _, w in my_jobs)
+    h2d = sum(h2d_list)
+    d2h = sum(d2h_list)
 
     # ---- parity with the reference on the step's own files (written by --impl reference on this box)
     parity = {}

@@ -125,6 +125,9 @@ int b200_params_destroy(b200_params *p);
  * build them on first use if this was not called. Idempotent per (rank, world). */
 int b200_params_precompute(b200_params *p, int rank, int world);
 double b200_params_precompute_ms(const b200_params *p);
+/* One throw-away proof on pseudo-random inputs: loads every kernel and sizes every workspace for this key, so that the
+ * first real proof of a process does not pay first-use costs (B::read_params calls it after the tables are built). */
+int b200_params_warmup(b200_params *p);
 int b200_set_precompute(int on);
 /* sum_i scalars[i] * query[i] over one whole query of the key (which: 0 A, 1 B1, 2 B2 (G2), 3 L, 4 H); uses the
  * pre-shifted base table when precomputation is enabled and n is the query's length. Result: projective, host memory.

@@ -115,6 +115,7 @@ _SIGNATURES = {
     "b200_params_destroy": (_i, [_vp]),
     "b200_params_precompute": (_i, [_vp, _i, _i]),
     "b200_params_precompute_ms": (ctypes.c_double, [_vp]),
+    "b200_params_warmup": (_i, [_vp]),
     "b200_set_precompute": (_i, [_i]),
     "b200_params_msm": (_i, [_vp, _i, _vp, _sz, _vp]),
     "b200_params_msm_async": (_i, [_vp, _i, _vp, _sz, _vp, ctypes.POINTER(_vp)]),

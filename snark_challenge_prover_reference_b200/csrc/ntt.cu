@@ -103,6 +103,27 @@ __global__ void __launch_bounds__(128) ntt_pass_kernel(const Fp<P> *src, Fp<P> *
   }
 }
 
+// pseudo-random field elements (< 2^752, i.e. valid Montgomery representations) for the warm-up proof of a freshly
+// loaded key: SplitMix64 of the limb index
+__global__ void __launch_bounds__(256) fr_fill_kernel(uint64_t *__restrict__ out, size_t n_limbs, uint64_t seed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_limbs) return;
+  uint64_t z = seed + (i + 1) * 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  if (i % 12 == 11) z &= 0x0000ffffffffffffull;
+  out[i] = z;
+}
+int fr_fill_pseudo_random(void *d_out, size_t n_elements, uint64_t seed) {
+  const size_t limbs = n_elements * 12;
+  if (limbs == 0) return 0;
+  fr_fill_kernel<<<grid_for(limbs, 256), 256, 0, g_ntt_stream>>>((uint64_t *)d_out, limbs, seed);
+  B200_CUDA_CHECK(cudaGetLastError());
+  note_launch();
+  return 0;
+}
+
 template <class P>
 __global__ void __launch_bounds__(128) fr_muleq_kernel(Fp<P> *__restrict__ a, const Fp<P> *__restrict__ b, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

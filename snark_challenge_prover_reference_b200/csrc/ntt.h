@@ -14,6 +14,7 @@ int domain_transform(Domain *d, void *d_a, int kind);
 int domain_divide_by_z(Domain *d, void *d_a);
 int fr_muleq(int curve, void *d_a, const void *d_b, size_t n);
 int fr_subeq(int curve, void *d_a, const void *d_b, size_t n);
+int fr_fill_pseudo_random(void *d_out, size_t n_elements, uint64_t seed);
 int compute_h(Domain *d, void *d_ca, void *d_cb, void *d_cc, void *d_out);
 // stream used by the transforms / point-wise kernels issued from the calling host thread (0 = legacy default)
 void ntt_set_stream(cudaStream_t st);
