@@ -90,6 +90,8 @@ int b200_g1_to_affine(int curve, const void *h_p, void *h_out_xy);              
 int b200_g2_to_affine(int curve, const void *h_p, void *h_out_xy);                  /* write_g2 (serialization.hpp:56-67) */
 int b200_g1_from_affine(int curve, const void *h_xy, void *h_out_proj);             /* read_g1  (serialization.hpp:83-91) */
 int b200_g2_from_affine(int curve, const void *h_xy, void *h_out_proj);
+/* test hook: 2^k * P (P affine, not O) through the Jacobian doubling the base-table builder uses -> affine */
+int b200_host_jacobian_doublings(int curve, int group, const void *h_xy, int k, void *h_out_xy);
 /* host field ops (tag 0 = modulus A, 1 = modulus B); op: 0 add 1 sub 2 mul 3 inv 4 from_mont 5 to_mont
  * 6 inv by the bitwise binary gcd (the device's routine, run on the host) 7 inv by the batched binary gcd (what op 3
  * uses on the host) 8 inv by Fermat's little theorem */

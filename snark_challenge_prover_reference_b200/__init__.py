@@ -105,6 +105,7 @@ _SIGNATURES = {
     "b200_g2_to_affine": (_i, [_i, _vp, _vp]),
     "b200_g1_from_affine": (_i, [_i, _vp, _vp]),
     "b200_g2_from_affine": (_i, [_i, _vp, _vp]),
+    "b200_host_jacobian_doublings": (_i, [_i, _i, _vp, _i, _vp]),
     "b200_host_fp_op": (_i, [_i, _i, _vp, _vp, _vp]),
     "b200_params_from_host": (_i, [_i, _vp, _sz, ctypes.POINTER(_vp)]),
     "b200_params_from_file": (_i, [_i, ctypes.c_char_p, ctypes.POINTER(_vp)]),

@@ -71,6 +71,24 @@ struct HostOps {
     proj_to_affine<G>(o, a);
     memcpy(out, &o, sizeof(o));
   }
+  // 2^k * P through the Jacobian doubling of the base-table builder, affine wire format (test hook: the same template
+  // runs on the device)
+  static void jacobian_doublings(const void *xy, int k, void *out) {
+    Affine<F> a, o;
+    memcpy(&a, xy, sizeof(a));
+    Proj<F> cur;
+    cur.X = a.x;
+    cur.Y = a.y;
+    F::set_one(cur.Z);
+    for (int i = 0; i < k; i++) jac_dbl<G>(cur, cur);
+    F zi, zi2;
+    F::inv(zi, cur.Z);
+    F::sqr(zi2, zi);
+    F::mul(o.x, cur.X, zi2);
+    F::mul(zi2, zi2, zi);
+    F::mul(o.y, cur.Y, zi2);
+    memcpy(out, &o, sizeof(o));
+  }
   static void from_affine(const void *xy, void *out) {
     Affine<F> a;
     Proj<F> p;
@@ -224,11 +242,14 @@ static size_t group_equal_bases(const unsigned char *pts, size_t n, size_t point
   return merged;
 }
 
-static int find_equal_bases(const void *d_points, size_t n, size_t point_bytes, MsmDedup &dd) {
+// (copies go through `st`, a non-blocking stream: the caller runs this on a host thread of its own while the table
+// kernels occupy the default stream)
+static int find_equal_bases(const void *d_points, size_t n, size_t point_bytes, MsmDedup &dd, cudaStream_t st) {
   dd.reset();
   if (n < 8) return 0;
   std::vector<unsigned char> pts(n * point_bytes);
-  B200_CUDA_CHECK(cudaMemcpy(pts.data(), d_points, pts.size(), cudaMemcpyDeviceToHost));
+  B200_CUDA_CHECK(cudaMemcpyAsync(pts.data(), d_points, pts.size(), cudaMemcpyDeviceToHost, st));
+  B200_CUDA_CHECK(cudaStreamSynchronize(st));
   std::vector<uint32_t> members, segments, groups;
   const size_t merged = group_equal_bases(pts.data(), n, point_bytes, members, segments, groups);
   if (merged < std::max<size_t>(4, n / 32)) return 0;
@@ -238,9 +259,10 @@ static int find_equal_bases(const void *d_points, size_t n, size_t point_bytes, 
   B200_CHECK(dd.segments.reserve(segments.size() * 4));
   B200_CHECK(dd.groups.reserve(groups.size() * 4));
   B200_CHECK(dd.segment_sums.reserve((size_t)dd.nsegments * 96));
-  B200_CUDA_CHECK(cudaMemcpy(dd.members.p, members.data(), members.size() * 4, cudaMemcpyHostToDevice));
-  B200_CUDA_CHECK(cudaMemcpy(dd.segments.p, segments.data(), segments.size() * 4, cudaMemcpyHostToDevice));
-  B200_CUDA_CHECK(cudaMemcpy(dd.groups.p, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpyAsync(dd.members.p, members.data(), members.size() * 4, cudaMemcpyHostToDevice, st));
+  B200_CUDA_CHECK(cudaMemcpyAsync(dd.segments.p, segments.data(), segments.size() * 4, cudaMemcpyHostToDevice, st));
+  B200_CUDA_CHECK(cudaMemcpyAsync(dd.groups.p, groups.data(), groups.size() * 4, cudaMemcpyHostToDevice, st));
+  B200_CUDA_CHECK(cudaStreamSynchronize(st));
   dd.merged = merged;
   return 0;
 }
@@ -396,6 +418,10 @@ int b200_g2_to_affine(int curve, const void *p, void *out) { DISPATCH_GROUP(curv
 int b200_g1_from_affine(int curve, const void *xy, void *out) { DISPATCH_GROUP(curve, 1, from_affine(xy, out)); }
 int b200_g2_from_affine(int curve, const void *xy, void *out) { DISPATCH_GROUP(curve, 2, from_affine(xy, out)); }
 
+int b200_host_jacobian_doublings(int curve, int group, const void *h_xy, int k, void *h_out_xy) {
+  if (k < 0 || k > 4096) return set_error(-1, "bad doubling count");
+  DISPATCH_GROUP(curve, group, jacobian_doublings(h_xy, k, h_out_xy));
+}
 int b200_host_fp_op(int tag, int op, const void *a, const void *b, void *r) {
   if (op < 0 || op > 8) return set_error(-1, "bad op");
   if (tag == 0) host_fp_op_t<PrimeA>(op, a, b, r);
@@ -690,17 +716,46 @@ int b200_params_precompute(b200_params *p, int rank, int world) {
   const size_t d = p->d, m = p->m;
   const int jobq[5] = {0, 1, 2, 4, 3};                     // job order A, B1, B2, H, L -> query index
   p->pre.rank = p->pre.world = -1;
+  // The grouping of equal bases (host: hash + sort of the G1 queries' wire bytes) runs on a thread of its own, under
+  // the table kernels.
+  int dev = 0;
+  B200_CUDA_CHECK(cudaGetDevice(&dev));
+  struct Slice { const char *pts; size_t n; int group; };
+  Slice slices[5];
   for (int j = 0; j < 5; j++) {
     const int qi = jobq[j];
-    const int group = qi == 2 ? 2 : 1;
     size_t lo, hi;
     query_slice(d, m, qi, rank, world, lo, hi);
-    const char *pts = (const char *)p->q[qi] + lo * affine_bytes(p->curve, group);
-    p->pre.plan[j] = MsmPlan();
-    if (hi > lo) B200_CHECK(msm_precompute_dispatch(p->curve, group, pts, hi - lo, p->pre.plan[j], p->pre.table[j]));
+    slices[j].group = qi == 2 ? 2 : 1;
+    slices[j].pts = (const char *)p->q[qi] + lo * affine_bytes(p->curve, slices[j].group);
+    slices[j].n = hi - lo;
     p->pre.dedup[j].reset();
-    if (hi > lo && group == 1) B200_CHECK(find_equal_bases(pts, hi - lo, affine_bytes(p->curve, 1), p->pre.dedup[j]));
   }
+  int dedup_rc = 0;
+  std::string dedup_err;
+  std::thread dedup_thread([&] {
+    cudaStream_t st = nullptr;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+      dedup_rc = set_error(-2, "equal-base grouping: cannot set up device %d", dev);
+      dedup_err = last_error();
+      return;
+    }
+    for (int j = 0; j < 5 && dedup_rc == 0; j++)
+      if (slices[j].n > 0 && slices[j].group == 1) {
+        dedup_rc = find_equal_bases(slices[j].pts, slices[j].n, affine_bytes(p->curve, 1), p->pre.dedup[j], st);
+        if (dedup_rc) dedup_err = last_error();
+      }
+    cudaStreamDestroy(st);
+  });
+  int rc = 0;
+  for (int j = 0; j < 5 && rc == 0; j++) {
+    p->pre.plan[j] = MsmPlan();
+    if (slices[j].n > 0)
+      rc = msm_precompute_dispatch(p->curve, slices[j].group, slices[j].pts, slices[j].n, p->pre.plan[j], p->pre.table[j]);
+  }
+  dedup_thread.join();
+  if (rc) return rc;
+  if (dedup_rc) return set_error(dedup_rc, "%s", dedup_err.c_str());
   p->pre.rank = rank;
   p->pre.world = world;
   p->pre.build_ms = now_ms() - t0;

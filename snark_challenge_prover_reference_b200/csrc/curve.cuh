@@ -272,6 +272,46 @@ B200_HD inline void xyzz_to_proj(Proj<F> &r, const XYZZ<F> &p) {
   F::mul(r.Z, p.ZZ, p.ZZZ);
 }
 
+// ---- Jacobian doubling (x = X/Z^2, y = Y/Z^3) --------------------------------------------------------------------
+// Used only by the base-table builder (msm_precompute_kernel), which is nothing but doublings - 753 per base: EFD
+// "dbl-2007-bl" costs 1M + 8S (+ one multiplication by the curve's small a) against the 6M + 6S of the homogeneous
+// doubling above, and its squarings go through the dedicated squaring (sqr_fast). The affine results are the same
+// canonical bytes whatever the coordinate system. Never called on O (the builder filters y == 0); a point of order 2
+// does not exist in these prime-order groups.
+template <class G>
+B200_HD void jac_dbl(Proj<typename G::F> &r, const Proj<typename G::F> &p) {
+  typedef typename G::F F;
+  F XX, YY, YYYY, ZZ, S, M, t;
+  F::sqr_fast(XX, p.X);
+  F::sqr_fast(YY, p.Y);
+  F::sqr_fast(YYYY, YY);
+  F::sqr_fast(ZZ, p.Z);
+  F::add(S, p.X, YY);
+  F::sqr_fast(S, S);
+  F::sub(S, S, XX);
+  F::sub(S, S, YYYY);
+  F::dbl(S, S);              // S = 2((X+YY)^2 - XX - YYYY)
+  F::sqr_fast(t, ZZ);
+  G::mul_by_a(M, t);         // a*ZZ^2
+  F::add(M, M, XX);
+  F::add(M, M, XX);
+  F::add(M, M, XX);          // M = 3XX + a*ZZ^2
+  F::add(t, p.Y, p.Z);
+  F::sqr_fast(t, t);
+  F::sub(t, t, YY);
+  F::sub(r.Z, t, ZZ);        // Z3 = (Y+Z)^2 - YY - ZZ   (p.Y, p.Z no longer needed after this line)
+  F::sqr_fast(t, M);
+  F::sub(t, t, S);
+  F::sub(t, t, S);           // X3 = M^2 - 2S
+  F::sub(S, S, t);
+  F::mul(S, M, S);           // M(S - X3)
+  F::dbl(YYYY, YYYY);
+  F::dbl(YYYY, YYYY);
+  F::dbl(YYYY, YYYY);        // 8 YYYY
+  F::sub(r.Y, S, YYYY);
+  r.X = t;
+}
+
 template <class F>
 B200_HD inline void proj_neg(Proj<F> &r, const Proj<F> &p) {
   r.X = p.X;

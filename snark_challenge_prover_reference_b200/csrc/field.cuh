@@ -332,9 +332,29 @@ struct alignas(16) Fp {
   // r = a * b with b streamed from global memory
   static __device__ __forceinline__ void mul_bg(Fp &r, const Fp &a, const Fp &b) { mul_dev(r.l, a.l, b.l, 1); }
 #endif
-  // (a dedicated 876-MAC squaring was generated, validated and timed in round 2: G1 accumulation 49.5 -> 49.0 ms, G2
-  // 160.7 -> 162.0 ms - noise, so squarings stay multiplications; tools/gen_fp_ptx.py --experimental still emits it)
+  // sqr: a multiplication. A dedicated 876-MAC squaring exists (sqr_fast) but does not pay in the bucket accumulation
+  // (round 2: G1 49.5 -> 49.0 ms, G2 160.7 -> 162.0 ms - squarings are 2 of 10 multiplications there and a second
+  // 22 KB body competes for the instruction cache); the base-table builder, whose Jacobian doublings are 8 squarings +
+  // 1 multiplication, calls sqr_fast.
   B200_HD static B200_INLINE void sqr(Fp &r, const Fp &a) { mul(r, a, a); }
+#if defined(__CUDACC__)
+  static __device__ __noinline__ void sqr_dev(uint32_t *r, const uint32_t *a) {
+    uint32_t x[kLimbs], z[kLimbs];
+    load_limbs(x, a);
+    if (P::kTag == 'A')
+      fp_sqr_ptx_A(z, x);
+    else
+      fp_sqr_ptx_B(z, x);
+    store_limbs(r, z);
+  }
+#endif
+  B200_HD static B200_INLINE void sqr_fast(Fp &r, const Fp &a) {
+#if defined(__CUDA_ARCH__)
+    sqr_dev(r.l, a.l);
+#else
+    host_mul(r, a, a);
+#endif
+  }
 
   // out-of-line add / sub / small-constant multiply for the tower fields (keeps Fq2/Fq3 code a short list of calls:
   // with the ~100-instruction carry chains inlined ~40 times the G2 kernels no longer fit the instruction cache)
@@ -733,6 +753,7 @@ struct alignas(16) Fp2 {
     B::sub_ni(r.c0, s, t);
     B::add_ni(r.c1, ab, ab);
   }
+  B200_HD static B200_INLINE void sqr_fast(Fp2 &r, const Fp2 &a) { sqr(r, a); }  // complex squaring has no base squarings
   B200_HD static void inv(Fp2 &r, const Fp2 &a) {  // fp2.tcc:128-142
     B t0, t1, t2;
     B::sqr(t0, a.c0);
@@ -813,6 +834,26 @@ struct alignas(16) Fp3 {
     B::add_ni(s3, s3, s3);
     B::sqr(s4, a.c2);
     // c0 = s0 + nr*s3 ; c1 = s1 + nr*s4 ; c2 = s1 + s2 + s3 - s0 - s4
+    B::template mul_small_ni<NR>(t, s3);
+    B::add_ni(r.c0, s0, t);
+    B::template mul_small_ni<NR>(t, s4);
+    B::add_ni(r.c1, s1, t);
+    B::add_ni(t, s1, s2);
+    B::add_ni(t, t, s3);
+    B::sub_ni(t, t, s0);
+    B::sub_ni(r.c2, t, s4);
+  }
+  B200_HD static B200_NOINLINE void sqr_fast(Fp3 &r, const Fp3 &a) {  // CH-SQR2 with the dedicated base squaring
+    B s0, s1, s2, s3, s4, t;
+    B::sqr_fast(s0, a.c0);
+    B::mul(s1, a.c0, a.c1);
+    B::add_ni(s1, s1, s1);
+    B::sub_ni(t, a.c0, a.c1);
+    B::add_ni(t, t, a.c2);
+    B::sqr_fast(s2, t);
+    B::mul(s3, a.c1, a.c2);
+    B::add_ni(s3, s3, s3);
+    B::sqr_fast(s4, a.c2);
     B::template mul_small_ni<NR>(t, s3);
     B::add_ni(r.c0, s0, t);
     B::template mul_small_ni<NR>(t, s4);

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) msm_dedup_group_kernel(const uint32_t *__
 template <class FrP>
 static int msm_dedup_scalars(const void *d_scalars, size_t n, const MsmDedup &dd, MsmWorkspace &ws) {
   typedef Fp<FrP> F;
-  cudaStream_t st = ws.stream;
+  cudaStream_t st = ws.prep_stream;
   B200_CHECK(ws.merged_scalars.reserve(n * sizeof(F)));
   B200_CUDA_CHECK(cudaMemcpyAsync(ws.merged_scalars.p, d_scalars, n * sizeof(F), cudaMemcpyDeviceToDevice, st));
   msm_dedup_segment_kernel<FrP><<<dd.nsegments, 128, 0, st>>>((const F *)d_scalars, dd.members.as<uint32_t>(),
@@ -344,6 +344,8 @@ MsmWorkspace &msm_workspace_slot(int slot) {
       cudaStreamCreateWithPriority(&ws.stream, cudaStreamNonBlocking, g_high_priority ? greatest : least);
       ws.acc_stream = ws.stream;
     }
+    cudaStreamCreateWithPriority(&ws.prep_stream, cudaStreamNonBlocking, greatest);
+    cudaEventCreateWithFlags(&ws.aff_ready, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ws.acc_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ws.prep_done, cudaEventDisableTiming);
     ws.prepared = new MsmPlan();
@@ -392,7 +394,18 @@ int msm_prepare(int fr_tag, const void *d_scalars, size_t n, MsmPlan &plan, cons
   const int merged = plan.merged ? 1 : 0;
   const size_t nbuckets = plan.nbuckets;
   MsmWorkspace &ws = msm_workspace();
-  cudaStream_t st = ws.stream;
+  cudaStream_t st = ws.prep_stream;
+  {
+    // this workspace's previous MSM may still be reading the arrays that are rebuilt here
+    static thread_local cudaEvent_t prev = nullptr;
+    if (!prev) B200_CUDA_CHECK(cudaEventCreateWithFlags(&prev, cudaEventDisableTiming));
+    B200_CUDA_CHECK(cudaEventRecord(prev, ws.stream));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(st, prev, 0));
+    if (ws.acc_stream != ws.stream) {
+      B200_CUDA_CHECK(cudaEventRecord(prev, ws.acc_stream));
+      B200_CUDA_CHECK(cudaStreamWaitEvent(st, prev, 0));
+    }
+  }
   {
     // inputs are produced on the default stream (copies, compute_H, generators): order this MSM after it
     static thread_local cudaEvent_t fence = nullptr;
@@ -605,7 +618,7 @@ __global__ void __launch_bounds__(256) msm_affine_pairs_kernel(const uint32_t *_
 int msm_affine_levels(const uint32_t *counts, const uint32_t *offsets, uint32_t nbuckets, uint32_t max_count,
                       std::vector<size_t> &totals) {
   MsmWorkspace &ws = msm_workspace();
-  cudaStream_t st = ws.stream;
+  cudaStream_t st = ws.prep_stream;
   int rounds = 0;
   for (uint32_t c = max_count; c > 1; c = (c + 1) / 2) rounds++;
   totals.assign(rounds + 1, 0);
@@ -651,7 +664,7 @@ int msm_base_flags(const void *d_points, size_t n, size_t point_bytes, DevBuf &f
 int msm_affine_pairs(MsmWorkspace &ws, const uint32_t *cnt, const uint32_t *off, uint32_t nbuckets,
                      const std::vector<size_t> &totals, const uint32_t *entries, const uint8_t *base_is_O, size_t n_bases,
                      std::vector<size_t> &pair_off) {
-  cudaStream_t st = ws.stream;
+  cudaStream_t st = ws.prep_stream;
   const int rounds = (int)totals.size() - 1;
   pair_off.assign(rounds + 2, 0);
   for (int r = 1; r <= rounds; r++) pair_off[r + 1] = pair_off[r] + totals[r];

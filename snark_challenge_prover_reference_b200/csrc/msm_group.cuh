@@ -635,11 +635,20 @@ int msm_accumulate_batch_affine(const void *d_points, size_t n_bases, const MsmP
   cudaStream_t st = ws.stream;
   const size_t nbuckets = plan.nbuckets;
   std::vector<size_t> totals, pair_off;
-  B200_CHECK(msm_base_flags(d_points, n_bases, sizeof(Affine<F>), ws.base_flags, st));
+  // bookkeeping (levels, operand pairs, O flags of the bases) on the high-priority preparation stream
+  B200_CUDA_CHECK(cudaStreamWaitEvent(ws.prep_stream, pw.prep_done, 0));
+  {
+    // the previous MSM of this workspace may still read the pair / flag arrays
+    B200_CUDA_CHECK(cudaEventRecord(ws.aff_ready, st));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(ws.prep_stream, ws.aff_ready, 0));
+  }
+  B200_CHECK(msm_base_flags(d_points, n_bases, sizeof(Affine<F>), ws.base_flags, ws.prep_stream));
   B200_CHECK(msm_affine_levels(pw.counts.as<uint32_t>(), pw.offsets.as<uint32_t>(), (uint32_t)nbuckets, plan.max_count, totals));
   const int rounds = (int)totals.size() - 1;
   const uint32_t *cnt = ws.aff_cnt.as<uint32_t>(), *off = ws.aff_off.as<uint32_t>();
   B200_CHECK(msm_affine_pairs(ws, cnt, off, (uint32_t)nbuckets, totals, entries, ws.base_flags.as<uint8_t>(), n_bases, pair_off));
+  B200_CUDA_CHECK(cudaEventRecord(ws.aff_ready, ws.prep_stream));
+  B200_CUDA_CHECK(cudaStreamWaitEvent(st, ws.aff_ready, 0));
   static int wave = 0;  // resident threads of one full wave of the round kernel
   if (!wave) {
     int per_sm = 0, dev = 0, sms = 0;
@@ -720,7 +729,8 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
     plan = *prep_ws->prepared;
     B200_CUDA_CHECK(cudaStreamWaitEvent(st, prep_ws->prep_done, 0));
   } else {
-    B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan, dedup));
+    B200_CHECK(msm_prepare(FrP::kTag == 'A' ? 0 : 1, d_scalars, n, plan, dedup));  // on ws.prep_stream
+    B200_CUDA_CHECK(cudaStreamWaitEvent(st, ws.prep_done, 0));
   }
   MsmWorkspace &pw = *prep_ws;  // owner of entries / offsets / task arrays
   const uint32_t *entries = pw.entries.as<uint32_t>();
@@ -910,9 +920,13 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<typena
     for (int j = 0; j < W; j++) table[(size_t)j * n + i] = a;
     return;
   }
+  // Jacobian coordinates (jac_dbl: 1M + 8S per doubling, squarings through the dedicated squaring): the table builder
+  // is 753 doublings per base and nothing else
   F zs[MAXW], prefix[MAXW];
-  Proj<F> cur;
-  proj_from_affine(cur, a);
+  Proj<F> cur;  // (X : Y : Z) read as Jacobian here: x = X/Z^2, y = Y/Z^3
+  cur.X = a.x;
+  cur.Y = a.y;
+  F::set_one(cur.Z);
   for (int j = 0; j < W; j++) {
     // stash X, Y in the output slot, keep Z and the running product of Z's
     Affine<F> xy;
@@ -924,19 +938,21 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const Affine<typena
     else F::mul(prefix[j], prefix[j - 1], cur.Z);
     if (j + 1 < W) {
       uint32_t width = plan[j] >> 16;
-      for (uint32_t k = 0; k < width; k++) proj_dbl<G>(cur, cur);
+      for (uint32_t k = 0; k < width; k++) jac_dbl<G>(cur, cur);
     }
   }
   F inv;
   F::inv(inv, prefix[W - 1]);
   for (int j = W - 1; j >= 0; j--) {
-    F zinv;
+    F zinv, zinv2;
     if (j > 0) F::mul(zinv, inv, prefix[j - 1]);
     else zinv = inv;
     F::mul(inv, inv, zs[j]);
     Affine<F> xy = table[(size_t)j * n + i];
-    F::mul(xy.x, xy.x, zinv);
-    F::mul(xy.y, xy.y, zinv);
+    F::sqr(zinv2, zinv);
+    F::mul(xy.x, xy.x, zinv2);      // X / Z^2
+    F::mul(zinv2, zinv2, zinv);
+    F::mul(xy.y, xy.y, zinv2);      // Y / Z^3
     table[(size_t)j * n + i] = xy;
   }
 }

@@ -46,6 +46,12 @@ struct MsmWorkspace {
   // kernel. The block scheduler serves pending blocks of high-priority streams first, so the latency-bound phases of
   // one MSM (and compute_H) run in the slots that free up while another MSM's accumulation saturates the multiplier.
   cudaStream_t stream = nullptr, acc_stream = nullptr;
+  // The scalar-side preparation (digits, counting sort, task lists, batch-affine bookkeeping) runs on a stream of the
+  // HIGHEST priority: its kernels are tiny, the issuing host thread has to wait for two of their results (task count,
+  // largest bucket), and on the MSM's own low-priority stream they queue behind the accumulation grids of the MSMs
+  // issued before - at 8 GPUs (150 K points per rank) the host spent 25 ms of an 88 ms proof blocked there.
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t aff_ready = nullptr;
   cudaEvent_t acc_done = nullptr;
   cudaEvent_t tm_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // diagnostics: digits start/end, sort start/end
   // ring of pinned staging buffers + events for the asynchronous copy of the window sums to the host

@@ -133,3 +133,27 @@ def test_equal_bases_are_grouped_on_the_host(b200):
     # nothing to merge
     merged, groups = b200.host_equal_bases(b"".join(pts[3601:3700]), 99, pb)
     assert merged == 0 and groups == []
+
+
+def test_jacobian_doubling_of_the_table_builder_matches_oracle(b200, oracle):
+    """jac_dbl (curve.cuh: the doubling msm_precompute_kernel runs 753 times per base) against the oracle's projective
+    doubling, all four groups, host instantiation of the template the device compiles too."""
+    import ctypes
+    import random
+    import mnt753 as M
+    for curve in (0, 1):
+        c = util.curve_obj(curve)
+        for group in (1, 2):
+            rng = random.Random(50 + 2 * curve + group)
+            G = b200.g_from_affine(curve, group, util.generator_affine(curve, group))
+            k = util.fe_bytes(M.to_mont(rng.randrange(2, c.r), c.r))
+            P = util.orc_group(oracle, curve, group, 3, G, k)
+            xy = util.orc_to_affine(oracle, curve, group, P)
+            for nd in (1, 2, 21):
+                out = ctypes.create_string_buffer(len(xy))
+                src = ctypes.create_string_buffer(xy, len(xy))
+                b200.check(b200.lib().b200_host_jacobian_doublings(curve, group, ctypes.addressof(src), nd, ctypes.addressof(out)))
+                Q = P
+                for _ in range(nd):
+                    Q = util.orc_group(oracle, curve, group, 1, Q)
+                assert out.raw == util.orc_to_affine(oracle, curve, group, Q), (curve, group, nd)

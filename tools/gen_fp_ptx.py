@@ -246,16 +246,17 @@ def main():
         parts.append(emit_function(f"fp_mul_ptx_{tag}", gen_mul_body(p)))
         parts.append("")
         if "--experimental" in sys.argv:
-            # Two measured-and-rejected variants (kept in the generator with their interpreter tests, no longer emitted):
-            # one-level Karatsuba (round 1: -12 % wide MACs, multiplier pipe 94 % -> 84 % busy, no net gain) and the
-            # dedicated squaring (round 2: 876 instead of 1152 wide MACs; G1 accumulation 49.5 -> 49.0 ms, G2 160.7 ->
-            # 162.0 ms, i.e. noise: squarings are 2 of 10 multiplications and the longer carry chains cost what they save).
+            # measured and rejected (kept in the generator with its interpreter tests, not emitted): one-level Karatsuba
+            # (round 1: -12 % wide MACs, multiplier pipe 94 % -> 84 % busy, no net gain)
             kl, nk = gen_mul_karatsuba_body(p)
             parts.append(emit_function(f"fp_mulk_ptx_{tag}", kl, nk=nk))
             parts.append("")
-            sl, ns = gen_sqr_body(p)
-            parts.append(emit_function(f"fp_sqr_ptx_{tag}", sl, sqr=True, nk=ns))
-            parts.append("")
+        # dedicated squaring, 876 instead of 1152 wide MACs. NOT used by the bucket accumulation (round 2: squarings are
+        # 2 of its 10 multiplications; G1 49.5 -> 49.0 ms, G2 160.7 -> 162.0 ms, noise), but by the base-table builder,
+        # whose Jacobian doublings are 8 squarings + 1 multiplication (Fp::sqr_fast).
+        sl, ns = gen_sqr_body(p)
+        parts.append(emit_function(f"fp_sqr_ptx_{tag}", sl, sqr=True, nk=ns))
+        parts.append("")
         parts.append(emit_function(f"fp_add_ptx_{tag}", gen_add_body(p)))
         parts.append("")
         parts.append(emit_function(f"fp_sub_ptx_{tag}", gen_sub_body(p)))
