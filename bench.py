@@ -269,27 +269,55 @@ def regroup_partials(blobs, pbytes):
     return out
 
 
+PLAN_UNITS = 64   # an uneven split of the large proof is expressed in runs of 1/64 slices (b200_prove_partial_span)
+# model behind the "balanced" plan, from this round's single-GPU measurements (profiles/r02_summary.md): the MNT4753
+# proof costs a fixed ~25 ms (replicated compute_H, bucket reductions, preparation) plus ~365 ms x the rank's share of
+# the points; the whole MNT6753 proof adds ~40 ms to a rank that also works on MNT4753 (its latency-bound kernels hide
+# partly under the accumulations)
+PLAN_MODEL = {"mnt4_fixed_ms": 25.0, "mnt4_per_share_ms": 365.0, "mnt6_whole_ms": 40.0}
+
+
 def step_plan(world, mode=None):
     """Who proves what in one step. Only the 2^20 MNT4753 proof is worth sharding: one rank's share of the 2^15 MNT6753
-    proof would be 4096 points at N = 8, all latency. From 4 GPUs on the small proof runs WHOLE on the last rank while
-    the other N-1 ranks share the large one ("dedicated"); below that both are sharded over all ranks ("shard").
-    Returns (mode, ranks sharing MNT4753, rank proving MNT6753 or None when it is sharded too)."""
-    mode = mode or os.environ.get("B200_BENCH_MNT6_MODE") or ("dedicated" if world >= 4 else "shard")
+    proof would be 4096 points at N = 8, all latency. Plans:
+      shard     both proofs cut into `world` equal slices (round 1);
+      dedicated MNT6753 whole on the last rank, MNT4753 over the other N-1 ranks in equal slices;
+      balanced  (default for N >= 2) MNT6753 whole on the last rank, which ALSO takes a smaller run of MNT4753 slices,
+                sized so that all ranks finish together under PLAN_MODEL.
+    Returns (mode, runs, small_rank): runs[r] = (lo, hi) in units of 1/PLAN_UNITS of the MNT4753 point ranges (lo == hi:
+    the rank takes no part in it); small_rank = the rank proving MNT6753 whole, or None when it is sharded too."""
+    mode = mode or os.environ.get("B200_BENCH_MNT6_MODE") or ("balanced" if world >= 2 else "shard")
+    U = PLAN_UNITS
     if world == 1 or mode == "shard":
-        return "shard", list(range(world)), None
-    return "dedicated", list(range(world - 1)), world - 1
+        cuts = [r * U // world for r in range(world)] + [U]
+        return "shard", [(cuts[r], cuts[r + 1]) for r in range(world)], None
+    if mode == "dedicated":
+        cuts = [r * U // (world - 1) for r in range(world - 1)] + [U]
+        return "dedicated", [(cuts[r], cuts[r + 1]) for r in range(world - 1)] + [(U, U)], world - 1
+    M = PLAN_MODEL
+    per_other = M["mnt4_per_share_ms"] / (world - 1)
+    x = max(0.0, (per_other - M["mnt6_whole_ms"]) / (M["mnt4_per_share_ms"] + per_other))
+    last = int(round(x * U))
+    rest = U - last
+    cuts = [r * rest // (world - 1) for r in range(world - 1)] + [rest, U]
+    return "balanced", [(cuts[r], cuts[r + 1]) for r in range(world)], world - 1
 
 
 def rank_jobs(rank, world, mode=None):
-    """this rank's share of a step: [(proof index, rank within that proof's group, size of the group)]"""
-    mode, big_ranks, small_rank = step_plan(world, mode)
+    """this rank's share of a step: [(proof index, first slice, number of slices the proof is cut into, end slice)] -
+    the rank sums slices [first, end) of every MSM of that proof; (i, 0, 1, 1) = the whole proof"""
+    mode, runs, small_rank = step_plan(world, mode)
     jobs = []
-    if rank in big_ranks:
-        jobs.append((0, big_ranks.index(rank), len(big_ranks)))
+    lo, hi = runs[rank]
+    if hi > lo:
+        jobs.append((0, lo, PLAN_UNITS, hi) if world > 1 else (0, 0, 1, 1))
     if small_rank is None:
-        jobs.append((1, rank, world))
+        if world > 1:
+            jobs.append((1, rank, world, rank + 1))
+        else:
+            jobs.append((1, 0, 1, 1))
     elif rank == small_rank:
-        jobs.append((1, 0, 1))
+        jobs.append((1, 0, 1, 1))
     return jobs
 
 
@@ -297,16 +325,17 @@ def pack_rank_blob(jobs, outs, slot):
     """what one rank contributes to the step's all_gather: per proof a fixed-size slot holding its partial sums (or,
     for a proof it ran whole, the finished proof), zeros where it took no part"""
     blob = bytearray(sum(slot))
-    for (i, _, _), o in zip(jobs, outs):
-        off = sum(slot[:i])
+    for job, o in zip(jobs, outs):
+        off = sum(slot[:job[0]])
         blob[off:off + len(o)] = o
     return blob
 
 
 def combine_step(pkg, blobs, world, slot, pbytes, proof_len, r_fr, mode=None):
     """rank 0: the gathered blobs -> the step's two proofs"""
-    _, big_ranks, small_rank = step_plan(world, mode)
+    _, runs, small_rank = step_plan(world, mode)
     parts = regroup_partials(blobs, slot)
+    big_ranks = [r for r in range(world) if runs[r][1] > runs[r][0]]
     big = b"".join(parts[0][r * slot[0]:r * slot[0] + pbytes[0]] for r in big_ranks)
     proofs = [pkg.prove_combine(0, big, len(big_ranks), r_fr[0])]
     if small_rank is None:
@@ -392,8 +421,8 @@ def b200_arm(args):
     k4, k6 = args.log2_mnt4, args.log2_mnt6
     shapes = ((0, k4), (1, k6))
     files = ensure_synth(k4, k6, wait_only=local != 0)
-    mode, big_ranks, small_rank = step_plan(world)
-    my_jobs = rank_jobs(rank, world)  # (index into shapes, rank within the proof's group, size of that group)
+    mode, runs, small_rank = step_plan(world)
+    my_jobs = rank_jobs(rank, world)  # (index into shapes, first slice, slices per proof, end slice)
     # the drop-in path, measured before this process takes its own 100 GB of HBM (separate processes, N = 1 only)
     drop_in = drop_in_run(files) if world == 1 and not args.no_cpu_baseline else None
 
@@ -401,15 +430,15 @@ def b200_arm(args):
     # loading (main.cpp:200-203); both are reported
     keys, load_ms, preprocess_s = {}, {}, {}
     pkg.set_precompute(True)
-    for i, r, w in my_jobs:
+    for i, r, w, e in my_jobs:
         name = CURVES[i]
         t0 = time.perf_counter()
         keys[i] = pkg.Params.from_file(shapes[i][0], os.path.join(files, name + "-parameters"))
         load_ms[name] = dict(keys[i].load_ms(), wall=1e3 * (time.perf_counter() - t0))
-        preprocess_s[name] = keys[i].precompute(r, w)
+        preprocess_s[name] = keys[i].precompute(r, w, e)
     import numpy as np
     host_inputs, dev_inputs = {}, {}
-    for i, _, _ in my_jobs:
+    for i, _, _, _ in my_jobs:
         raw = np.fromfile(os.path.join(files, CURVES[i] + "-input"), dtype=np.uint8)
         host_inputs[i] = torch.from_numpy(raw).pin_memory()
         dev_inputs[i] = host_inputs[i].to(dev)
@@ -424,9 +453,9 @@ def b200_arm(args):
         partial sums (or finished small proof), rank 0 combines. Returns the two proofs' bytes on rank 0."""
         t0 = time.perf_counter()
         if world == 1:
-            proofs, tms = pkg.prove_batch([(keys[i], inputs[i]) for i, _, _ in my_jobs], timings=True)
+            proofs, tms = pkg.prove_batch([(keys[i], inputs[i]) for i, _, _, _ in my_jobs], timings=True)
         else:
-            jobs = [(keys[i], inputs[i], r, w) if w > 1 else (keys[i], inputs[i]) for i, r, w in my_jobs]
+            jobs = [(keys[i], inputs[i], r, w, e) if w > 1 else (keys[i], inputs[i]) for i, r, w, e in my_jobs]
             outs, tms = pkg.prove_batch(jobs, timings=True) if jobs else ([], [])
             mine = torch.frombuffer(pack_rank_blob(my_jobs, outs, slot), dtype=torch.uint8).to(dev)
             allp = [torch.empty_like(mine) for _ in range(world)]
@@ -437,7 +466,7 @@ def b200_arm(args):
                 proofs = combine_step(pkg, blobs, world, slot, pbytes, proof_len, r_fr)
         if timings is not None:
             wall = time.perf_counter() - t0
-            for (i, _, _), tm in zip(my_jobs, tms):
+            for (i, _, _, _), tm in zip(my_jobs, tms):
                 # latency of this proof inside the concurrent step (its own call's wall clock); step_wall_s = both
                 tm["wall_s"] = tm["total_ms"] / 1e3
                 tm["step_wall_s"] = wall
@@ -478,11 +507,11 @@ def b200_arm(args):
     sampler.join(timeout=2)
     # bytes this rank moves per e2e step: its slice of w (b200_prove_partial uploads only what its MSM slices read) plus
     # ca, cb, cc in full (compute_H is replicated); back come the partial sums or the finished proof
-    def slice_len(n, r, w):
-        one = n // w
-        return n - r * one if r == w - 1 else one
-    my_h2d = sum(FE * (slice_len((1 << shapes[i][1]) + 1, r, w) + 3 * (1 << shapes[i][1]) + 1) for i, r, w in my_jobs)
-    my_d2h = sum(pbytes[i] if w > 1 else proof_len[i] for i, _, w in my_jobs)
+    def slice_len(n, r, w, e):
+        cut = lambda k: n if k >= w else k * (n // w)
+        return cut(e) - cut(r)
+    my_h2d = sum(FE * (slice_len((1 << shapes[i][1]) + 1, r, w, e) + 3 * (1 << shapes[i][1]) + 1) for i, r, w, e in my_jobs)
+    my_d2h = sum(pbytes[i] if w > 1 else proof_len[i] for i, _, w, _ in my_jobs)
     h2d_list, d2h_list = [my_h2d], [my_d2h]
     if world > 1:
         lt = torch.tensor([launches, my_h2d, my_d2h], device=dev, dtype=torch.int64)
@@ -639,7 +668,7 @@ def b200_arm(args):
                        "files": "tools/synth_key output in the reference's formats; the reference arm proves the same files",
                        "l2": "inputs larger than L2: each step streams >1.6 GB of bases and 416 MB of scalars",
                        "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys",
-                       "multi_gpu": {"mode": mode, "mnt4753_ranks": big_ranks, "mnt6753_rank": small_rank},
+                       "multi_gpu": {"mode": mode, "mnt4753_runs_of_%d" % PLAN_UNITS: runs, "mnt6753_rank": small_rank},
                        "accumulation": lib_mode + " (auto = batched affine additions for large G2/Fq2 MSMs, XYZZ mixed additions otherwise)",
                        "key_preprocess": "pre-shifted base tables 2^(start_j)*P_i per MSM window, built once per key, "
                                          "outside the timed region (see key_load); see no_tables"},

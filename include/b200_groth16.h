@@ -162,6 +162,12 @@ int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_
                b200_prove_timings *timings);
 int b200_prove_partial(b200_params *p, const void *h_input, size_t input_bytes, int rank, int world,
                        void *h_partials, size_t *partial_bytes, b200_prove_timings *timings);
+/* Uneven sharding: the caller owns the run [rank, rank_end) of `world` equal slices (b200_prove_partial is the run of
+ * length one). A GPU that also proves another curve takes a shorter run; the partial sums of any set of runs that
+ * tile [0, world) combine to the proof. b200_params_precompute_span builds the base tables for such a run. */
+int b200_prove_partial_span(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
+                            void *h_partials, size_t *partial_bytes, b200_prove_timings *timings);
+int b200_params_precompute_span(b200_params *p, int rank, int rank_end, int world);
 /* combine `world` partial results (rank-major, as produced by b200_prove_partial) into the final proof */
 int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
                        size_t *out_bytes);
@@ -178,6 +184,7 @@ typedef struct {
   void *h_out;
   size_t out_bytes; /* set by the call */
   int rank, world;
+  int rank_end; /* world > 1: the job owns slices [rank, rank_end) of world; 0 means rank + 1 */
   int status; /* set by the call: 0 or the job's error code */
   b200_prove_timings timings;
 } b200_proof_job;

@@ -149,7 +149,7 @@ struct b200_domain {
 
 // Pre-shifted base tables for one (rank, world) slicing of the five queries (see msm_precompute_kernel).
 struct Precomputed {
-  int rank = -1, world = -1;
+  int rank = -1, rank_end = -1, world = -1;  // the slicing the tables were built for: virtual ranks [rank, rank_end) of world
   DevBuf table[5];
   MsmPlan plan[5];
   MsmDedup dedup[5];  // equal bases inside this rank's slice of each G1 query (job order A, B1, B2, H, L)
@@ -687,15 +687,17 @@ const void *b200_params_query(const b200_params *p, int which) { return (which >
 // that a rank's scalars are ONE range of w - A / B1 / B2 take points [lo1, hi1) of m+1, and L, whose point i belongs to
 // w[i + 2] (main.cpp:247-250), takes points [lo1 - 2, hi1 - 2) clipped to [0, m-1) - so the four MSMs of a rank share
 // one digit extraction and one counting sort at every world size.
-static void query_slice(size_t d, size_t m, int qi, int rank, int world, size_t &lo, size_t &hi) {
+// A caller may own a RUN of consecutive slices, [rank, rank_end) of `world` (uneven sharding: bench.py gives the GPU
+// that also proves the small curve a smaller share of the large one); its range is their union.
+static void query_slice(size_t d, size_t m, int qi, int rank, int rank_end, int world, size_t &lo, size_t &hi) {
+  auto cut = [&](size_t n, int r) -> size_t { return r >= world ? n : (size_t)r * (n / (size_t)world); };
   if (qi == 4) {
-    const size_t one = d / (size_t)world;
-    lo = (size_t)rank * one;
-    hi = rank == world - 1 ? d : lo + one;
+    lo = cut(d, rank);
+    hi = cut(d, rank_end);
     return;
   }
-  const size_t n1 = m + 1, one = n1 / (size_t)world;
-  const size_t lo1 = (size_t)rank * one, hi1 = rank == world - 1 ? n1 : lo1 + one;
+  const size_t n1 = m + 1;
+  const size_t lo1 = cut(n1, rank), hi1 = cut(n1, rank_end);
   if (qi != 3) {
     lo = lo1;
     hi = hi1;
@@ -708,14 +710,16 @@ static void query_slice(size_t d, size_t m, int qi, int rank, int world, size_t 
 }
 
 // Build (once per key and slicing) the tables of pre-shifted bases for this rank's slice of the five queries.
-int b200_params_precompute(b200_params *p, int rank, int world) {
+int b200_params_precompute(b200_params *p, int rank, int world) { return b200_params_precompute_span(p, rank, rank + 1, world); }
+int b200_params_precompute_span(b200_params *p, int rank, int rank_end, int world) {
   B200_CHECK(require_device());
-  if (world < 1 || rank < 0 || rank >= world) return set_error(-1, "bad rank/world %d/%d", rank, world);
-  if (p->pre.rank == rank && p->pre.world == world) return 0;
+  if (world < 1 || rank < 0 || rank_end < rank || rank_end > world)
+    return set_error(-1, "bad slice run [%d, %d) of %d", rank, rank_end, world);
+  if (p->pre.rank == rank && p->pre.rank_end == rank_end && p->pre.world == world) return 0;
   double t0 = now_ms();
   const size_t d = p->d, m = p->m;
   const int jobq[5] = {0, 1, 2, 4, 3};                     // job order A, B1, B2, H, L -> query index
-  p->pre.rank = p->pre.world = -1;
+  p->pre.rank = p->pre.rank_end = p->pre.world = -1;
   // The grouping of equal bases (host: hash + sort of the G1 queries' wire bytes) runs on a thread of its own, under
   // the table kernels.
   int dev = 0;
@@ -725,7 +729,7 @@ int b200_params_precompute(b200_params *p, int rank, int world) {
   for (int j = 0; j < 5; j++) {
     const int qi = jobq[j];
     size_t lo, hi;
-    query_slice(d, m, qi, rank, world, lo, hi);
+    query_slice(d, m, qi, rank, rank_end, world, lo, hi);
     slices[j].group = qi == 2 ? 2 : 1;
     slices[j].pts = (const char *)p->q[qi] + lo * affine_bytes(p->curve, slices[j].group);
     slices[j].n = hi - lo;
@@ -757,6 +761,7 @@ int b200_params_precompute(b200_params *p, int rank, int world) {
   if (rc) return rc;
   if (dedup_rc) return set_error(dedup_rc, "%s", dedup_err.c_str());
   p->pre.rank = rank;
+  p->pre.rank_end = rank_end;
   p->pre.world = world;
   p->pre.build_ms = now_ms() - t0;
   return 0;
@@ -829,12 +834,13 @@ int b200_msm_wait(b200_msm_pending *pending) {
 
 // Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
 // multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
-static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, int rank, int world,
+static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
                           unsigned char *partials, b200_prove_timings *tm) {
   const size_t d = p->d, m = p->m;
   const size_t need = 96 * ((m + 1) + 3 * (d + 1) + 1);
   if (input_bytes != need) return set_error(-4, "input image has %zu bytes, expected %zu", input_bytes, need);
-  if (world < 1 || rank < 0 || rank >= world) return set_error(-1, "bad rank/world %d/%d", rank, world);
+  if (world < 1 || rank < 0 || rank_end < rank || rank_end > world)
+    return set_error(-1, "bad slice run [%d, %d) of %d", rank, rank_end, world);
   const char *in = (const char *)h_input;
   double t0 = now_ms();
   // w first (it drives four of the five MSMs); ca/cb/cc follow asynchronously on the default stream right before
@@ -842,14 +848,14 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   // (a rank of a sharded proof only needs the part of w its slices of A/B1/B2 (w[i]) and L (w[i+2]) read)
   {
     size_t lo, hi;
-    query_slice(d, m, 0, rank, world, lo, hi);  // covers L's scalars w[lo3 + 2 .. hi3 + 2) too (query_slice)
+    query_slice(d, m, 0, rank, rank_end, world, lo, hi);  // covers L's scalars w[lo3 + 2 .. hi3 + 2) too (query_slice)
     B200_CUDA_CHECK(cudaMemcpy((char *)p->w.p + lo * 96, in + lo * 96, (hi - lo) * 96, cudaMemcpyDefault));
   }
   double t1 = now_ms();
   const int curve = p->curve;
   const size_t g1a = affine_bytes(curve, 1), g2a = affine_bytes(curve, 2);
   const size_t g1p = proj_bytes(curve, 1), g2p = proj_bytes(curve, 2);
-  if (use_precompute()) B200_CHECK(b200_params_precompute(p, rank, world));
+  if (use_precompute()) B200_CHECK(b200_params_precompute_span(p, rank, rank_end, world));
   struct Job { int group; const char *scalars; const char *points; size_t n; size_t stride; size_t outb; double *ms; };
   double ms[5] = {0, 0, 0, 0, 0};
   Job jobs[5] = {
@@ -890,7 +896,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     const Job &J = jobs[j];
     const int jobq[5] = {0, 1, 2, 4, 3};  // job -> query index
     size_t lo, hi;
-    query_slice(d, m, jobq[j], rank, world, lo, hi);
+    query_slice(d, m, jobq[j], rank, rank_end, world, lo, hi);
     double a = now_ms();
     MsmTail tail;
     msm_select_slot(jj);
@@ -903,7 +909,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     MsmShare share;
     if (use_precompute() && !merges && hi > lo && p->pre.plan[j].c == p->pre.plan[2].c && share_prep_enabled()) {
       size_t lo1, hi1;
-      query_slice(d, m, 2, rank, world, lo1, hi1);
+      query_slice(d, m, 2, rank, rank_end, world, lo1, hi1);
       if (jj == 1 || jj == 2) share.slot = 0;
       if (jj == 3 && hi1 > lo1) {
         share.slot = 0;
@@ -950,8 +956,12 @@ static size_t partial_size(int curve) { return 4 * proj_bytes(curve, 1) + proj_b
 
 int b200_prove_partial(b200_params *p, const void *h_input, size_t input_bytes, int rank, int world, void *h_partials,
                        size_t *partial_bytes, b200_prove_timings *timings) {
+  return b200_prove_partial_span(p, h_input, input_bytes, rank, rank + 1, world, h_partials, partial_bytes, timings);
+}
+int b200_prove_partial_span(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
+                            void *h_partials, size_t *partial_bytes, b200_prove_timings *timings) {
   B200_CHECK(require_device());
-  B200_CHECK(prove_partials(p, h_input, input_bytes, rank, world, (unsigned char *)h_partials, timings));
+  B200_CHECK(prove_partials(p, h_input, input_bytes, rank, rank_end, world, (unsigned char *)h_partials, timings));
   if (partial_bytes) *partial_bytes = partial_size(p->curve);
   return 0;
 }
@@ -992,7 +1002,7 @@ int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_
   B200_CHECK(require_device());
   double t0 = now_ms();
   std::vector<unsigned char> part(partial_size(p->curve));
-  B200_CHECK(prove_partials(p, h_input, input_bytes, 0, 1, part.data(), timings));
+  B200_CHECK(prove_partials(p, h_input, input_bytes, 0, 1, 1, part.data(), timings));
   double t1 = now_ms();
   unsigned char r[96];  // the input image may live in host or device memory
   B200_CUDA_CHECK(cudaMemcpy(r, (const unsigned char *)h_input + input_bytes - 96, 96, cudaMemcpyDefault));
@@ -1113,8 +1123,8 @@ class ProofWorker {
 int run_proof_job(b200_proof_job *j) {
   if (!j->key || !j->h_input || !j->h_out) return set_error(-1, "proof job: null key, input or output");
   if (j->world > 1)
-    return b200_prove_partial(j->key, j->h_input, j->input_bytes, j->rank, j->world, j->h_out, &j->out_bytes,
-                              &j->timings);
+    return b200_prove_partial_span(j->key, j->h_input, j->input_bytes, j->rank, j->rank_end > j->rank ? j->rank_end : j->rank + 1,
+                                   j->world, j->h_out, &j->out_bytes, &j->timings);
   return b200_prove(j->key, j->h_input, j->input_bytes, j->h_out, &j->out_bytes, &j->timings);
 }
 }  // namespace

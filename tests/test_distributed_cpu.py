@@ -111,25 +111,26 @@ def test_two_rank_step_with_both_curves_in_one_gather():
     assert ret.get("ok") is True
 
 
-def _worker_dedicated(rank, world, port, ret):
-    """bench.py's plan from 4 GPUs on (forced here at world 2): the small proof runs WHOLE on the last rank, the other
-    ranks share the large one; one all_gather of fixed-size slots; rank 0 combines."""
+def _worker_plan(rank, world, port, mode, ret):
+    """bench.py's multi-GPU plans at world 2: the small proof WHOLE on the last rank, the large one in runs of 1/64
+    slices - none on the last rank ("dedicated") or a shorter run there ("balanced"); one all_gather of fixed-size
+    slots; rank 0 combines."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
     import snark_challenge_prover_reference_b200 as b200
     O = util.load_oracle()
-    cases = [(0, 5), (1, 5)]
+    cases = [(0, 8), (1, 5)]
     pbytes = [b200.partial_bytes(c) for c, _ in cases]
     proof_len = [b200.proof_bytes(c) for c, _ in cases]
     slot = [max(a, b) for a, b in zip(pbytes, proof_len)]
-    jobs = bench.rank_jobs(rank, world, "dedicated")
+    jobs = bench.rank_jobs(rank, world, mode)
     outs, r_fr = [], [util.golden(c, k)[1][-96:] for c, k in cases]
-    for i, r, w in jobs:
+    for i, first, units, end in jobs:
         curve, k = cases[i]
         if i == 0:
-            outs.append(_oracle_partials(b200, O, curve, k, r, w)[0])
+            outs.append(_oracle_partials_span(b200, O, curve, k, first, end, units))
         else:
             params, inp, _ = util.golden(curve, k)
             outs.append(util.orc_prove(O, curve, params, inp))
@@ -138,20 +139,51 @@ def _worker_dedicated(rank, world, port, ret):
     dist.all_gather(gathered, mine)
     if rank == 0:
         blobs = [t.numpy().tobytes() for t in gathered]
-        proofs = bench.combine_step(b200, blobs, world, slot, pbytes, proof_len, r_fr, "dedicated")
+        proofs = bench.combine_step(b200, blobs, world, slot, pbytes, proof_len, r_fr, mode)
         ret["ok"] = proofs == [util.golden(c, k)[2] for c, k in cases]
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_step_with_dedicated_small_proof_rank():
+def _oracle_partials_span(b200, O, curve, k, first, end, units):
+    """oracle partial sums over the run [first, end) of `units` slices, cut like b200_prove_partial_span (capi.cu
+    query_slice): A / B1 / B2 by m+1, L aligned to the same scalars, H by d"""
+    params, inp, _ = util.golden(curve, k)
+    d, m, q = util.split_params(curve, params)
+    x = util.split_input(inp, d, m)
+    H = util.orc_compute_h(O, curve, d, x["ca"], x["cb"], x["cc"])
+    cut = lambda n, r: n if r >= units else r * (n // units)
+    lo1, hi1 = cut(m + 1, first), cut(m + 1, end)
+    lo3, hi3 = max(lo1 - 2, 0), min(max(hi1 - 2, 0), m - 1)
+    jobs = [(1, x["w"], q["A"], lo1, hi1, 0), (1, x["w"], q["B1"], lo1, hi1, 0), (2, x["w"], q["B2"], lo1, hi1, 0),
+            (1, H, q["H"], cut(d, first), cut(d, end), 0), (1, x["w"], q["L"], lo3, max(hi3, lo3), 2)]
+    part = b""
+    for group, sc, pts, lo, hi, shift in jobs:
+        ab = b200.affine_bytes(curve, group)
+        out = ctypes.create_string_buffer(b200.proj_bytes(curve, group))
+        sb, pb = util.buf(sc[(lo + shift) * 96:(hi + shift) * 96]), util.buf(pts[lo * ab:hi * ab])
+        O.orc_msm(curve, group, ctypes.addressof(sb), ctypes.addressof(pb), hi - lo, ctypes.addressof(out), 1)
+        part += out.raw
+    return part
+
+
+@pytest.mark.parametrize("mode", ["dedicated", "balanced"])
+def test_two_rank_step_plans(mode):
     import bench
-    assert bench.step_plan(8)[:1] + bench.step_plan(8)[2:] == ("dedicated", 7) and bench.step_plan(8)[1] == list(range(7))
-    assert bench.step_plan(2) == ("shard", [0, 1], None) and bench.step_plan(1) == ("shard", [0], None)
-    assert bench.rank_jobs(7, 8) == [(1, 0, 1)] and bench.rank_jobs(3, 8) == [(0, 3, 7)] and bench.rank_jobs(1, 2) == [(0, 1, 2), (1, 1, 2)]
+    U = bench.PLAN_UNITS
+    for world in (2, 4, 8):
+        for md in ("shard", "dedicated", "balanced"):
+            m, runs, small = bench.step_plan(world, md)
+            assert runs[0][0] == 0 and runs[-1][1] == U and all(runs[r][1] == runs[r + 1][0] for r in range(world - 1)), (world, md, runs)
+            assert (small is None) == (md == "shard")
+    assert bench.step_plan(8, "dedicated")[1][-1] == (U, U) and bench.step_plan(1)[:1] == ("shard",)
+    b2 = bench.step_plan(2, "balanced")[1]
+    assert 0 < b2[1][1] - b2[1][0] < b2[0][1] - b2[0][0]   # the rank that also proves MNT6753 takes the shorter run
+    assert bench.rank_jobs(7, 8, "dedicated") == [(1, 0, 1, 1)] and bench.rank_jobs(1, 2, "shard") == [(0, U // 2, U, U), (1, 1, 2, 2)]
+    assert bench.rank_jobs(0, 1) == [(0, 0, 1, 1), (1, 0, 1, 1)]
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29950 + (os.getpid() % 40)
-    mp.spawn(_worker_dedicated, args=(world, port, ret), nprocs=world, join=True)
+    port = 29950 + (os.getpid() % 40) + (0 if mode == "dedicated" else 41)
+    mp.spawn(_worker_plan, args=(world, port, mode, ret), nprocs=world, join=True)
     assert ret.get("ok") is True

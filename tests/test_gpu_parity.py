@@ -385,6 +385,10 @@ def test_sharded_prover_matches_reference_golden(b200, dev, precompute, curve, a
     for world in (2, 3):
         parts = b"".join(P.prove_partial(inp, r, world)[0] for r in range(world))
         assert b200.prove_combine(curve, parts, world, inp[-FE:]) == expected
+    # uneven sharding: runs of 1/64 slices (b200_prove_partial_span), one of them empty
+    runs = [(0, 36), (36, 36), (36, 61), (61, 64)]
+    parts = b"".join(P.prove_partial(inp, lo, 64, hi)[0] for lo, hi in runs)
+    assert b200.prove_combine(curve, parts, len(runs), inp[-FE:]) == expected
     P.close()
 
 
