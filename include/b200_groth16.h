@@ -74,6 +74,13 @@ int b200_compute_h(b200_domain *dom, void *d_ca, void *d_cb, void *d_cc, void *d
  * libff::multi_exp_with_mixed_addition (multiexp.tcc:443-496). */
 int b200_msm_g1(int curve, const void *d_scalars, const void *d_points, size_t n, void *h_out_proj);
 int b200_msm_g2(int curve, const void *d_scalars, const void *d_points, size_t n, void *h_out_proj);
+/* Fixed-base MSM context: pre-shifted base tables for ANY point set (what a proving key builds for its five queries,
+ * without the key around it): create once per base set, run for every scalar vector over it. Used by the sharded size
+ * sweeps (each rank owns the table of its point range). */
+typedef struct b200_msm_ctx b200_msm_ctx;
+int b200_msm_ctx_create(int curve, int group, const void *d_points, size_t n, b200_msm_ctx **out);
+int b200_msm_ctx_run(b200_msm_ctx *ctx, const void *d_scalars, void *h_out_proj);
+int b200_msm_ctx_destroy(b200_msm_ctx *ctx);
 /* tuning hook: force the Pippenger window width (0 = automatic) */
 int b200_msm_set_window(int c);
 /* Bucket accumulation of every following MSM: 0 = XYZZ mixed additions, 1 = batched affine additions with

@@ -87,6 +87,9 @@ _SIGNATURES = {
     "b200_compute_h": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_msm_g1": (_i, [_i, _vp, _vp, _sz, _vp]),
     "b200_msm_g2": (_i, [_i, _vp, _vp, _sz, _vp]),
+    "b200_msm_ctx_create": (_i, [_i, _i, _vp, _sz, ctypes.POINTER(_vp)]),
+    "b200_msm_ctx_run": (_i, [_vp, _vp, _vp]),
+    "b200_msm_ctx_destroy": (_i, [_vp]),
     "b200_prove_batch": (_i, [_vp, _i]),
     "b200_prove_timeline": (_i, [_i, _vp]),
     "b200_host_equal_bases": (_i, [_vp, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
@@ -252,6 +255,27 @@ def msm_phase_totals(reset=False):
 
 def launch_count():
     return int(lib().b200_launch_count())
+
+
+class MsmContext:
+    """Pre-shifted base tables for an arbitrary point set (b200_msm_ctx_*): create once, run per scalar vector."""
+
+    def __init__(self, curve, group, d_points, n):
+        self.curve, self.group, self.n = curve, group, n
+        self.h = ctypes.c_void_p()
+        check(lib().b200_msm_ctx_create(curve, group, _ptr(d_points), n, ctypes.byref(self.h)))
+
+    def run(self, d_scalars):
+        out = ctypes.create_string_buffer(proj_bytes(self.curve, self.group))
+        check(lib().b200_msm_ctx_run(self.h, _ptr(d_scalars), ctypes.addressof(out)))
+        return out.raw
+
+    def close(self):
+        if self.h and _lib is not None:
+            _lib.b200_msm_ctx_destroy(self.h)
+        self.h = None
+
+    __del__ = close
 
 
 class Domain:

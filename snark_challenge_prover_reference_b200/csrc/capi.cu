@@ -368,6 +368,39 @@ int b200_msm_g2(int curve, const void *d_scalars, const void *d_points, size_t n
   B200_CHECK(require_device());
   return msm_dispatch(curve, 2, d_scalars, d_points, n, h_out);
 }
+struct b200_msm_ctx {
+  int curve, group;
+  size_t n;
+  DevBuf table;
+  MsmPlan plan;
+};
+int b200_msm_ctx_create(int curve, int group, const void *d_points, size_t n, b200_msm_ctx **out) {
+  B200_CHECK(require_device());
+  if ((curve != 0 && curve != 1) || (group != 1 && group != 2)) return set_error(-1, "bad curve/group %d/%d", curve, group);
+  if (n == 0 || !d_points) return set_error(-1, "msm_ctx_create: empty point set");
+  std::unique_ptr<b200_msm_ctx> c(new b200_msm_ctx());
+  c->curve = curve;
+  c->group = group;
+  c->n = n;
+  B200_CHECK(msm_precompute_dispatch(curve, group, d_points, n, c->plan, c->table));
+  *out = c.release();
+  return 0;
+}
+int b200_msm_ctx_run(b200_msm_ctx *ctx, const void *d_scalars, void *h_out) {
+  B200_CHECK(require_device());
+  MsmTail tail;
+  msm_select_slot(0);
+  B200_CHECK(msm_table_dispatch_deferred(ctx->curve, ctx->group, d_scalars, ctx->table.p, ctx->n, ctx->plan, h_out, tail,
+                                         MsmShare(), nullptr));
+  std::string err;
+  const int rc = tail(err);
+  if (rc) return set_error(rc, "%s", err.c_str());
+  return 0;
+}
+int b200_msm_ctx_destroy(b200_msm_ctx *ctx) {
+  delete ctx;
+  return 0;
+}
 int b200_msm_set_batch_affine(int on) {
   msm_set_batch_affine(on);
   return 0;
@@ -752,12 +785,17 @@ int b200_params_precompute_span(b200_params *p, int rank, int rank_end, int worl
     cudaStreamDestroy(st);
   });
   int rc = 0;
+  const bool verbose = getenv("B200_VERBOSE") != nullptr;
   for (int j = 0; j < 5 && rc == 0; j++) {
     p->pre.plan[j] = MsmPlan();
+    const double a = now_ms();
     if (slices[j].n > 0)
       rc = msm_precompute_dispatch(p->curve, slices[j].group, slices[j].pts, slices[j].n, p->pre.plan[j], p->pre.table[j]);
+    if (verbose) fprintf(stderr, "[b200] base table %d (G%d, %zu points, %d windows): %.0f ms\n", j, slices[j].group, slices[j].n, p->pre.plan[j].W, now_ms() - a);
   }
+  const double tj = now_ms();
   dedup_thread.join();
+  if (verbose) fprintf(stderr, "[b200] waited %.0f ms for the equal-base grouping\n", now_ms() - tj);
   if (rc) return rc;
   if (dedup_rc) return set_error(dedup_rc, "%s", dedup_err.c_str());
   p->pre.rank = rank;

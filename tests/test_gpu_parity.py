@@ -599,3 +599,23 @@ def test_batch_exp_vs_oracle(b200, oracle, dev, curve, group, window):
     for i in range(n):
         exp = util.orc_to_affine(oracle, curve, group, util.orc_group(oracle, curve, group, 3, base_proj, sc[i * FE:(i + 1) * FE]))
         assert got[i * ab:(i + 1) * ab] == exp, (curve, group, window, i)
+
+
+@pytest.mark.parametrize("curve,group", [(0, 1), (1, 2)])
+def test_msm_context_vs_oracle(b200, oracle, dev, curve, group, accum):
+    """b200_msm_ctx_*: pre-shifted base tables for an arbitrary point set (what the sharded sweeps use per rank)"""
+    import torch
+    c = util.curve_obj(curve)
+    n = 257
+    ab = b200.affine_bytes(curve, group)
+    pts = torch.empty(n * ab, dtype=torch.uint8, device=dev)
+    b200.check(b200.lib().b200_gen_points(curve, group, pts.data_ptr(), n, 4242))
+    points = bytearray(b200.from_device(pts))
+    points[3 * ab:4 * ab] = bytes(ab)             # a point at infinity
+    points[9 * ab:10 * ab] = points[8 * ab:9 * ab]  # a duplicate pair
+    sc = _scalars_with_specials(curve, n, 9400 + curve)
+    ctx = b200.MsmContext(curve, group, b200.to_device(bytes(points)), n)
+    for _ in range(2):
+        got = b200.g_to_affine(curve, group, ctx.run(b200.to_device(sc)))
+        assert got == util.orc_msm_affine(oracle, curve, group, sc, bytes(points), n)
+    ctx.close()
