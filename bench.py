@@ -454,9 +454,11 @@ def b200_arm(args):
         t0 = time.perf_counter()
         if world == 1:
             proofs, tms = pkg.prove_batch([(keys[i], inputs[i]) for i, _, _, _ in my_jobs], timings=True)
+            busy = time.perf_counter() - t0
         else:
             jobs = [(keys[i], inputs[i], r, w, e) if w > 1 else (keys[i], inputs[i]) for i, r, w, e in my_jobs]
             outs, tms = pkg.prove_batch(jobs, timings=True) if jobs else ([], [])
+            busy = time.perf_counter() - t0
             mine = torch.frombuffer(pack_rank_blob(my_jobs, outs, slot), dtype=torch.uint8).to(dev)
             allp = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allp, mine)
@@ -470,6 +472,7 @@ def b200_arm(args):
                 # latency of this proof inside the concurrent step (its own call's wall clock); step_wall_s = both
                 tm["wall_s"] = tm["total_ms"] / 1e3
                 tm["step_wall_s"] = wall
+                tm["busy_s"] = busy
                 tm["curve"] = CURVES[i]
                 timings.append(tm)
         return proofs
@@ -513,6 +516,14 @@ def b200_arm(args):
     my_h2d = sum(FE * (slice_len((1 << shapes[i][1]) + 1, r, w, e) + 3 * (1 << shapes[i][1]) + 1) for i, r, w, e in my_jobs)
     my_d2h = sum(pbytes[i] if w > 1 else proof_len[i] for i, _, w, _ in my_jobs)
     h2d_list, d2h_list = [my_h2d], [my_d2h]
+    # every rank's own time inside b200_prove_batch per step (what the plan tries to equalise)
+    my_busy = statistics.mean(t["busy_s"] for t in tms_dev) * 1e3 if tms_dev else 0.0
+    rank_busy_ms = [my_busy]
+    if world > 1:
+        bt = torch.zeros(world, device=dev, dtype=torch.float64)
+        bt[rank] = my_busy
+        dist.all_reduce(bt)
+        rank_busy_ms = [round(float(v), 2) for v in bt.tolist()]
     if world > 1:
         lt = torch.tensor([launches, my_h2d, my_d2h], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
@@ -668,7 +679,8 @@ def b200_arm(args):
                        "files": "tools/synth_key output in the reference's formats; the reference arm proves the same files",
                        "l2": "inputs larger than L2: each step streams >1.6 GB of bases and 416 MB of scalars",
                        "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys",
-                       "multi_gpu": {"mode": mode, "mnt4753_runs_of_%d" % PLAN_UNITS: runs, "mnt6753_rank": small_rank},
+                       "multi_gpu": {"mode": mode, "mnt4753_runs_of_%d" % PLAN_UNITS: runs, "mnt6753_rank": small_rank,
+                                     "rank_busy_ms_per_step": rank_busy_ms},
                        "accumulation": lib_mode + " (auto = batched affine additions for large G2/Fq2 MSMs, XYZZ mixed additions otherwise)",
                        "key_preprocess": "pre-shifted base tables 2^(start_j)*P_i per MSM window, built once per key, "
                                          "outside the timed region (see key_load); see no_tables"},
