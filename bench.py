@@ -271,10 +271,10 @@ def regroup_partials(blobs, pbytes):
 
 PLAN_UNITS = 64   # an uneven split of the large proof is expressed in runs of 1/64 slices (b200_prove_partial_span)
 # model behind the "balanced" plan, from this round's single-GPU measurements (profiles/r02_summary.md): the MNT4753
-# proof costs a fixed ~25 ms (replicated compute_H, bucket reductions, preparation) plus ~365 ms x the rank's share of
+# proof costs a fixed ~35 ms (replicated compute_H, bucket reductions, preparation) plus ~370 ms x the rank's share of
 # the points; the whole MNT6753 proof adds ~40 ms to a rank that also works on MNT4753 (its latency-bound kernels hide
 # partly under the accumulations)
-PLAN_MODEL = {"mnt4_fixed_ms": 25.0, "mnt4_per_share_ms": 365.0, "mnt6_whole_ms": 40.0}
+PLAN_MODEL = {"mnt4_fixed_ms": 35.0, "mnt4_per_share_ms": 370.0, "mnt6_whole_ms": 40.0}
 
 
 def step_plan(world, mode=None):
