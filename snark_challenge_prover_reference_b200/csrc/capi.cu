@@ -911,7 +911,14 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   // on separate high / low priority streams, both lengthen the proof (391 -> 407 / 411 ms): whatever runs beside an
   // accumulation kernel takes register-file space from it for longer than it saves.
   const size_t outoff[5] = {0, g1p, 2 * g1p, 2 * g1p + g2p, 3 * g1p + g2p};
-  const int order[5] = {2, 0, 1, 4, 3};
+  // B200_H_FIRST=1: the witness map and the H MSM are issued BEFORE the w-driven MSMs. When a rank's share of the points
+  // is small (8 GPUs) compute_H - 21 short launches on the default stream - otherwise crawls behind the accumulation
+  // blocks of four MSMs (13 ms alone, ~50 ms in their shadow) and the H MSM, which waits for it, ends the proof alone.
+  static const int h_first_env = getenv("B200_H_FIRST") ? atoi(getenv("B200_H_FIRST")) : -1;
+  const bool h_first = h_first_env >= 0 ? h_first_env != 0 : false;
+  const int order_default[5] = {2, 0, 1, 4, 3}, order_h_first[5] = {3, 2, 0, 1, 4};
+  const int *order = h_first ? order_h_first : order_default;
+  const int slot_of_job[5] = {1, 2, 0, 4, 3};  // workspace of A, B1, B2, H, L (B2's is the one the others share)
   // every tail reports its own status and message (it runs on another thread, whose thread-local error slot this thread
   // cannot see); a failed tail fails the proof
   struct TailResult { int rc = 0; std::string err; };
@@ -937,7 +944,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     query_slice(d, m, jobq[j], rank, rank_end, world, lo, hi);
     double a = now_ms();
     MsmTail tail;
-    msm_select_slot(jj);
+    msm_select_slot(slot_of_job[j]);
     // A and B1 (slots 1, 2) run over the same scalars and window plan as B2 (slot 0): they reuse its digits, counting
     // sort and task list
     // (not when this query's equal bases are merged: its scalars then differ from w)
@@ -948,8 +955,8 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     if (use_precompute() && !merges && hi > lo && p->pre.plan[j].c == p->pre.plan[2].c && share_prep_enabled()) {
       size_t lo1, hi1;
       query_slice(d, m, 2, rank, rank_end, world, lo1, hi1);
-      if (jj == 1 || jj == 2) share.slot = 0;
-      if (jj == 3 && hi1 > lo1) {
+      if (j == 0 || j == 1) share.slot = 0;
+      if (j == 4 && hi1 > lo1) {
         share.slot = 0;
         share.n_src = (uint32_t)(hi1 - lo1);
         share.shift = (uint32_t)(lo + 2 - lo1);
