@@ -283,10 +283,9 @@ static int choose_window(size_t n, bool merged) {
     double W = (754 + c - 1) / c;
     double nb = (double)(1u << (c - 1));
     double red = nb * 2.0 * 14.0 + nb / 32.0 * 30.0 * 13.0;
-    // measured (round 2, 2^20 points): a bucket of the reduction costs 5.5 (G1) - 6.4 (G2) bucket insertions, not the
-    // 3.65 the multiplication counts give - the reduction is latency-bound - so the single merged bucket set is weighted
-    // 1.7x: one bit narrower windows (c = 20, 38 windows at 2^20: -1 ms per G1 MSM, -5 ms for the G2 one)
-    if (merged) red *= 1.7;
+    // (round 2: weighting the merged bucket set's reduction 1.7x - its measured latency-bound cost - moves every choice one
+    // bit down, c = 20 / 38 windows at 2^20; measured: G1 52.6 + 5.2 ms against 49.3 + 7.6 ms, G2 152.7 + 17.9 against
+    // 146 + 26, step 430.1 against 428.3 ms - a wash, so the multiplication-count model stays)
     double cost = merged ? W * (double)n * 11.0 + red : W * ((double)n * 11.0 + red);
     if (cost < best) {
       best = cost;
