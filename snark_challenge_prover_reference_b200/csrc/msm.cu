@@ -46,6 +46,15 @@ void msm_set_batch_affine(int on) { g_batch_affine = on < 0 || on > 2 ? 2 : on; 
 // set holds millions of entries (2^20 points: 145 vs 157 ms); for G1 the two are within 1 %, and for small MSMs the
 // ~7 dependent rounds (one inversion latency each) lose to the single XYZZ launch (2^15 points: 9.3 vs 2.8 ms).
 bool msm_affine_wins(int degree, size_t entries) { return degree == 2 && entries >= ((size_t)8 << 20); }
+// Lane-cooperative bucket reduction (coop.cuh): B200_COOP=0 never, 1 always, default: bucket sets of at most 2^18 buckets,
+// where the reduction is a latency problem (sharded proofs, the MNT6753 proof); at 2^20 buckets it is a throughput
+// problem and the thread-per-chunk kernel does the same work with all 32 lanes.
+bool msm_use_coop(size_t total_buckets) {
+  static const int mode = getenv("B200_COOP") ? atoi(getenv("B200_COOP")) : 2;
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  return total_buckets <= ((size_t)1 << 18);
+}
 // B200_AFF_SPLIT=1: cut large batch-affine rounds into an 80 % and a 20 % region (see AffRegions) to fill the tail of the
 // single wave. Measured on B200 and left off: the second region's shorter batches pay more per addition for the shared
 // inversion than the tail costs (G1 2^20: 52.9 vs 49.2 ms, G2: 149.5 vs 145.2 ms).

@@ -5,6 +5,7 @@
 #include <functional>
 #include <memory>
 #include "common.cuh"
+#include "coop.cuh"
 #include "curve.cuh"
 #include "msm.h"
 #include "msm_internal.h"
@@ -766,6 +767,46 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
 
   // ---- bucket reduction (enqueued, not awaited): chunks of K buckets, then tree sum per bucket set
   B200_CUDA_CHECK(cudaEventRecord(stage->t0, st));
+  Proj<F> *cur = nullptr;
+  if (msm_use_coop((size_t)W * nb)) {
+    // lane-cooperative reduction (coop.cuh): a group of 8 / 16 / 32 lanes per chunk. The chunk length makes the chunks
+    // about one wave of resident groups: short dependent chains, no second wave.
+    typedef CoopTables<G> CT;
+    constexpr int LG = CT::kLanes, groups_per_block = 128 / LG;
+    const size_t smem_red = groups_per_block * coop_group_bytes<G>(4), smem_sum = groups_per_block * coop_group_bytes<G>(2);
+    static int resident_groups = 0;
+    if (!resident_groups) {
+      int per_sm = 0, dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      B200_CUDA_CHECK(cudaFuncSetAttribute(msm_reduce_coop_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_red));
+      B200_CUDA_CHECK(cudaFuncSetAttribute(msm_sum_coop_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sum));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_reduce_coop_kernel<G>, 128, smem_red);
+      resident_groups = (per_sm > 0 ? per_sm : 1) * sms * groups_per_block;
+    }
+    uint32_t K = 4;
+    while (K < 64 && (size_t)W * (nb / K) > (size_t)resident_groups) K <<= 1;
+    if (K > nb) K = nb;
+    uint32_t per = nb / K;
+    B200_CHECK(ws.red_a.reserve((size_t)W * per * sizeof(Proj<F>)));
+    B200_CHECK(ws.red_b.reserve((size_t)W * ((per + 1) / 2) * sizeof(Proj<F>) + 16));
+    msm_reduce_coop_kernel<G><<<grid_for((size_t)W * per * LG, 128), 128, smem_red, st>>>(ws.buckets.as<Proj<F>>(), W, nb, K,
+                                                                                        ws.red_a.as<Proj<F>>());
+    B200_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    cur = ws.red_a.as<Proj<F>>();
+    Proj<F> *nxt = ws.red_b.as<Proj<F>>();
+    while (per > 1) {  // pairwise: one cooperative addition of latency per level
+      const uint32_t per_out = (per + 1) / 2;
+      msm_sum_coop_kernel<G><<<grid_for((size_t)W * per_out * LG, 128), 128, smem_sum, st>>>(cur, W, per, 2, nxt);
+      B200_CUDA_CHECK(cudaGetLastError());
+      note_launch();
+      Proj<F> *t = cur;
+      cur = nxt;
+      nxt = t;
+      per = per_out;
+    }
+  } else {
   // chunk length: long chunks amortise the lo*sum fix-up, short ones keep enough threads in flight (>= ~32 K)
   uint32_t K = 32;
   while (K > 2 && (size_t)W * (nb / K) < 32768) K >>= 1;
@@ -777,7 +818,8 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
                                                                        ws.red_a.as<Proj<F>>());
   B200_CUDA_CHECK(cudaGetLastError());
   note_launch();
-  Proj<F> *cur = ws.red_a.as<Proj<F>>(), *nxt = ws.red_b.as<Proj<F>>();
+  cur = ws.red_a.as<Proj<F>>();
+  Proj<F> *nxt = ws.red_b.as<Proj<F>>();
   while (per > 1) {
     // radix of the tree sum: 8 while a level still fills the GPU, 2 below that (every level then costs one
     // point addition of latency instead of eight)
@@ -790,6 +832,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
     cur = nxt;
     nxt = t;
     per = per_out;
+  }
   }
   B200_CUDA_CHECK(cudaMemcpyAsync(stage->pinned, cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost, st));
   B200_CUDA_CHECK(cudaEventRecord(stage->t1, st));
