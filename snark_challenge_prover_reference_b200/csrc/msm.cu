@@ -288,7 +288,8 @@ static int choose_window(size_t n, bool merged) {
   if (g_forced_window >= 3 && g_forced_window <= 22) return g_forced_window;
   double best = 1e300;
   int best_c = 4;
-  for (int c = 3; c <= (merged ? 22 : 20); c++) {
+  // (table mode: at least 8 bits, i.e. at most 95 windows - the table builder holds one Z per window on its stack)
+  for (int c = merged ? 8 : 3; c <= (merged ? 22 : 20); c++) {
     double W = (754 + c - 1) / c;
     double nb = (double)(1u << (c - 1));
     double red = nb * 2.0 * 14.0 + nb / 32.0 * 30.0 * 13.0;

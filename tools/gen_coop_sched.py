@@ -178,25 +178,44 @@ def schedule(bld, outputs, keep, lanes):
             stack.append(a)
             if b is not None:
                 stack.append(b)
-    level = [0] * n
+    # Levels are ordered by (multiplication depth, addition depth inside it): all multiplications with the same number of
+    # multiplications on their longest input path share ONE level - a level that contains a multiplication costs a
+    # multiplication (~4 us) however many lanes multiply, so what matters is the number of such levels (4 for an
+    # addition, whatever the tower) - and the cheap additions / subtractions / small-constant products fill sub-levels
+    # between them.
+    md, ad = [0] * n, [0] * n
     for i, (kind, a, b, k) in enumerate(nodes):
         if kind == "in" or not live[i]:
             continue
-        level[i] = 1 + max(level[a], level[b] if b is not None else 0)
+        ops_ = [a] + ([b] if b is not None else [])
+        m = max(md[o] for o in ops_)
+        if kind == MUL:
+            md[i], ad[i] = m + 1, 0
+        else:
+            md[i] = m
+            ad[i] = 1 + max([ad[o] for o in ops_ if md[o] == m and nodes[o][0] != "in"] + [0])
+    keys = sorted({(md[i], ad[i]) for i in range(n) if live[i] and nodes[i][0] != "in"})
+    rank = {kk: r + 1 for r, kk in enumerate(keys)}
+    level = [0] * n
+    for i in range(n):
+        if live[i] and nodes[i][0] != "in":
+            level[i] = rank[(md[i], ad[i])]
     # an output node must be computed by an operation (never a bare input) and each output slot is written once
     assert all(nodes[o][0] != "in" for o in outputs) and len(set(outputs)) == len(outputs)
-    # the outputs are written in the LAST level (as late as possible, not as soon as possible): the destination point may
-    # alias an input point, so nothing may be written while an input can still be read. No output feeds another node.
+    # The destination point may alias an input point: nothing may be written while an input can still be read. An output
+    # is therefore placed after the last level that reads an input (and no output feeds another node).
     users = set()
+    last_input_read = 0
     for i, (kind, a, b, k) in enumerate(nodes):
         if kind != "in" and live[i]:
-            users.add(a)
-            if b is not None:
-                users.add(b)
+            for o in (a, b):
+                if o is not None:
+                    users.add(o)
+                    if nodes[o][0] == "in":
+                        last_input_read = max(last_input_read, level[i])
     assert not (users & set(outputs))
-    top = max(level)
     for o in outputs:
-        level[o] = top
+        level[o] = max(level[o], last_input_read + 1)
     by_level = {}
     for i in range(n):
         if live[i] and nodes[i][0] != "in":
