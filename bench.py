@@ -448,6 +448,45 @@ def b200_arm(args):
     proof_len = [pkg.proof_bytes(c) for c, _ in shapes]
     slot = [max(pbytes[i], proof_len[i]) for i in range(2)]   # per-rank bytes exchanged per proof
 
+    # ---- optional: the witness map of the large proof split over three ranks (B200_BENCH_SPLIT_H=1, N >= 3). Replicated,
+    # compute_H costs every rank 13 ms of multiplier time; split, the first three ranks of the MNT4753 group transform a, b
+    # and c (iFFT + cosetFFT each), two 100 MB vectors travel over NVLink to the first rank, which finishes
+    # (a*b - c) / Z -> icosetFFT and broadcasts the coefficients; every rank then runs its MSMs on them
+    # (b200_prove_partial_ext). NCCL is the plumbing, the transforms are the same kernels.
+    big_ranks = [r for r in range(world) if runs[r][1] > runs[r][0]]
+    split_h = world >= 3 and len(big_ranks) >= 3 and os.environ.get("B200_BENCH_SPLIT_H", "0") == "1"
+    h_state = {}
+    if split_h:
+        grp = dist.new_group(big_ranks)   # every rank must take part in creating it
+        if rank in big_ranks:
+            m4 = 1 << k4
+            h_state.update(group=grp, m=m4, dom=pkg.Domain(0, m4), H=torch.zeros((m4 + 1) * FE, dtype=torch.uint8, device=dev),
+                           mine=torch.empty(m4 * FE, dtype=torch.uint8, device=dev),
+                           other=[torch.empty(m4 * FE, dtype=torch.uint8, device=dev) for _ in range(2)] if rank == big_ranks[0] else None)
+
+    def witness_map_split(image):
+        """-> device tensor with the H coefficients (m + 1 elements, the last one zero) on every MNT4753 rank"""
+        m4, dom, H, mine = h_state["m"], h_state["dom"], h_state["H"], h_state["mine"]
+        idx = big_ranks.index(rank)
+        if idx < 3:  # a, b or c: elements [m+1 + idx*m, +m) of the input image (host or device)
+            lo = (m4 + 1 + idx * m4) * FE
+            mine.copy_(image[lo:lo + m4 * FE], non_blocking=True)
+            dom.ifft(mine)
+            dom.coset_fft(mine)
+        if idx == 0:
+            reqs = [dist.irecv(h_state["other"][j], src=big_ranks[j + 1], group=h_state["group"]) for j in range(2)]
+            for rq in reqs:
+                rq.wait()
+            pkg.check(pkg.lib().b200_fr_muleq(0, mine.data_ptr(), h_state["other"][0].data_ptr(), m4))
+            pkg.check(pkg.lib().b200_fr_subeq(0, mine.data_ptr(), h_state["other"][1].data_ptr(), m4))
+            dom.divide_by_z_on_coset(mine)
+            dom.icoset_fft(mine)
+            H[:m4 * FE].copy_(mine)
+        elif idx < 3:
+            dist.send(mine, dst=big_ranks[0], group=h_state["group"])
+        dist.broadcast(H, src=big_ranks[0], group=h_state["group"])
+        return H
+
     def prove_all(inputs, timings=None):
         """one step: this rank's proofs IN FLIGHT TOGETHER (b200_prove_batch); N > 1: one all_gather of every rank's
         partial sums (or finished small proof), rank 0 combines. Returns the two proofs' bytes on rank 0."""
@@ -456,7 +495,8 @@ def b200_arm(args):
             proofs, tms = pkg.prove_batch([(keys[i], inputs[i]) for i, _, _, _ in my_jobs], timings=True)
             busy = time.perf_counter() - t0
         else:
-            jobs = [(keys[i], inputs[i], r, w, e) if w > 1 else (keys[i], inputs[i]) for i, r, w, e in my_jobs]
+            h_ext = witness_map_split(inputs[0]) if split_h and rank in big_ranks else None
+            jobs = [(keys[i], inputs[i], r, w, e, h_ext if i == 0 else None) if w > 1 else (keys[i], inputs[i]) for i, r, w, e in my_jobs]
             outs, tms = pkg.prove_batch(jobs, timings=True) if jobs else ([], [])
             busy = time.perf_counter() - t0
             mine = torch.frombuffer(pack_rank_blob(my_jobs, outs, slot), dtype=torch.uint8).to(dev)
@@ -680,7 +720,7 @@ def b200_arm(args):
                        "l2": "inputs larger than L2: each step streams >1.6 GB of bases and 416 MB of scalars",
                        "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys",
                        "multi_gpu": {"mode": mode, "mnt4753_runs_of_%d" % PLAN_UNITS: runs, "mnt6753_rank": small_rank,
-                                     "rank_busy_ms_per_step": rank_busy_ms},
+                                     "rank_busy_ms_per_step": rank_busy_ms, "witness_map": "split over 3 ranks + broadcast" if split_h else "replicated"},
                        "accumulation": lib_mode + " (auto = batched affine additions for large G2/Fq2 MSMs, XYZZ mixed additions otherwise)",
                        "key_preprocess": "pre-shifted base tables 2^(start_j)*P_i per MSM window, built once per key, "
                                          "outside the timed region (see key_load); see no_tables"},

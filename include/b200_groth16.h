@@ -175,6 +175,12 @@ int b200_prove_partial(b200_params *p, const void *h_input, size_t input_bytes, 
 int b200_prove_partial_span(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
                             void *h_partials, size_t *partial_bytes, b200_prove_timings *timings);
 int b200_params_precompute_span(b200_params *p, int rank, int rank_end, int world);
+/* The same with the witness map done elsewhere: d_h_coefficients (device, d+1 Fr elements = what b200_compute_h writes,
+ * ready on the default stream) replaces this call's own compute_H; the ca / cb / cc part of the input image is then not
+ * read. At N GPUs the three chains of compute_H (iFFT + cosetFFT of a, b, c: main.cpp:116-135) can run on three ranks
+ * and the result be broadcast, instead of every rank repeating all seven transforms (bench.py: B200_BENCH_SPLIT_H). */
+int b200_prove_partial_ext(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
+                           const void *d_h_coefficients, void *h_partials, size_t *partial_bytes, b200_prove_timings *timings);
 /* combine `world` partial results (rank-major, as produced by b200_prove_partial) into the final proof */
 int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
                        size_t *out_bytes);
@@ -192,6 +198,7 @@ typedef struct {
   size_t out_bytes; /* set by the call */
   int rank, world;
   int rank_end; /* world > 1: the job owns slices [rank, rank_end) of world; 0 means rank + 1 */
+  const void *d_h_coefficients; /* world > 1, optional: see b200_prove_partial_ext */
   int status; /* set by the call: 0 or the job's error code */
   b200_prove_timings timings;
 } b200_proof_job;

@@ -53,7 +53,8 @@ class ProofJob(ctypes.Structure):
     """b200_proof_job of include/b200_groth16.h"""
     _fields_ = [("key", ctypes.c_void_p), ("h_input", ctypes.c_void_p), ("input_bytes", ctypes.c_size_t),
                 ("h_out", ctypes.c_void_p), ("out_bytes", ctypes.c_size_t), ("rank", ctypes.c_int),
-                ("world", ctypes.c_int), ("rank_end", ctypes.c_int), ("status", ctypes.c_int), ("timings", ProveTimings)]
+                ("world", ctypes.c_int), ("rank_end", ctypes.c_int), ("d_h_coefficients", ctypes.c_void_p),
+                ("status", ctypes.c_int), ("timings", ProveTimings)]
 
 
 _lib = None
@@ -133,6 +134,7 @@ _SIGNATURES = {
     "b200_prove_full": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, ctypes.POINTER(_sz)]),
     "b200_prove_partial_span": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
     "b200_params_precompute_span": (_i, [_vp, _i, _i, _i]),
+    "b200_prove_partial_ext": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
     "b200_prove_combine": (_i, [_i, _vp, _i, _vp, _vp, ctypes.POINTER(_sz)]),
     "b200_dev_fp_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
     "b200_dev_fqe_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
@@ -396,14 +398,15 @@ class Params:
                                     ctypes.addressof(out), ctypes.byref(n)))
         return out.raw[:n.value]
 
-    def prove_partial(self, input_image, rank, world, rank_end=None):
-        """partial sums over slice `rank` - or the run of slices [rank, rank_end) - of `world`"""
+    def prove_partial(self, input_image, rank, world, rank_end=None, d_h=None):
+        """partial sums over slice `rank` - or the run of slices [rank, rank_end) - of `world`; d_h: device vector of
+        H coefficients computed elsewhere (b200_prove_partial_ext)"""
         out = ctypes.create_string_buffer(partial_bytes(self.curve))
         n = ctypes.c_size_t()
         tm = ProveTimings()
-        check(lib().b200_prove_partial_span(self.h, _ptr(input_image), _len(input_image), rank,
-                                            rank + 1 if rank_end is None else rank_end, world,
-                                            ctypes.addressof(out), ctypes.byref(n), ctypes.byref(tm)))
+        check(lib().b200_prove_partial_ext(self.h, _ptr(input_image), _len(input_image), rank,
+                                           rank + 1 if rank_end is None else rank_end, world, _ptr(d_h),
+                                           ctypes.addressof(out), ctypes.byref(n), ctypes.byref(tm)))
         return out.raw[:n.value], tm.as_dict()
 
 
@@ -450,6 +453,7 @@ def prove_batch(jobs, timings=False):
         key, image = job[0], job[1]
         rank, world = (job[2], job[3]) if len(job) > 2 else (0, 1)
         a.rank_end = job[4] if len(job) > 4 else 0   # (key, image, rank, world, rank_end): a run of slices
+        a.d_h_coefficients = _ptr(job[5]) if len(job) > 5 and job[5] is not None else None   # witness map done elsewhere
         out = ctypes.create_string_buffer(max(proof_bytes(key.curve), partial_bytes(key.curve)))
         outs.append(out)
         a.key = key.h.value if hasattr(key.h, "value") else key.h

@@ -873,7 +873,7 @@ int b200_msm_wait(b200_msm_pending *pending) {
 // Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
 // multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
 static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
-                          unsigned char *partials, b200_prove_timings *tm) {
+                          unsigned char *partials, b200_prove_timings *tm, const void *d_h_external = nullptr) {
   const size_t d = p->d, m = p->m;
   const size_t need = 96 * ((m + 1) + 3 * (d + 1) + 1);
   if (input_bytes != need) return set_error(-4, "input image has %zu bytes, expected %zu", input_bytes, need);
@@ -900,7 +900,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
       {1, (const char *)p->w.p, (const char *)p->q[0], m + 1, g1a, g1p, &ms[0]},        // A   main.cpp:227
       {1, (const char *)p->w.p, (const char *)p->q[1], m + 1, g1a, g1p, &ms[1]},        // B1  main.cpp:232
       {2, (const char *)p->w.p, (const char *)p->q[2], m + 1, g2a, g2p, &ms[2]},        // B2  main.cpp:237
-      {1, (const char *)p->h.p, (const char *)p->q[4], d, g1a, g1p, &ms[3]},            // H   main.cpp:242
+      {1, d_h_external ? (const char *)d_h_external : (const char *)p->h.p, (const char *)p->q[4], d, g1a, g1p, &ms[3]},  // H   main.cpp:242
       {1, (const char *)p->w.p + 2 * 96, (const char *)p->q[3], m - 1, g1a, g1p, &ms[4]} // L   main.cpp:247 (w+2)
   };
   // The GPU half of each MSM runs here, back to back; the serial host halves (window combine, 753 doublings each)
@@ -927,7 +927,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   double t2 = t1;
   for (int jj = 0; jj < 5 && rc_all == 0; jj++) {
     const int j = order[jj];
-    if (j == 3) {  // H needs the witness map
+    if (j == 3 && !d_h_external) {  // H needs the witness map (unless the caller computed it elsewhere)
       double a = now_ms();
       const char *abc = in + (m + 1) * 96;
       B200_CUDA_CHECK(cudaMemcpyAsync(p->ca.p, abc, (d + 1) * 96, cudaMemcpyDefault, 0));
@@ -1005,8 +1005,12 @@ int b200_prove_partial(b200_params *p, const void *h_input, size_t input_bytes, 
 }
 int b200_prove_partial_span(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
                             void *h_partials, size_t *partial_bytes, b200_prove_timings *timings) {
+  return b200_prove_partial_ext(p, h_input, input_bytes, rank, rank_end, world, nullptr, h_partials, partial_bytes, timings);
+}
+int b200_prove_partial_ext(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
+                           const void *d_h_coefficients, void *h_partials, size_t *partial_bytes, b200_prove_timings *timings) {
   B200_CHECK(require_device());
-  B200_CHECK(prove_partials(p, h_input, input_bytes, rank, rank_end, world, (unsigned char *)h_partials, timings));
+  B200_CHECK(prove_partials(p, h_input, input_bytes, rank, rank_end, world, (unsigned char *)h_partials, timings, d_h_coefficients));
   if (partial_bytes) *partial_bytes = partial_size(p->curve);
   return 0;
 }
@@ -1168,14 +1172,19 @@ class ProofWorker {
 int run_proof_job(b200_proof_job *j) {
   if (!j->key || !j->h_input || !j->h_out) return set_error(-1, "proof job: null key, input or output");
   if (j->world > 1)
-    return b200_prove_partial_span(j->key, j->h_input, j->input_bytes, j->rank, j->rank_end > j->rank ? j->rank_end : j->rank + 1,
-                                   j->world, j->h_out, &j->out_bytes, &j->timings);
+    return b200_prove_partial_ext(j->key, j->h_input, j->input_bytes, j->rank, j->rank_end > j->rank ? j->rank_end : j->rank + 1,
+                                  j->world, j->d_h_coefficients, j->h_out, &j->out_bytes, &j->timings);
   return b200_prove(j->key, j->h_input, j->input_bytes, j->h_out, &j->out_bytes, &j->timings);
 }
 }  // namespace
 
 int b200_prove_batch(b200_proof_job *jobs, int count) {
   B200_CHECK(require_device());
+  struct ConcurrencyNote {  // several proofs in flight: the GPU is throughput-bound, see msm_use_coop
+    int n;
+    explicit ConcurrencyNote(int k) : n(k) { msm_note_concurrent_proofs(n); }
+    ~ConcurrencyNote() { msm_note_concurrent_proofs(1); }
+  } note(count);
   constexpr int kMaxJobs = 8;
   if (!jobs || count < 1 || count > kMaxJobs) return set_error(-1, "prove_batch: count %d not in [1, %d]", count, kMaxJobs);
   for (int i = 0; i < count; i++)

@@ -49,11 +49,18 @@ bool msm_affine_wins(int degree, size_t entries) { return degree == 2 && entries
 // Lane-cooperative bucket reduction (coop.cuh): B200_COOP=0 never, 1 always, default: bucket sets of at most 2^18 buckets,
 // where the reduction is a latency problem (sharded proofs, the MNT6753 proof); at 2^20 buckets it is a throughput
 // problem and the thread-per-chunk kernel does the same work with all 32 lanes.
+// A cooperative addition keeps 5 of 8 ... 30 of 32 lanes busy in its multiplication levels and none in the others: it
+// trades multiplier throughput (1.5-2x the pipe time of the thread-per-chunk kernel) for latency (5-15x shorter chains).
+// Measured (profiles/r02_summary.md): the MNT6753 2^15 proof alone 57.7 -> 47.3 ms (its G2 reduction 16.9 -> 6.3 ms), but the
+// two-proof step, where the small proof's kernels share the multiplier with the large proof's accumulations, 428 -> 438 ms.
+// So: only when this is the only proof in flight (b200_prove_batch notes how many it runs).
+static std::atomic<int> g_concurrent_proofs{1};
+void msm_note_concurrent_proofs(int n) { g_concurrent_proofs = n; }
 bool msm_use_coop(size_t total_buckets) {
   static const int mode = getenv("B200_COOP") ? atoi(getenv("B200_COOP")) : 2;
   if (mode == 0) return false;
   if (mode == 1) return true;
-  return total_buckets <= ((size_t)1 << 18);
+  return total_buckets <= ((size_t)1 << 18) && g_concurrent_proofs <= 1;
 }
 // B200_AFF_SPLIT=1: cut large batch-affine rounds into an 80 % and a 20 % region (see AffRegions) to fill the tail of the
 // single wave. Measured on B200 and left off: the second region's shorter batches pay more per addition for the shared

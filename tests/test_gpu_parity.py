@@ -389,6 +389,18 @@ def test_sharded_prover_matches_reference_golden(b200, dev, precompute, curve, a
     runs = [(0, 36), (36, 36), (36, 61), (61, 64)]
     parts = b"".join(P.prove_partial(inp, lo, 64, hi)[0] for lo, hi in runs)
     assert b200.prove_combine(curve, parts, len(runs), inp[-FE:]) == expected
+    # the witness map computed outside the call (what bench.py does when it splits compute_H over three ranks)
+    import torch
+    d, m = P.d, P.m
+    vecs = [b200.to_device(inp[(m + 1 + i * (d + 1)) * FE:(m + 1 + (i + 1) * (d + 1)) * FE]) for i in range(3)]
+    h = torch.zeros((d + 2) * FE, dtype=torch.uint8, device=dev)
+    dom = b200.Domain(curve, d + 1)
+    dom.compute_h(vecs[0], vecs[1], vecs[2], h)
+    garbage = bytearray(inp)
+    garbage[(m + 1) * FE:(m + 1 + 3 * (d + 1)) * FE] = bytes(3 * (d + 1) * FE)   # ca / cb / cc must not be read
+    parts = b"".join(P.prove_partial(bytes(garbage), r, 2, d_h=h)[0] for r in range(2))
+    assert b200.prove_combine(curve, parts, 2, inp[-FE:]) == expected
+    dom.close()
     P.close()
 
 

@@ -25,9 +25,9 @@ IN_A, IN_B, OUT = 0x4000, 0x8000, 0xC000
 
 GROUPS = {
     # name: (curve, degree, non-residue, lanes per group)
-    "Mnt4G1": (M.MNT4753, 1, 0, 8),
+    "Mnt4G1": (M.MNT4753, 1, 0, 4),
     "Mnt4G2": (M.MNT4753, 2, 13, 16),
-    "Mnt6G1": (M.MNT6753, 1, 0, 8),
+    "Mnt6G1": (M.MNT6753, 1, 0, 4),
     "Mnt6G2": (M.MNT6753, 3, 11, 32),
 }
 
@@ -183,17 +183,50 @@ def schedule(bld, outputs, keep, lanes):
     # multiplication (~4 us) however many lanes multiply, so what matters is the number of such levels (4 for an
     # addition, whatever the tower) - and the cheap additions / subtractions / small-constant products fill sub-levels
     # between them.
-    md, ad = [0] * n, [0] * n
-    for i, (kind, a, b, k) in enumerate(nodes):
-        if kind == "in" or not live[i]:
-            continue
-        ops_ = [a] + ([b] if b is not None else [])
-        m = max(md[o] for o in ops_)
-        if kind == MUL:
-            md[i], ad[i] = m + 1, 0
-        else:
-            md[i] = m
-            ad[i] = 1 + max([ad[o] for o in ops_ if md[o] == m and nodes[o][0] != "in"] + [0])
+    forced = {}  # multiplication -> minimum depth (a multiplication with slack deferred out of an over-full level)
+
+    def depths():
+        md, ad = [0] * n, [0] * n
+        for i, (kind, a, b, k) in enumerate(nodes):
+            if kind == "in" or not live[i]:
+                continue
+            ops_ = [a] + ([b] if b is not None else [])
+            m = max(md[o] for o in ops_)
+            if kind == MUL:
+                md[i], ad[i] = max(m + 1, forced.get(i, 0)), 0
+            else:
+                md[i] = m
+                ad[i] = 1 + max([ad[o] for o in ops_ if md[o] == m and nodes[o][0] != "in"] + [0])
+        return md, ad
+
+    md, ad = depths()
+    # A level holds at most `lanes` multiplications. When a depth has more, multiplications whose results are not needed
+    # at the next depth (slack) move one depth down instead of opening an extra multiplication level: with 4-lane groups
+    # the G1 addition's 5 + 2 + 3 + 4 multiplications become 4 + 3 + 3 + 4.
+    for _ in range(64):
+        top_md = max(md)
+        alap = [top_md] * n
+        for i in range(n - 1, -1, -1):
+            kind, a, b, k = nodes[i]
+            if kind == "in" or not live[i]:
+                continue
+            need = alap[i] - (1 if kind == MUL else 0)
+            for o in (a, b):
+                if o is not None:
+                    alap[o] = min(alap[o], need)
+        moved = False
+        for m in range(1, top_md):
+            here = [i for i in range(n) if live[i] and nodes[i][0] == MUL and md[i] == m]
+            if len(here) > lanes:
+                slack = sorted((i for i in here if alap[i] > m), key=lambda i: -alap[i])
+                for i in slack[:len(here) - lanes]:
+                    forced[i] = m + 1
+                    moved = True
+                if moved:
+                    break
+        if not moved:
+            break
+        md, ad = depths()
     keys = sorted({(md[i], ad[i]) for i in range(n) if live[i] and nodes[i][0] != "in"})
     rank = {kk: r + 1 for r, kk in enumerate(keys)}
     level = [0] * n
