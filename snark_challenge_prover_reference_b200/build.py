@@ -20,7 +20,7 @@ SOURCES = ["msm_g_mnt6g2.cu", "devops_g_mnt6g2.cu", "msm_g_mnt4g2.cu", "devops_g
            "devops_g_mnt4g1.cu", "devops_g_mnt6g1.cu", "devops.cu", "msm.cu", "ntt.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-mbmi2", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-mbmi2", "-Xcompiler", "-madx", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
          "-ccbin", "/usr/bin/g++"]
 
 
