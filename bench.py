@@ -487,6 +487,8 @@ def b200_arm(args):
         dist.broadcast(H, src=big_ranks[0], group=h_state["group"])
         return H
 
+    b1_scaled = os.environ.get("B200_BENCH_SCALE_AT_COMBINE", "0") != "1"
+
     def prove_all(inputs, timings=None):
         """one step: this rank's proofs IN FLIGHT TOGETHER (b200_prove_batch); N > 1: one all_gather of every rank's
         partial sums (or finished small proof), rank 0 combines. Returns the two proofs' bytes on rank 0."""
@@ -497,7 +499,9 @@ def b200_arm(args):
         else:
             h_ext = witness_map_split(inputs[0]) if split_h and rank in big_ranks else None
             jobs = [(keys[i], inputs[i], r, w, e, h_ext if i == 0 else None) if w > 1 else (keys[i], inputs[i]) for i, r, w, e in my_jobs]
-            outs, tms = pkg.prove_batch(jobs, timings=True) if jobs else ([], [])
+            # every rank multiplies its own B1 sum by r under its GPU work (b200_prove_partial_scaled): rank 0's combine is
+            # then additions and three inversions, not 753 serial doublings (B200_BENCH_SCALE_AT_COMBINE=1: the old way)
+            outs, tms = pkg.prove_batch(jobs, timings=True, b1_scaled=b1_scaled) if jobs else ([], [])
             busy = time.perf_counter() - t0
             mine = torch.frombuffer(pack_rank_blob(my_jobs, outs, slot), dtype=torch.uint8).to(dev)
             allp = [torch.empty_like(mine) for _ in range(world)]
@@ -505,7 +509,7 @@ def b200_arm(args):
             proofs = []
             if rank == 0:
                 blobs = [bytes(t.cpu().numpy().tobytes()) for t in allp]
-                proofs = combine_step(pkg, blobs, world, slot, pbytes, proof_len, r_fr)
+                proofs = combine_step(pkg, blobs, world, slot, pbytes, proof_len, [None, None] if b1_scaled else r_fr)
         if timings is not None:
             wall = time.perf_counter() - t0
             for (i, _, _, _), tm in zip(my_jobs, tms):

@@ -181,7 +181,14 @@ int b200_params_precompute_span(b200_params *p, int rank, int rank_end, int worl
  * and the result be broadcast, instead of every rank repeating all seven transforms (bench.py: B200_BENCH_SPLIT_H). */
 int b200_prove_partial_ext(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
                            const void *d_h_coefficients, void *h_partials, size_t *partial_bytes, b200_prove_timings *timings);
-/* combine `world` partial results (rank-major, as produced by b200_prove_partial) into the final proof */
+/* As b200_prove_partial_ext, but the B1 slot of the partial sums holds r * (this rank's B1 sum), r read from the input
+ * image: the 753 doublings of r * Bt1 (main.cpp:253) then run on every rank's host under its own GPU work instead of
+ * serially on the combining rank. Such partials are combined with h_r_fr == NULL. */
+int b200_prove_partial_scaled(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
+                              const void *d_h_coefficients, void *h_partials, size_t *partial_bytes,
+                              b200_prove_timings *timings);
+/* combine `world` partial results (rank-major, as produced by b200_prove_partial) into the final proof; h_r_fr == NULL:
+ * the B1 slots are already multiplied by r (b200_prove_partial_scaled) */
 int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
                        size_t *out_bytes);
 
@@ -199,6 +206,7 @@ typedef struct {
   int rank, world;
   int rank_end; /* world > 1: the job owns slices [rank, rank_end) of world; 0 means rank + 1 */
   const void *d_h_coefficients; /* world > 1, optional: see b200_prove_partial_ext */
+  int b1_scaled; /* world > 1: nonzero = partial sums as b200_prove_partial_scaled writes them */
   int status; /* set by the call: 0 or the job's error code */
   b200_prove_timings timings;
 } b200_proof_job;

@@ -54,7 +54,7 @@ class ProofJob(ctypes.Structure):
     _fields_ = [("key", ctypes.c_void_p), ("h_input", ctypes.c_void_p), ("input_bytes", ctypes.c_size_t),
                 ("h_out", ctypes.c_void_p), ("out_bytes", ctypes.c_size_t), ("rank", ctypes.c_int),
                 ("world", ctypes.c_int), ("rank_end", ctypes.c_int), ("d_h_coefficients", ctypes.c_void_p),
-                ("status", ctypes.c_int), ("timings", ProveTimings)]
+                ("b1_scaled", ctypes.c_int), ("status", ctypes.c_int), ("timings", ProveTimings)]
 
 
 _lib = None
@@ -135,6 +135,7 @@ _SIGNATURES = {
     "b200_prove_partial_span": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
     "b200_params_precompute_span": (_i, [_vp, _i, _i, _i]),
     "b200_prove_partial_ext": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
+    "b200_prove_partial_scaled": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
     "b200_prove_combine": (_i, [_i, _vp, _i, _vp, _vp, ctypes.POINTER(_sz)]),
     "b200_dev_fp_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
     "b200_dev_fqe_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
@@ -398,13 +399,15 @@ class Params:
                                     ctypes.addressof(out), ctypes.byref(n)))
         return out.raw[:n.value]
 
-    def prove_partial(self, input_image, rank, world, rank_end=None, d_h=None):
+    def prove_partial(self, input_image, rank, world, rank_end=None, d_h=None, b1_scaled=False):
         """partial sums over slice `rank` - or the run of slices [rank, rank_end) - of `world`; d_h: device vector of
-        H coefficients computed elsewhere (b200_prove_partial_ext)"""
+        H coefficients computed elsewhere (b200_prove_partial_ext); b1_scaled: the B1 slot holds r * (the rank's B1 sum)
+        (b200_prove_partial_scaled; combine with r_fr=None)"""
         out = ctypes.create_string_buffer(partial_bytes(self.curve))
         n = ctypes.c_size_t()
         tm = ProveTimings()
-        check(lib().b200_prove_partial_ext(self.h, _ptr(input_image), _len(input_image), rank,
+        fn = lib().b200_prove_partial_scaled if b1_scaled else lib().b200_prove_partial_ext
+        check(fn(self.h, _ptr(input_image), _len(input_image), rank,
                                            rank + 1 if rank_end is None else rank_end, world, _ptr(d_h),
                                            ctypes.addressof(out), ctypes.byref(n), ctypes.byref(tm)))
         return out.raw[:n.value], tm.as_dict()
@@ -420,9 +423,9 @@ def prove_combine(curve, partials_all, world, r_fr):
     out = ctypes.create_string_buffer(proof_bytes(curve))
     n = ctypes.c_size_t()
     pb = ctypes.create_string_buffer(bytes(partials_all), len(partials_all))
-    rb = ctypes.create_string_buffer(bytes(r_fr), FE)
-    check(lib().b200_prove_combine(curve, ctypes.addressof(pb), world, ctypes.addressof(rb), ctypes.addressof(out),
-                                   ctypes.byref(n)))
+    rb = ctypes.create_string_buffer(bytes(r_fr), FE) if r_fr is not None else None   # None: B1 slots already scaled
+    check(lib().b200_prove_combine(curve, ctypes.addressof(pb), world, ctypes.addressof(rb) if rb else None,
+                                   ctypes.addressof(out), ctypes.byref(n)))
     return out.raw[:n.value]
 
 
@@ -443,7 +446,7 @@ def groth16_finalize(curve, proof, r_fr, s_fr, extras):
     return out.raw[:n.value]
 
 
-def prove_batch(jobs, timings=False):
+def prove_batch(jobs, timings=False, b1_scaled=False):
     """Several proofs in flight at once on the current device (b200_prove_batch). jobs: sequence of
     (Params, host_input_image) for whole proofs or (Params, host_input_image, rank, world) for one rank's partial
     sums. Returns the list of proof (or partial-sum) byte strings, in job order."""
@@ -459,6 +462,7 @@ def prove_batch(jobs, timings=False):
         a.key = key.h.value if hasattr(key.h, "value") else key.h
         a.h_input, a.input_bytes = _ptr(image), _len(image)
         a.h_out, a.rank, a.world = ctypes.addressof(out), rank, world
+        a.b1_scaled = 1 if b1_scaled else 0   # partial sums with r * B1 in the B1 slot (b200_prove_partial_scaled)
     check(lib().b200_prove_batch(ctypes.addressof(arr), len(jobs)))
     res = [o.raw[:a.out_bytes] for o, a in zip(outs, arr)]
     return (res, [a.timings.as_dict() for a in arr]) if timings else res

@@ -61,7 +61,27 @@ struct HostOps {
     Fp<FrP>::from_mont(k, k);
     Proj<F> a, c;
     memcpy(&a, p, sizeof(a));
-    proj_scalar_mul<G>(c, a, k.l, kLimbs);
+    // fixed 4-bit windows: 14 additions for the table 1P .. 15P, then 4 doublings + at most one addition per nibble
+    // (753 doublings + ~190 additions instead of + ~376): the same group element, hence the same affine bytes
+    Proj<F> tab[16];
+    proj_set_zero(tab[0]);
+    tab[1] = a;
+    for (int i = 2; i < 16; i++) {
+      if (i % 2 == 0) proj_dbl<G>(tab[i], tab[i / 2]);
+      else proj_add<G>(tab[i], tab[i - 1], a);
+    }
+    proj_set_zero(c);
+    bool found = false;
+    for (int nib = kLimbs * 8 - 1; nib >= 0; nib--) {
+      const uint32_t d = (k.l[nib / 8] >> ((nib % 8) * 4)) & 15u;
+      if (found)
+        for (int t = 0; t < 4; t++) proj_dbl<G>(c, c);
+      if (d) {
+        if (found) proj_add<G>(c, c, tab[d]);
+        else c = tab[d];
+        found = true;
+      }
+    }
     memcpy(out, &c, sizeof(c));
   }
   static void to_affine(const void *p, void *out) {
@@ -872,8 +892,11 @@ int b200_msm_wait(b200_msm_pending *pending) {
 
 // Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
 // multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
+// h_r_fr / r_b1_out (optional, both or neither): r * (this call's B1 sum) is computed in B1's host tail, i.e. while the
+// GPU is still busy with the L and H MSMs, instead of serially after the join (753 doublings on one core).
 static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
-                          unsigned char *partials, b200_prove_timings *tm, const void *d_h_external = nullptr) {
+                          unsigned char *partials, b200_prove_timings *tm, const void *d_h_external = nullptr,
+                          const unsigned char *h_r_fr = nullptr, unsigned char *r_b1_out = nullptr) {
   const size_t d = p->d, m = p->m;
   const size_t need = 96 * ((m + 1) + 3 * (d + 1) + 1);
   if (input_bytes != need) return set_error(-4, "input image has %zu bytes, expected %zu", input_bytes, need);
@@ -967,12 +990,18 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
                                            p->pre.plan[j], o, tail, share, &p->pre.dedup[j]);
     else
       rc_all = msm_dispatch_deferred(curve, J.group, J.scalars + lo * 96, J.points + lo * J.stride, hi - lo, o, tail);
-    if (rc_all == 0)
-      tails.push_back(std::async(std::launch::async, [tail] {
+    if (rc_all == 0) {
+      const unsigned char *scale_by = (j == 1 && r_b1_out) ? h_r_fr : nullptr;  // r_b1_out may be o itself
+      tails.push_back(std::async(std::launch::async, [tail, scale_by, o, r_b1_out, curve] {
         TailResult r;
         r.rc = tail(r.err);
+        if (r.rc == 0 && scale_by && b200_g1_scale(curve, scale_by, o, r_b1_out) != 0) {
+          r.rc = -1;
+          r.err = "r * Bt1 failed";
+        }
         return r;
       }));
+    }
     *J.ms = now_ms() - a;
   }
   msm_select_slot(0);
@@ -1014,10 +1043,24 @@ int b200_prove_partial_ext(b200_params *p, const void *h_input, size_t input_byt
   if (partial_bytes) *partial_bytes = partial_size(p->curve);
   return 0;
 }
+int b200_prove_partial_scaled(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
+                              const void *d_h_coefficients, void *h_partials, size_t *partial_bytes,
+                              b200_prove_timings *timings) {
+  B200_CHECK(require_device());
+  unsigned char r[96];
+  if (input_bytes < 96) return set_error(-4, "input image has %zu bytes", input_bytes);
+  B200_CUDA_CHECK(cudaMemcpy(r, (const unsigned char *)h_input + input_bytes - 96, 96, cudaMemcpyDefault));
+  unsigned char *part = (unsigned char *)h_partials;
+  B200_CHECK(prove_partials(p, h_input, input_bytes, rank, rank_end, world, part, timings, d_h_coefficients, r,
+                            part + proj_bytes(p->curve, 1)));  // the B1 slot is scaled in place by its own tail
+  if (partial_bytes) *partial_bytes = partial_size(p->curve);
+  return 0;
+}
 
 // C = Ht + Lt + r*Bt1 (main.cpp:253), then A | B | C in wire format (main.cpp:94-100)
-int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
-                       size_t *out_bytes) {
+// r_b1 (optional): r * Bt1 when the caller already has it (b200_prove computes it under the GPU work)
+static int combine_partials(int curve, const void *h_partials_all, int world, const void *h_r_fr, const unsigned char *r_b1,
+                            void *h_out, size_t *out_bytes) {
   if (curve != 0 && curve != 1) return set_error(-1, "bad curve %d", curve);
   const size_t g1p = proj_bytes(curve, 1), g2p = proj_bytes(curve, 2), ps = partial_size(curve);
   const size_t off[5] = {0, g1p, 2 * g1p, 2 * g1p + g2p, 3 * g1p + g2p};
@@ -1032,7 +1075,9 @@ int b200_prove_combine(int curve, const void *h_partials_all, int world, const v
     }
   }
   std::vector<unsigned char> rb(g1p), c(g1p);
-  B200_CHECK(b200_g1_scale(curve, h_r_fr, sum.data() + off[1], rb.data()));
+  if (r_b1) memcpy(rb.data(), r_b1, g1p);
+  else if (!h_r_fr) memcpy(rb.data(), sum.data() + off[1], g1p);  // partials of b200_prove_partial_scaled
+  else B200_CHECK(b200_g1_scale(curve, h_r_fr, sum.data() + off[1], rb.data()));
   B200_CHECK(b200_g1_add(curve, sum.data() + off[4], rb.data(), c.data()));
   B200_CHECK(b200_g1_add(curve, sum.data() + off[3], c.data(), c.data()));
   unsigned char *o = (unsigned char *)h_out;
@@ -1045,17 +1090,22 @@ int b200_prove_combine(int curve, const void *h_partials_all, int world, const v
   if (out_bytes) *out_bytes = (size_t)(o - (unsigned char *)h_out);
   return 0;
 }
+int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
+                       size_t *out_bytes) {
+  return combine_partials(curve, h_partials_all, world, h_r_fr, nullptr, h_out, out_bytes);
+}
 
 int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_out, size_t *out_bytes,
                b200_prove_timings *timings) {
   B200_CHECK(require_device());
   double t0 = now_ms();
-  std::vector<unsigned char> part(partial_size(p->curve));
-  B200_CHECK(prove_partials(p, h_input, input_bytes, 0, 1, 1, part.data(), timings));
-  double t1 = now_ms();
+  std::vector<unsigned char> part(partial_size(p->curve)), r_b1(proj_bytes(p->curve, 1));
   unsigned char r[96];  // the input image may live in host or device memory
+  if (input_bytes < 96) return set_error(-4, "input image has %zu bytes", input_bytes);
   B200_CUDA_CHECK(cudaMemcpy(r, (const unsigned char *)h_input + input_bytes - 96, 96, cudaMemcpyDefault));
-  B200_CHECK(b200_prove_combine(p->curve, part.data(), 1, r, h_out, out_bytes));
+  B200_CHECK(prove_partials(p, h_input, input_bytes, 0, 1, 1, part.data(), timings, nullptr, r, r_b1.data()));
+  double t1 = now_ms();
+  B200_CHECK(combine_partials(p->curve, part.data(), 1, r, r_b1.data(), h_out, out_bytes));
   if (timings) {
     timings->tail_ms += now_ms() - t1;
     timings->total_ms = now_ms() - t0;
@@ -1171,6 +1221,9 @@ class ProofWorker {
 
 int run_proof_job(b200_proof_job *j) {
   if (!j->key || !j->h_input || !j->h_out) return set_error(-1, "proof job: null key, input or output");
+  if (j->world > 1 && j->b1_scaled)
+    return b200_prove_partial_scaled(j->key, j->h_input, j->input_bytes, j->rank, j->rank_end > j->rank ? j->rank_end : j->rank + 1,
+                                     j->world, j->d_h_coefficients, j->h_out, &j->out_bytes, &j->timings);
   if (j->world > 1)
     return b200_prove_partial_ext(j->key, j->h_input, j->input_bytes, j->rank, j->rank_end > j->rank ? j->rank_end : j->rank + 1,
                                   j->world, j->d_h_coefficients, j->h_out, &j->out_bytes, &j->timings);

@@ -424,6 +424,14 @@ def test_concurrent_proofs_match_reference_golden(b200, dev):
     for j in (0, 1):
         allp = b"".join(parts[r][j] for r in range(world))
         assert b200.prove_combine(cases[j][0], allp, world, inputs[j][-FE:]) == expected[j]
+    # the same with every rank multiplying its own B1 sum by r (b200_prove_partial_scaled): combine without r
+    parts = [b200.prove_batch([(keys[0], inputs[0], r, world), (keys[1], inputs[1], r, world)], b1_scaled=True)
+             for r in range(world)]
+    for j in (0, 1):
+        allp = b"".join(parts[r][j] for r in range(world))
+        assert b200.prove_combine(cases[j][0], allp, world, None) == expected[j]
+    one = b"".join(keys[0].prove_partial(inputs[0], r, 3, b1_scaled=True)[0] for r in range(3))
+    assert b200.prove_combine(0, one, 3, None) == expected[0]
     # a failing job is reported with its index and does not wedge the workers
     with pytest.raises(b200.B200Error, match="proof job 1"):
         b200.prove_batch([(keys[0], inputs[0]), (keys[1], inputs[1][:-FE])])

@@ -90,6 +90,13 @@ def test_combine_of_oracle_partials_reproduces_golden(b200, oracle):
                 oracle.orc_msm(curve, group, ctypes.addressof(sb), ctypes.addressof(pb), hi - lo, ctypes.addressof(out), 1)
                 partials += out.raw
         assert b200.prove_combine(curve, partials, world, x["r"]) == expected
+        # ranks that multiplied their own B1 sum by r (b200_prove_partial_scaled) are combined without r
+        g1p, ps = b200.proj_bytes(curve, 1), len(partials) // world
+        scaled = b""
+        for rank in range(world):
+            part = partials[rank * ps:(rank + 1) * ps]
+            scaled += part[:g1p] + b200.g_scale(curve, 1, x["r"], part[g1p:2 * g1p]) + part[2 * g1p:]
+        assert b200.prove_combine(curve, scaled, world, None) == expected
 
 
 def test_compute_fails_loudly_without_gpu(b200):
