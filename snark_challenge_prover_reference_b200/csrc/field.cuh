@@ -18,6 +18,7 @@
 #include "constants_gen.h"
 
 #if defined(__CUDACC__)
+#pragma nv_diag_suppress 1675  // "#pragma GCC unroll" in the host-only arithmetic is meant for the host compiler
 #include "fp_ptx_gen.cuh"
 #define B200_DEV __device__
 #define B200_INLINE __forceinline__

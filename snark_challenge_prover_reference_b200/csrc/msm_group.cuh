@@ -544,6 +544,52 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
   out[(size_t)j * per_out + q] = acc;
 }
 
+// ---- bucket reduction without per-chunk scalar multiplications (one bucket set: pre-shifted bases) --------------------
+// sum_v v * B_v over nb = per * K buckets (bucket i has value i + 1). A thread (coop.cuh: a lane group) takes K consecutive
+// buckets:  run_q = sum_k B[qK + k],  sum_q = sum_k (k + 1) B[qK + k]  (2K additions by running sums), and the total is
+//   sum_q sum_q  +  K * sum_q q * run_q.
+// msm_reduce_kernel computes q * run_q per chunk by double-and-add: ~28 more point operations per chunk. Here the second
+// sum is taken bit by bit of q:  sum_q q * run_q = sum_b 2^b O_b,  O_b = sum of run_q over the q with bit b set, and the
+// O_b fall out of ONE pairwise tree over the runs: level b adds neighbours, X_{b+1}[i] = X_b[2i] + X_b[2i+1]; the odd
+// elements X_b[2i+1] are exactly the partial sums over the q with bit b set, so they open a new row that the following
+// levels halve like every other row. Rows = {X, S (the sum_q), O_0, O_1, ...}: a step halves all rows and opens one; about
+// 3 additions per chunk in total, log2(per) steps of one addition each. The host finishes
+//   S + K * (O_0 + 2 (O_1 + 2 (...)))   (log2(nb) doublings, msm_host_phase).
+template <class G>
+__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : 1) msm_reduce_rows_kernel(const Proj<typename G::F> *__restrict__ buckets, uint32_t per,
+                                                              uint32_t K, Proj<typename G::F> *__restrict__ rows) {
+  typedef typename G::F F;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= per) return;
+  const Proj<F> *B = buckets + (size_t)t * K;
+  Proj<F> run, sum;
+  proj_set_zero(run);
+  proj_set_zero(sum);
+  for (uint32_t k = K; k-- > 0;) {
+    Proj<F> cur = B[k];
+    proj_add<G>(run, run, cur);
+    proj_add<G>(sum, sum, run);
+  }
+  rows[t] = run;                 // row 0: X_0
+  rows[(size_t)per + t] = sum;   // row 1: S
+}
+// `rows` rows of `len` points -> rows + 1 rows of len / 2 points
+template <class G>
+__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : 1) msm_planes_step_kernel(const Proj<typename G::F> *__restrict__ in, uint32_t rows,
+                                                              uint32_t len, Proj<typename G::F> *__restrict__ out) {
+  typedef typename G::F F;
+  const uint32_t half = len / 2;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (rows + 1) * half) return;
+  const uint32_t r = t / half, i = t % half;
+  if (r == rows) {  // the new row: the odd elements of X
+    out[t] = in[2 * i + 1];
+    return;
+  }
+  Proj<F> a = in[(size_t)r * len + 2 * i], b = in[(size_t)r * len + 2 * i + 1];
+  proj_add<G>(a, a, b);
+  out[t] = a;
+}
 
 // Bucket accumulation, default mode: one thread per task (XYZZ mixed additions), parallel fold of heavy buckets,
 // per-bucket combine of the task sums. `pw` owns the entry lists / task arrays (this MSM's workspace or the one it
@@ -747,7 +793,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   const uint32_t nb = plan.nb;
   const size_t nbuckets = plan.nbuckets;
   B200_CHECK(ws.buckets.reserve(nbuckets * sizeof(Proj<F>)));
-  stage = ws.next_staging((size_t)W * sizeof(Proj<F>));
+  stage = ws.next_staging((size_t)(W > 1 ? W : 32) * sizeof(Proj<F>));  // one bucket set: up to 1 + log2(nb) points
   if (!stage) return set_error(-5, "msm: pinned staging allocation failed");
   stage->slot = msm_current_slot();
   for (int i = 0; i < 4; i++) stage->prep_ev[i] = share_slot >= 0 ? nullptr : ws.tm_ev[i];
@@ -768,7 +814,73 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   // ---- bucket reduction (enqueued, not awaited): chunks of K buckets, then tree sum per bucket set
   B200_CUDA_CHECK(cudaEventRecord(stage->t0, st));
   Proj<F> *cur = nullptr;
-  if (msm_use_coop((size_t)W * nb)) {
+  size_t nout = (size_t)W;  // points copied to the host
+  static const bool planes_env = getenv("B200_REDUCE_PLANES") ? atoi(getenv("B200_REDUCE_PLANES")) != 0 : true;
+  if (W == 1 && planes_env) {
+    // one bucket set: chunk sums + bit-plane tree (msm_reduce_rows_kernel), thread per chunk or lane group per chunk
+    const bool coop = msm_use_coop(nb);
+    typedef CoopTables<G> CT;
+    constexpr int LG = CT::kLanes, groups_per_block = 128 / LG;
+    const size_t smem_red = groups_per_block * coop_group_bytes<G>(3), smem_step = groups_per_block * coop_group_bytes<G>(2);
+    static uint32_t resident[2] = {0, 0};  // chunks in flight at once: threads / lane groups of one wave
+    if (!resident[coop]) {
+      int per_sm = 0, dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (coop) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(msm_reduce_rows_coop_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_red));
+        B200_CUDA_CHECK(cudaFuncSetAttribute(msm_planes_step_coop_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_step));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_reduce_rows_coop_kernel<G>, 128, smem_red);
+      } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msm_reduce_rows_kernel<G>, 128, 0);
+      }
+      resident[coop] = (uint32_t)((per_sm > 0 ? per_sm : 1) * sms * (coop ? groups_per_block : 128));
+    }
+    // chunk length: the dependent chain is waves * 2K additions + log2(per) tree levels; ties go to the longer chunk
+    // ((2K + 3) / K additions per bucket)
+    uint32_t K = coop ? 4 : 2, best = 0xffffffffu;
+    for (uint32_t k = K; k <= 64 && k <= nb; k <<= 1) {
+      const uint32_t chunks = nb / k, waves = (chunks + resident[coop] - 1) / resident[coop];
+      uint32_t lg = 0;
+      while ((1u << lg) < chunks) lg++;
+      const uint32_t est = waves * 2 * k + lg;
+      if (est <= best) {
+        best = est;
+        K = k;
+      }
+    }
+    if (K > nb) K = nb;
+    const uint32_t per = nb / K;
+    B200_CHECK(ws.red_a.reserve((size_t)2 * per * sizeof(Proj<F>)));
+    B200_CHECK(ws.red_b.reserve(((size_t)3 * per / 2 + 2) * sizeof(Proj<F>)));
+    cur = ws.red_a.as<Proj<F>>();
+    Proj<F> *nxt = ws.red_b.as<Proj<F>>();
+    if (coop)
+      msm_reduce_rows_coop_kernel<G><<<grid_for((size_t)per * LG, 128), 128, smem_red, st>>>(ws.buckets.as<Proj<F>>(), per, K, cur);
+    else
+      msm_reduce_rows_kernel<G><<<grid_for(per, 128), 128, 0, st>>>(ws.buckets.as<Proj<F>>(), per, K, cur);
+    B200_CUDA_CHECK(cudaGetLastError());
+    note_launch();
+    uint32_t rows = 2, len = per;
+    while (len > 1) {
+      const size_t outs = (size_t)(rows + 1) * (len / 2);
+      if (coop)
+        msm_planes_step_coop_kernel<G><<<grid_for(outs * LG, 128), 128, smem_step, st>>>(cur, rows, len, nxt);
+      else
+        msm_planes_step_kernel<G><<<grid_for(outs, 128), 128, 0, st>>>(cur, rows, len, nxt);
+      B200_CUDA_CHECK(cudaGetLastError());
+      note_launch();
+      Proj<F> *t = cur;
+      cur = nxt;
+      nxt = t;
+      rows++;
+      len /= 2;
+    }
+    plan.red_planes = (int)rows - 2;
+    plan.red_K = K;
+    nout = (size_t)rows - 1;  // S, O_0 .. O_{planes-1}
+    cur += 1;                 // (skip X: the sum of all buckets carries weight 0)
+  } else if (msm_use_coop((size_t)W * nb)) {
     // lane-cooperative reduction (coop.cuh): a group of 8 / 16 / 32 lanes per chunk. The chunk length makes the chunks
     // about one wave of resident groups: short dependent chains, no second wave.
     typedef CoopTables<G> CT;
@@ -834,7 +946,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
     per = per_out;
   }
   }
-  B200_CUDA_CHECK(cudaMemcpyAsync(stage->pinned, cur, (size_t)W * sizeof(Proj<F>), cudaMemcpyDeviceToHost, st));
+  B200_CUDA_CHECK(cudaMemcpyAsync(stage->pinned, cur, nout * sizeof(Proj<F>), cudaMemcpyDeviceToHost, st));
   B200_CUDA_CHECK(cudaEventRecord(stage->t1, st));
   B200_CUDA_CHECK(cudaEventRecord(stage->done, st));
   return 0;
@@ -845,7 +957,7 @@ template <class G>
 int msm_collect(const MsmPlan &plan, MsmWorkspace::Staging *stage, std::vector<Proj<typename G::F>> &win) {
   typedef typename G::F F;
   B200_CUDA_CHECK(cudaEventSynchronize(stage->done));
-  const int W = plan.merged ? 1 : plan.W;
+  const int W = plan.red_planes >= 0 ? 1 + plan.red_planes : plan.merged ? 1 : plan.W;
   win.resize(W);
   memcpy(win.data(), stage->pinned, (size_t)W * sizeof(Proj<F>));
   float ms = 0;
@@ -873,8 +985,22 @@ double msm_host_phase(const MsmPlan &plan, const std::vector<Proj<typename G::F>
   Proj<F> result;
   proj_set_zero(result);
   auto t0 = std::chrono::steady_clock::now();
-  if (plan.merged) result = win[0];  // pre-shifted bases: the single bucket set already carries the 2^start_j weights
-  for (int j = plan.merged ? -1 : plan.W - 1; j >= 0; j--) {
+  if (plan.red_planes >= 0) {
+    // one bucket set reduced by bit planes: win = {S, O_0, .., O_{planes-1}}, result = S + K * sum_b 2^b O_b
+    result = win[0];
+    if (plan.red_planes > 0) {
+      Proj<F> acc = win[plan.red_planes];
+      for (int b = plan.red_planes - 2; b >= 0; b--) {
+        proj_dbl<G>(acc, acc);
+        proj_add<G>(acc, acc, win[1 + b]);
+      }
+      for (uint32_t k = plan.red_K; k > 1; k >>= 1) proj_dbl<G>(acc, acc);
+      proj_add<G>(result, result, acc);
+    }
+  } else if (plan.merged) {
+    result = win[0];  // pre-shifted bases: the single bucket set already carries the 2^start_j weights
+  }
+  for (int j = (plan.merged || plan.red_planes >= 0) ? -1 : plan.W - 1; j >= 0; j--) {
     if (!proj_is_zero(result))
       for (uint32_t k = 0; k < (plan.windows[j] >> 16); k++) proj_dbl<G>(result, result);
     proj_add<G>(result, result, win[j]);

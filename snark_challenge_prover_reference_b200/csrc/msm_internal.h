@@ -105,6 +105,10 @@ struct MsmPlan {
   size_t ntasks = 0;            // number of tasks of this call (set by msm_prepare)
   uint32_t max_tasks_per_bucket = 0;  // largest number of task sums any bucket has (set by msm_prepare)
   uint32_t max_count = 0;             // largest bucket (set by msm_prepare)
+  // bucket reduction by bit planes (msm_reduce_rows_kernel, one bucket set): the device returns S and O_0 .. O_{planes-1},
+  // the host finishes S + red_K * sum_b 2^b O_b. -1: the device returns one finished sum per bucket set.
+  int red_planes = -1;
+  uint32_t red_K = 0;
 };
 
 // Diagnostics: when a base event has been set (msm_timeline_begin), msm_collect stores for the issuing slot the times
