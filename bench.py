@@ -271,10 +271,10 @@ def regroup_partials(blobs, pbytes):
 
 PLAN_UNITS = 64   # an uneven split of the large proof is expressed in runs of 1/64 slices (b200_prove_partial_span)
 # model behind the "balanced" plan, from this round's single-GPU measurements (profiles/r02_summary.md): the MNT4753
-# proof costs a fixed ~35 ms (replicated compute_H, bucket reductions, preparation) plus ~370 ms x the rank's share of
-# the points; the whole MNT6753 proof adds ~40 ms to a rank that also works on MNT4753 (its latency-bound kernels hide
-# partly under the accumulations)
-PLAN_MODEL = {"mnt4_fixed_ms": 35.0, "mnt4_per_share_ms": 370.0, "mnt6_whole_ms": 40.0}
+# proof costs a fixed ~34 ms (replicated compute_H, bucket reductions, preparation) plus ~336 ms x the rank's share of
+# the points (370 ms whole, 81.7 ms for a 1/7 share); the whole MNT6753 proof adds ~38 ms to a rank that also works on
+# MNT4753 (34 ms alone; next to MNT4753's accumulations its kernels get no free multiplier cycles)
+PLAN_MODEL = {"mnt4_fixed_ms": 34.0, "mnt4_per_share_ms": 336.0, "mnt6_whole_ms": 38.0}
 
 
 def step_plan(world, mode=None):
