@@ -555,8 +555,11 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 // levels halve like every other row. Rows = {X, S (the sum_q), O_0, O_1, ...}: a step halves all rows and opens one; about
 // 3 additions per chunk in total, log2(per) steps of one addition each. The host finishes
 //   S + K * (O_0 + 2 (O_1 + 2 (...)))   (log2(nb) doublings, msm_host_phase).
+#ifndef B200_RED_BLOCKS_G2
+#define B200_RED_BLOCKS_G2 1  // resident blocks per SM asked of the G2 instantiations (1: ptxas' choice, ~255 registers)
+#endif
 template <class G>
-__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : 1) msm_reduce_rows_kernel(const Proj<typename G::F> *__restrict__ buckets, uint32_t per,
+__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : B200_RED_BLOCKS_G2) msm_reduce_rows_kernel(const Proj<typename G::F> *__restrict__ buckets, uint32_t per,
                                                               uint32_t K, Proj<typename G::F> *__restrict__ rows) {
   typedef typename G::F F;
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : 1) msm_reduce_ro
 }
 // `rows` rows of `len` points -> rows + 1 rows of len / 2 points
 template <class G>
-__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : 1) msm_planes_step_kernel(const Proj<typename G::F> *__restrict__ in, uint32_t rows,
+__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : B200_RED_BLOCKS_G2) msm_planes_step_kernel(const Proj<typename G::F> *__restrict__ in, uint32_t rows,
                                                               uint32_t len, Proj<typename G::F> *__restrict__ out) {
   typedef typename G::F F;
   const uint32_t half = len / 2;
