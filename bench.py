@@ -269,6 +269,7 @@ def regroup_partials(blobs, pbytes):
     return out
 
 
+DEFAULT_PLAN = "balanced"
 PLAN_UNITS = 64   # an uneven split of the large proof is expressed in runs of 1/64 slices (b200_prove_partial_span)
 # model behind the "balanced" plan, from this round's single-GPU measurements (profiles/r02_summary.md): the MNT4753
 # proof costs a fixed ~34 ms (replicated compute_H, bucket reductions, preparation) plus ~336 ms x the rank's share of
@@ -286,8 +287,11 @@ def step_plan(world, mode=None):
                 sized so that all ranks finish together under PLAN_MODEL.
     Returns (mode, runs, small_rank): runs[r] = (lo, hi) in units of 1/PLAN_UNITS of the MNT4753 point ranges (lo == hi:
     the rank takes no part in it); small_rank = the rank proving MNT6753 whole, or None when it is sharded too."""
-    mode = mode or os.environ.get("B200_BENCH_MNT6_MODE") or ("balanced" if world >= 2 else "shard")
+    mode = mode or os.environ.get("B200_BENCH_MNT6_MODE") or (DEFAULT_PLAN if world >= 2 else "shard")
     U = PLAN_UNITS
+    if world > 1 and mode == "queries":
+        spans, _ = query_plan(world)
+        return "queries", [(0, sum(e - b for b, e in sp)) if sp else (0, 0) for sp in spans], world - 1
     if world == 1 or mode == "shard":
         cuts = [r * U // world for r in range(world)] + [U]
         return "shard", [(cuts[r], cuts[r + 1]) for r in range(world)], None
@@ -303,6 +307,80 @@ def step_plan(world, mode=None):
     return "balanced", [(cuts[r], cuts[r + 1]) for r in range(world)], world - 1
 
 
+# ---- per-query plan ("queries"): the five MSMs of the large proof are cut independently (b200_prove_partial_queries).
+# Cutting every MSM N ways makes every GPU repeat what does not shrink with its share: the witness map (13 ms), five
+# bucket reductions and preparations, and narrower windows (c = 18 instead of 21 at a 1/7 share: 17 % more bucket
+# insertions per point). Here a GPU gets FEW MSMs and a large share of each: e.g. the whole H MSM (one compute_H on one
+# GPU), a third of B2, ... Model, ms on one B200 at full size (profiles/r02_summary.md 8): accumulation per MSM, its
+# bucket reduction, and what a slice of f costs.
+QUERY_ORDER = ("A", "B1", "B2", "L", "H")          # the order of b200_params_query / of the spans
+QUERY_MODEL = {"acc": {"A": 24.3, "B1": 49.3, "B2": 146.0, "L": 49.3, "H": 49.3},
+               "red": {"A": 5.9, "B1": 5.9, "B2": 20.5, "L": 5.9, "H": 5.9},
+               "compute_h": 13.0, "prep": 1.3, "rank_fixed": 3.0, "mnt6_whole": 38.0}
+
+
+def slice_cost_ms(q, units, model=None):
+    """modelled time of `units`/PLAN_UNITS of MSM q on one GPU: accumulation with the window width a slice of that size
+    gets (one bit narrower per halving), its bucket reduction (which shrinks with the bucket count, not below 30 %),
+    one preparation; H also pays the witness map"""
+    M = model or QUERY_MODEL
+    if units <= 0:
+        return 0.0
+    import math
+    f = units / PLAN_UNITS
+    c = max(8, round(21 + math.log2(f)))
+    windows = -(-754 // c)
+    t = M["acc"][q] * f * windows / 36.0 + M["red"][q] * max(0.3, 2.0 ** (c - 21)) + M["prep"]
+    return t + (M["compute_h"] if q == "H" else 0.0)
+
+
+def query_plan(world, model=None):
+    """per rank the runs [first, end) of PLAN_UNITS slices of A, B1, B2, L, H it sums (None: no part in the large proof),
+    and the modelled per-rank times. MNT6753 runs whole on the last rank. Smallest makespan T for which a greedy fill
+    works: MSMs largest first, each poured into the least-loaded GPUs up to T."""
+    M = model or QUERY_MODEL
+    U = PLAN_UNITS
+    # largest first, H counted with its witness map so that it is placed while whole GPUs are still free (every GPU with
+    # a part of H repeats compute_H); the cheapest MSMs come last and are the ones cut to even the GPUs out
+    order = sorted(QUERY_ORDER, key=lambda q: -(M["acc"][q] + (M["compute_h"] if q == "H" else 0.0)))
+
+    def fill(T):
+        load = [M["rank_fixed"]] * world
+        load[world - 1] += M["mnt6_whole"]
+        spans = [{q: (0, 0) for q in QUERY_ORDER} for _ in range(world)]
+        for q in order:
+            left, at = U, 0
+            for r in sorted(range(world), key=lambda r: load[r]):
+                if left == 0:
+                    break
+                u = left
+                while u > 0 and load[r] + slice_cost_ms(q, u, M) > T:
+                    u -= 1
+                if u == 0:
+                    continue
+                spans[r][q] = (at, at + u)
+                load[r] += slice_cost_ms(q, u, M)
+                at += u
+                left -= u
+            if left:
+                return None
+        return spans, load
+
+    lo, hi = 0.0, 2000.0
+    while hi - lo > 0.25:
+        mid = (lo + hi) / 2
+        if fill(mid) is None:
+            lo = mid
+        else:
+            hi = mid
+    spans, load = fill(hi)
+    out = []
+    for r in range(world):
+        pairs = [spans[r][q] for q in QUERY_ORDER]
+        out.append(pairs if any(e > b for b, e in pairs) else None)
+    return out, [round(v, 1) for v in load]
+
+
 def rank_jobs(rank, world, mode=None):
     """this rank's share of a step: [(proof index, first slice, number of slices the proof is cut into, end slice)] -
     the rank sums slices [first, end) of every MSM of that proof; (i, 0, 1, 1) = the whole proof"""
@@ -310,7 +388,8 @@ def rank_jobs(rank, world, mode=None):
     jobs = []
     lo, hi = runs[rank]
     if hi > lo:
-        jobs.append((0, lo, PLAN_UNITS, hi) if world > 1 else (0, 0, 1, 1))
+        # ("queries": the runs differ per MSM - rank_spans(); the tuple only says that the rank has a part in the proof)
+        jobs.append(((0, 0, PLAN_UNITS, 0) if mode == "queries" else (0, lo, PLAN_UNITS, hi)) if world > 1 else (0, 0, 1, 1))
     if small_rank is None:
         if world > 1:
             jobs.append((1, rank, world, rank + 1))
@@ -319,6 +398,15 @@ def rank_jobs(rank, world, mode=None):
     elif rank == small_rank:
         jobs.append((1, 0, 1, 1))
     return jobs
+
+
+def rank_spans(rank, world, mode=None):
+    """{proof index: per-query runs} for the proofs this rank shards per query (plan "queries"), else {}"""
+    mode = step_plan(world, mode)[0]
+    if mode != "queries":
+        return {}
+    sp = query_plan(world)[0][rank]
+    return {0: sp} if sp else {}
 
 
 def pack_rank_blob(jobs, outs, slot):
@@ -423,6 +511,7 @@ def b200_arm(args):
     files = ensure_synth(k4, k6, wait_only=local != 0)
     mode, runs, small_rank = step_plan(world)
     my_jobs = rank_jobs(rank, world)  # (index into shapes, first slice, slices per proof, end slice)
+    my_spans = rank_spans(rank, world)  # plan "queries": {0: per-query runs of the large proof}
     # the drop-in path, measured before this process takes its own 100 GB of HBM (separate processes, N = 1 only)
     drop_in = drop_in_run(files) if world == 1 and not args.no_cpu_baseline else None
 
@@ -435,7 +524,7 @@ def b200_arm(args):
         t0 = time.perf_counter()
         keys[i] = pkg.Params.from_file(shapes[i][0], os.path.join(files, name + "-parameters"))
         load_ms[name] = dict(keys[i].load_ms(), wall=1e3 * (time.perf_counter() - t0))
-        preprocess_s[name] = keys[i].precompute(r, w, e)
+        preprocess_s[name] = keys[i].precompute_queries(my_spans[i], w) if i in my_spans else keys[i].precompute(r, w, e)
     import numpy as np
     host_inputs, dev_inputs = {}, {}
     for i, _, _, _ in my_jobs:
@@ -454,7 +543,7 @@ def b200_arm(args):
     # (a*b - c) / Z -> icosetFFT and broadcasts the coefficients; every rank then runs its MSMs on them
     # (b200_prove_partial_ext). NCCL is the plumbing, the transforms are the same kernels.
     big_ranks = [r for r in range(world) if runs[r][1] > runs[r][0]]
-    split_h = world >= 3 and len(big_ranks) >= 3 and os.environ.get("B200_BENCH_SPLIT_H", "0") == "1"
+    split_h = world >= 3 and len(big_ranks) >= 3 and os.environ.get("B200_BENCH_SPLIT_H", "0") == "1" and mode != "queries"
     h_state = {}
     if split_h:
         grp = dist.new_group(big_ranks)   # every rank must take part in creating it
@@ -498,7 +587,8 @@ def b200_arm(args):
             busy = time.perf_counter() - t0
         else:
             h_ext = witness_map_split(inputs[0]) if split_h and rank in big_ranks else None
-            jobs = [(keys[i], inputs[i], r, w, e, h_ext if i == 0 else None) if w > 1 else (keys[i], inputs[i]) for i, r, w, e in my_jobs]
+            jobs = [(keys[i], inputs[i], r, w, e, h_ext if i == 0 else None, my_spans.get(i)) if w > 1 else (keys[i], inputs[i])
+                    for i, r, w, e in my_jobs]
             # every rank multiplies its own B1 sum by r under its GPU work (b200_prove_partial_scaled): rank 0's combine is
             # then additions and three inversions, not 753 serial doublings (B200_BENCH_SCALE_AT_COMBINE=1: the old way)
             outs, tms = pkg.prove_batch(jobs, timings=True, b1_scaled=b1_scaled) if jobs else ([], [])
@@ -557,7 +647,18 @@ def b200_arm(args):
     def slice_len(n, r, w, e):
         cut = lambda k: n if k >= w else k * (n // w)
         return cut(e) - cut(r)
-    my_h2d = sum(FE * (slice_len((1 << shapes[i][1]) + 1, r, w, e) + 3 * (1 << shapes[i][1]) + 1) for i, r, w, e in my_jobs)
+
+    def h2d_elements(i, r, w, e):
+        m_i = 1 << shapes[i][1]
+        if i not in my_spans:
+            return slice_len(m_i + 1, r, w, e) + 3 * m_i + 1
+        # per-query runs: the union of the w ranges of A, B1, B2, L (one copy) and, with a part of H, ca / cb / cc
+        sp = my_spans[i]
+        cut = lambda k: m_i + 1 if k >= w else k * ((m_i + 1) // w)
+        los = [cut(b) for (b, en) in sp[:4] if en > b]
+        his = [cut(en) for (b, en) in sp[:4] if en > b]
+        return (max(his) - min(los) if los else 0) + (3 * m_i + 1 if sp[4][1] > sp[4][0] else 0)
+    my_h2d = sum(FE * h2d_elements(i, r, w, e) for i, r, w, e in my_jobs)
     my_d2h = sum(pbytes[i] if w > 1 else proof_len[i] for i, _, w, _ in my_jobs)
     h2d_list, d2h_list = [my_h2d], [my_d2h]
     # every rank's own time inside b200_prove_batch per step (what the plan tries to equalise)
@@ -726,7 +827,10 @@ def b200_arm(args):
                        "l2": "inputs larger than L2: each step streams >1.6 GB of bases and 416 MB of scalars",
                        "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys",
                        "multi_gpu": {"mode": mode, "mnt4753_runs_of_%d" % PLAN_UNITS: runs, "mnt6753_rank": small_rank,
-                                     "rank_busy_ms_per_step": rank_busy_ms, "witness_map": "split over 3 ranks + broadcast" if split_h else "replicated"},
+                                     "rank_busy_ms_per_step": rank_busy_ms,
+                                     "per_query_runs_A_B1_B2_L_H": query_plan(world)[0] if mode == "queries" else None,
+                                     "witness_map": ("on the ranks with a part of H" if mode == "queries" else
+                                                     "split over 3 ranks + broadcast" if split_h else "replicated")},
                        "accumulation": lib_mode + " (auto = batched affine additions for large G2/Fq2 MSMs, XYZZ mixed additions otherwise)",
                        "key_preprocess": "pre-shifted base tables 2^(start_j)*P_i per MSM window, built once per key, "
                                          "outside the timed region (see key_load); see no_tables"},

@@ -187,6 +187,15 @@ int b200_prove_partial_ext(b200_params *p, const void *h_input, size_t input_byt
 int b200_prove_partial_scaled(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
                               const void *d_h_coefficients, void *h_partials, size_t *partial_bytes,
                               b200_prove_timings *timings);
+/* Per-query sharding: spans[2*q], spans[2*q+1] = the run [first, end) of `world` slices this call sums of query q
+ * (0 A, 1 B1, 2 B2, 3 L, 4 H - the order of b200_params_query). An empty run (first == end) leaves O in that slot and, for
+ * H, skips the witness map: a GPU can be given the whole H MSM (one compute_H instead of one per GPU) while others
+ * split B2. Any set of calls whose runs tile [0, world) for every query combines to the proof. b1_scaled: as
+ * b200_prove_partial_scaled. b200_params_precompute_queries builds the base tables for such a slicing. */
+int b200_prove_partial_queries(b200_params *p, const void *h_input, size_t input_bytes, const int *spans, int world,
+                               int b1_scaled, const void *d_h_coefficients, void *h_partials, size_t *partial_bytes,
+                               b200_prove_timings *timings);
+int b200_params_precompute_queries(b200_params *p, const int *spans, int world);
 /* combine `world` partial results (rank-major, as produced by b200_prove_partial) into the final proof; h_r_fr == NULL:
  * the B1 slots are already multiplied by r (b200_prove_partial_scaled) */
 int b200_prove_combine(int curve, const void *h_partials_all, int world, const void *h_r_fr, void *h_out,
@@ -207,6 +216,7 @@ typedef struct {
   int rank_end; /* world > 1: the job owns slices [rank, rank_end) of world; 0 means rank + 1 */
   const void *d_h_coefficients; /* world > 1, optional: see b200_prove_partial_ext */
   int b1_scaled; /* world > 1: nonzero = partial sums as b200_prove_partial_scaled writes them */
+  const int *query_spans; /* world > 1, optional: 10 ints, per-query runs (b200_prove_partial_queries); overrides rank / rank_end */
   int status; /* set by the call: 0 or the job's error code */
   b200_prove_timings timings;
 } b200_proof_job;

@@ -54,7 +54,7 @@ class ProofJob(ctypes.Structure):
     _fields_ = [("key", ctypes.c_void_p), ("h_input", ctypes.c_void_p), ("input_bytes", ctypes.c_size_t),
                 ("h_out", ctypes.c_void_p), ("out_bytes", ctypes.c_size_t), ("rank", ctypes.c_int),
                 ("world", ctypes.c_int), ("rank_end", ctypes.c_int), ("d_h_coefficients", ctypes.c_void_p),
-                ("b1_scaled", ctypes.c_int), ("status", ctypes.c_int), ("timings", ProveTimings)]
+                ("b1_scaled", ctypes.c_int), ("query_spans", ctypes.POINTER(ctypes.c_int)), ("status", ctypes.c_int), ("timings", ProveTimings)]
 
 
 _lib = None
@@ -136,6 +136,9 @@ _SIGNATURES = {
     "b200_params_precompute_span": (_i, [_vp, _i, _i, _i]),
     "b200_prove_partial_ext": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
     "b200_prove_partial_scaled": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, _vp, ctypes.POINTER(_sz), ctypes.POINTER(ProveTimings)]),
+    "b200_prove_partial_queries": (_i, [_vp, _vp, _sz, ctypes.POINTER(_i), _i, _i, _vp, _vp, ctypes.POINTER(_sz),
+                                        ctypes.POINTER(ProveTimings)]),
+    "b200_params_precompute_queries": (_i, [_vp, ctypes.POINTER(_i), _i]),
     "b200_prove_combine": (_i, [_i, _vp, _i, _vp, _vp, ctypes.POINTER(_sz)]),
     "b200_dev_fp_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
     "b200_dev_fqe_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
@@ -399,6 +402,21 @@ class Params:
                                     ctypes.addressof(out), ctypes.byref(n)))
         return out.raw[:n.value]
 
+    def prove_partial_queries(self, input_image, spans, world, d_h=None, b1_scaled=False):
+        """partial sums with a run of slices PER QUERY: spans = [(first, end)] * 5 for A, B1, B2, L, H in units of 1/world
+        (b200_prove_partial_queries); an empty run leaves O in that slot"""
+        out = ctypes.create_string_buffer(partial_bytes(self.curve))
+        n = ctypes.c_size_t()
+        tm = ProveTimings()
+        check(lib().b200_prove_partial_queries(self.h, _ptr(input_image), _len(input_image), _spans(spans), world,
+                                               1 if b1_scaled else 0, _ptr(d_h), ctypes.addressof(out), ctypes.byref(n),
+                                               ctypes.byref(tm)))
+        return out.raw[:n.value], tm.as_dict()
+
+    def precompute_queries(self, spans, world):
+        check(lib().b200_params_precompute_queries(self.h, _spans(spans), world))
+        return lib().b200_params_precompute_ms(self.h) / 1e3
+
     def prove_partial(self, input_image, rank, world, rank_end=None, d_h=None, b1_scaled=False):
         """partial sums over slice `rank` - or the run of slices [rank, rank_end) - of `world`; d_h: device vector of
         H coefficients computed elsewhere (b200_prove_partial_ext); b1_scaled: the B1 slot holds r * (the rank's B1 sum)
@@ -411,6 +429,12 @@ class Params:
                                            rank + 1 if rank_end is None else rank_end, world, _ptr(d_h),
                                            ctypes.addressof(out), ctypes.byref(n), ctypes.byref(tm)))
         return out.raw[:n.value], tm.as_dict()
+
+
+def _spans(spans):
+    flat = [int(v) for pair in spans for v in pair]
+    assert len(flat) == 10, "spans: five (first, end) pairs, for A, B1, B2, L, H"
+    return (ctypes.c_int * 10)(*flat)
 
 
 def _len(x):
@@ -451,7 +475,7 @@ def prove_batch(jobs, timings=False, b1_scaled=False):
     (Params, host_input_image) for whole proofs or (Params, host_input_image, rank, world) for one rank's partial
     sums. Returns the list of proof (or partial-sum) byte strings, in job order."""
     arr = (ProofJob * len(jobs))()
-    outs = []
+    outs, keep = [], []
     for a, job in zip(arr, jobs):
         key, image = job[0], job[1]
         rank, world = (job[2], job[3]) if len(job) > 2 else (0, 1)
@@ -463,6 +487,9 @@ def prove_batch(jobs, timings=False, b1_scaled=False):
         a.h_input, a.input_bytes = _ptr(image), _len(image)
         a.h_out, a.rank, a.world = ctypes.addressof(out), rank, world
         a.b1_scaled = 1 if b1_scaled else 0   # partial sums with r * B1 in the B1 slot (b200_prove_partial_scaled)
+        if len(job) > 6 and job[6] is not None:   # (.., rank_end, d_h, spans): per-query runs
+            keep.append(_spans(job[6]))
+            a.query_spans = keep[-1]
     check(lib().b200_prove_batch(ctypes.addressof(arr), len(jobs)))
     res = [o.raw[:a.out_bytes] for o, a in zip(outs, arr)]
     return (res, [a.timings.as_dict() for a in arr]) if timings else res

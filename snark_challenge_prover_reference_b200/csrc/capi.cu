@@ -84,6 +84,11 @@ struct HostOps {
     }
     memcpy(out, &c, sizeof(c));
   }
+  static void zero(void *out) {  // O = (0 : 1 : 0)
+    Proj<F> z;
+    proj_set_zero(z);
+    memcpy(out, &z, sizeof(z));
+  }
   static void to_affine(const void *p, void *out) {
     Proj<F> a;
     Affine<F> o;
@@ -127,6 +132,7 @@ struct HostOps {
     return set_error(-1, "bad curve %d", (int)(curve));                     \
   } while (0)
 
+static int group_zero(int curve, int group, void *out) { DISPATCH_GROUP(curve, group, zero(out)); }
 static size_t g2_degree(int curve) { return curve == 0 ? 2 : 3; }
 static size_t affine_bytes(int curve, int group) { return 2 * 96 * (group == 1 ? 1 : g2_degree(curve)); }
 static size_t proj_bytes(int curve, int group) { return 3 * 96 * (group == 1 ? 1 : g2_degree(curve)); }
@@ -167,9 +173,11 @@ struct b200_domain {
   Domain *impl;
 };
 
-// Pre-shifted base tables for one (rank, world) slicing of the five queries (see msm_precompute_kernel).
+// Pre-shifted base tables for one slicing of the five queries (see msm_precompute_kernel).
 struct Precomputed {
-  int rank = -1, rank_end = -1, world = -1;  // the slicing the tables were built for: virtual ranks [rank, rank_end) of world
+  // the slicing the tables were built for: query qi (0 A, 1 B1, 2 B2, 3 L, 4 H) covers slices [spans[qi][0], spans[qi][1])
+  // of `world` (an empty span: no table)
+  int spans[5][2] = {{-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}, {-1, -1}}, world = -1;
   DevBuf table[5];
   MsmPlan plan[5];
   MsmDedup dedup[5];  // equal bases inside this rank's slice of each G1 query (job order A, B1, B2, H, L)
@@ -765,14 +773,24 @@ static void query_slice(size_t d, size_t m, int qi, int rank, int rank_end, int 
 // Build (once per key and slicing) the tables of pre-shifted bases for this rank's slice of the five queries.
 int b200_params_precompute(b200_params *p, int rank, int world) { return b200_params_precompute_span(p, rank, rank + 1, world); }
 int b200_params_precompute_span(b200_params *p, int rank, int rank_end, int world) {
+  const int spans[10] = {rank, rank_end, rank, rank_end, rank, rank_end, rank, rank_end, rank, rank_end};
+  return b200_params_precompute_queries(p, spans, world);
+}
+static int check_spans(const int *spans, int world) {
+  if (!spans || world < 1) return set_error(-1, "bad slicing (world %d)", world);
+  for (int q = 0; q < 5; q++)
+    if (spans[2 * q] < 0 || spans[2 * q + 1] < spans[2 * q] || spans[2 * q + 1] > world)
+      return set_error(-1, "bad slice run [%d, %d) of %d for query %d", spans[2 * q], spans[2 * q + 1], world, q);
+  return 0;
+}
+int b200_params_precompute_queries(b200_params *p, const int *spans, int world) {
   B200_CHECK(require_device());
-  if (world < 1 || rank < 0 || rank_end < rank || rank_end > world)
-    return set_error(-1, "bad slice run [%d, %d) of %d", rank, rank_end, world);
-  if (p->pre.rank == rank && p->pre.rank_end == rank_end && p->pre.world == world) return 0;
+  B200_CHECK(check_spans(spans, world));
+  if (p->pre.world == world && memcmp(p->pre.spans, spans, sizeof(p->pre.spans)) == 0) return 0;
   double t0 = now_ms();
   const size_t d = p->d, m = p->m;
   const int jobq[5] = {0, 1, 2, 4, 3};                     // job order A, B1, B2, H, L -> query index
-  p->pre.rank = p->pre.rank_end = p->pre.world = -1;
+  p->pre.world = -1;
   // The grouping of equal bases (host: hash + sort of the G1 queries' wire bytes) runs on a thread of its own, under
   // the table kernels.
   int dev = 0;
@@ -782,7 +800,7 @@ int b200_params_precompute_span(b200_params *p, int rank, int rank_end, int worl
   for (int j = 0; j < 5; j++) {
     const int qi = jobq[j];
     size_t lo, hi;
-    query_slice(d, m, qi, rank, rank_end, world, lo, hi);
+    query_slice(d, m, qi, spans[2 * qi], spans[2 * qi + 1], world, lo, hi);
     slices[j].group = qi == 2 ? 2 : 1;
     slices[j].pts = (const char *)p->q[qi] + lo * affine_bytes(p->curve, slices[j].group);
     slices[j].n = hi - lo;
@@ -818,8 +836,7 @@ int b200_params_precompute_span(b200_params *p, int rank, int rank_end, int worl
   if (verbose) fprintf(stderr, "[b200] waited %.0f ms for the equal-base grouping\n", now_ms() - tj);
   if (rc) return rc;
   if (dedup_rc) return set_error(dedup_rc, "%s", dedup_err.c_str());
-  p->pre.rank = rank;
-  p->pre.rank_end = rank_end;
+  memcpy(p->pre.spans, spans, sizeof(p->pre.spans));
   p->pre.world = world;
   p->pre.build_ms = now_ms() - t0;
   return 0;
@@ -894,29 +911,38 @@ int b200_msm_wait(b200_msm_pending *pending) {
 // multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
 // h_r_fr / r_b1_out (optional, both or neither): r * (this call's B1 sum) is computed in B1's host tail, i.e. while the
 // GPU is still busy with the L and H MSMs, instead of serially after the join (753 doublings on one core).
-static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
+// spans: per query (0 A, 1 B1, 2 B2, 3 L, 4 H) the run [first, end) of `world` slices this call sums; an empty run
+// leaves O in that slot (and, for H, skips the witness map).
+static int prove_partials(b200_params *p, const void *h_input, size_t input_bytes, const int *spans, int world,
                           unsigned char *partials, b200_prove_timings *tm, const void *d_h_external = nullptr,
                           const unsigned char *h_r_fr = nullptr, unsigned char *r_b1_out = nullptr) {
   const size_t d = p->d, m = p->m;
   const size_t need = 96 * ((m + 1) + 3 * (d + 1) + 1);
   if (input_bytes != need) return set_error(-4, "input image has %zu bytes, expected %zu", input_bytes, need);
-  if (world < 1 || rank < 0 || rank_end < rank || rank_end > world)
-    return set_error(-1, "bad slice run [%d, %d) of %d", rank, rank_end, world);
+  B200_CHECK(check_spans(spans, world));
   const char *in = (const char *)h_input;
   double t0 = now_ms();
   // w first (it drives four of the five MSMs); ca/cb/cc follow asynchronously on the default stream right before
   // compute_H, under the MSMs that are already running (truly asynchronous when the image is in pinned memory)
   // (a rank of a sharded proof only needs the part of w its slices of A/B1/B2 (w[i]) and L (w[i+2]) read)
   {
-    size_t lo, hi;
-    query_slice(d, m, 0, rank, rank_end, world, lo, hi);  // covers L's scalars w[lo3 + 2 .. hi3 + 2) too (query_slice)
-    B200_CUDA_CHECK(cudaMemcpy((char *)p->w.p + lo * 96, in + lo * 96, (hi - lo) * 96, cudaMemcpyDefault));
+    size_t wlo = m + 1, whi = 0;  // the union of the w ranges of the w-driven queries (L's point i reads w[i + 2])
+    for (int qi = 0; qi < 4; qi++) {
+      size_t lo, hi;
+      query_slice(d, m, qi, spans[2 * qi], spans[2 * qi + 1], world, lo, hi);
+      if (hi <= lo) continue;
+      const size_t off = qi == 3 ? 2 : 0;
+      if (lo + off < wlo) wlo = lo + off;
+      if (hi + off > whi) whi = hi + off;
+    }
+    if (whi > wlo)
+      B200_CUDA_CHECK(cudaMemcpy((char *)p->w.p + wlo * 96, in + wlo * 96, (whi - wlo) * 96, cudaMemcpyDefault));
   }
   double t1 = now_ms();
   const int curve = p->curve;
   const size_t g1a = affine_bytes(curve, 1), g2a = affine_bytes(curve, 2);
   const size_t g1p = proj_bytes(curve, 1), g2p = proj_bytes(curve, 2);
-  if (use_precompute()) B200_CHECK(b200_params_precompute_span(p, rank, rank_end, world));
+  if (use_precompute()) B200_CHECK(b200_params_precompute_queries(p, spans, world));
   struct Job { int group; const char *scalars; const char *points; size_t n; size_t stride; size_t outb; double *ms; };
   double ms[5] = {0, 0, 0, 0, 0};
   Job jobs[5] = {
@@ -941,7 +967,23 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   const bool h_first = h_first_env >= 0 ? h_first_env != 0 : false;
   const int order_default[5] = {2, 0, 1, 4, 3}, order_h_first[5] = {3, 2, 0, 1, 4};
   const int *order = h_first ? order_h_first : order_default;
-  const int slot_of_job[5] = {1, 2, 0, 4, 3};  // workspace of A, B1, B2, H, L (B2's is the one the others share)
+  int slot_of_job[5] = {1, 2, 0, 4, 3};  // workspace of A, B1, B2, H, L (slot 0 is the one the others share)
+  const int jobq[5] = {0, 1, 2, 4, 3};   // job -> query index
+  auto job_slice = [&](int j, size_t &lo, size_t &hi) {
+    query_slice(d, m, jobq[j], spans[2 * jobq[j]], spans[2 * jobq[j] + 1], world, lo, hi);
+  };
+  // The preparation (digits, counting sort, task lists) of the w-driven MSMs is made once, in workspace 0, by B2 - or by
+  // B1 when this call has no part in B2 (per-query sharding) - and reused by the others whose slice is the same range of w.
+  int producer = 2;
+  {
+    size_t lo, hi;
+    job_slice(2, lo, hi);
+    if (hi <= lo) {
+      producer = 1;
+      slot_of_job[1] = 0;
+      slot_of_job[2] = 2;
+    }
+  }
   // every tail reports its own status and message (it runs on another thread, whose thread-local error slot this thread
   // cannot see); a failed tail fails the proof
   struct TailResult { int rc = 0; std::string err; };
@@ -950,6 +992,14 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   double t2 = t1;
   for (int jj = 0; jj < 5 && rc_all == 0; jj++) {
     const int j = order[jj];
+    size_t lo, hi;
+    job_slice(j, lo, hi);
+    unsigned char *o = partials + outoff[j];
+    if (hi <= lo) {  // no part in this MSM: O, so that any set of partial results sums to the proof
+      B200_CHECK(group_zero(curve, j == 2 ? 2 : 1, o));
+      if (j == 1 && r_b1_out && r_b1_out != o) B200_CHECK(group_zero(curve, 1, r_b1_out));
+      continue;
+    }
     if (j == 3 && !d_h_external) {  // H needs the witness map (unless the caller computed it elsewhere)
       double a = now_ms();
       const char *abc = in + (m + 1) * 96;
@@ -960,11 +1010,7 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
       t2 = t1 + (now_ms() - a);
       if (rc_all) break;
     }
-    unsigned char *o = partials + outoff[j];
     const Job &J = jobs[j];
-    const int jobq[5] = {0, 1, 2, 4, 3};  // job -> query index
-    size_t lo, hi;
-    query_slice(d, m, jobq[j], rank, rank_end, world, lo, hi);
     double a = now_ms();
     MsmTail tail;
     msm_select_slot(slot_of_job[j]);
@@ -975,11 +1021,14 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     // re-indexed for it instead of being rebuilt (MsmShare)
     const bool merges = use_precompute() && p->pre.dedup[j].merged > 0;
     MsmShare share;
-    if (use_precompute() && !merges && hi > lo && p->pre.plan[j].c == p->pre.plan[2].c && share_prep_enabled()) {
+    if (use_precompute() && !merges && j != producer && j != 3 && p->pre.plan[j].c == p->pre.plan[producer].c &&
+        share_prep_enabled()) {
       size_t lo1, hi1;
-      query_slice(d, m, 2, rank, rank_end, world, lo1, hi1);
-      if (j == 0 || j == 1) share.slot = 0;
-      if (j == 4 && hi1 > lo1) {
+      job_slice(producer, lo1, hi1);
+      const bool producer_ok = hi1 > lo1 && !(p->pre.dedup[producer].merged > 0);
+      if (producer_ok && (j == 0 || j == 1 || j == 2) && lo == lo1 && hi == hi1) share.slot = 0;
+      // L's points [lo, hi) read w[lo + 2, hi + 2): inside the producer's range of w, and laid out as query_slice cuts it
+      if (producer_ok && j == 4 && lo + 2 >= lo1 && hi + 2 <= hi1) {
         share.slot = 0;
         share.n_src = (uint32_t)(hi1 - lo1);
         share.shift = (uint32_t)(lo + 2 - lo1);
@@ -1038,23 +1087,31 @@ int b200_prove_partial_span(b200_params *p, const void *h_input, size_t input_by
 }
 int b200_prove_partial_ext(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
                            const void *d_h_coefficients, void *h_partials, size_t *partial_bytes, b200_prove_timings *timings) {
+  const int spans[10] = {rank, rank_end, rank, rank_end, rank, rank_end, rank, rank_end, rank, rank_end};
+  return b200_prove_partial_queries(p, h_input, input_bytes, spans, world, 0, d_h_coefficients, h_partials, partial_bytes, timings);
+}
+int b200_prove_partial_queries(b200_params *p, const void *h_input, size_t input_bytes, const int *spans, int world,
+                               int b1_scaled, const void *d_h_coefficients, void *h_partials, size_t *partial_bytes,
+                               b200_prove_timings *timings) {
   B200_CHECK(require_device());
-  B200_CHECK(prove_partials(p, h_input, input_bytes, rank, rank_end, world, (unsigned char *)h_partials, timings, d_h_coefficients));
+  unsigned char *part = (unsigned char *)h_partials;
+  if (b1_scaled) {
+    unsigned char r[96];
+    if (input_bytes < 96) return set_error(-4, "input image has %zu bytes", input_bytes);
+    B200_CUDA_CHECK(cudaMemcpy(r, (const unsigned char *)h_input + input_bytes - 96, 96, cudaMemcpyDefault));
+    B200_CHECK(prove_partials(p, h_input, input_bytes, spans, world, part, timings, d_h_coefficients, r,
+                              part + proj_bytes(p->curve, 1)));  // the B1 slot is scaled in place by its own tail
+  } else {
+    B200_CHECK(prove_partials(p, h_input, input_bytes, spans, world, part, timings, d_h_coefficients));
+  }
   if (partial_bytes) *partial_bytes = partial_size(p->curve);
   return 0;
 }
 int b200_prove_partial_scaled(b200_params *p, const void *h_input, size_t input_bytes, int rank, int rank_end, int world,
                               const void *d_h_coefficients, void *h_partials, size_t *partial_bytes,
                               b200_prove_timings *timings) {
-  B200_CHECK(require_device());
-  unsigned char r[96];
-  if (input_bytes < 96) return set_error(-4, "input image has %zu bytes", input_bytes);
-  B200_CUDA_CHECK(cudaMemcpy(r, (const unsigned char *)h_input + input_bytes - 96, 96, cudaMemcpyDefault));
-  unsigned char *part = (unsigned char *)h_partials;
-  B200_CHECK(prove_partials(p, h_input, input_bytes, rank, rank_end, world, part, timings, d_h_coefficients, r,
-                            part + proj_bytes(p->curve, 1)));  // the B1 slot is scaled in place by its own tail
-  if (partial_bytes) *partial_bytes = partial_size(p->curve);
-  return 0;
+  const int spans[10] = {rank, rank_end, rank, rank_end, rank, rank_end, rank, rank_end, rank, rank_end};
+  return b200_prove_partial_queries(p, h_input, input_bytes, spans, world, 1, d_h_coefficients, h_partials, partial_bytes, timings);
 }
 
 // C = Ht + Lt + r*Bt1 (main.cpp:253), then A | B | C in wire format (main.cpp:94-100)
@@ -1103,7 +1160,8 @@ int b200_prove(b200_params *p, const void *h_input, size_t input_bytes, void *h_
   unsigned char r[96];  // the input image may live in host or device memory
   if (input_bytes < 96) return set_error(-4, "input image has %zu bytes", input_bytes);
   B200_CUDA_CHECK(cudaMemcpy(r, (const unsigned char *)h_input + input_bytes - 96, 96, cudaMemcpyDefault));
-  B200_CHECK(prove_partials(p, h_input, input_bytes, 0, 1, 1, part.data(), timings, nullptr, r, r_b1.data()));
+  const int whole[10] = {0, 1, 0, 1, 0, 1, 0, 1, 0, 1};
+  B200_CHECK(prove_partials(p, h_input, input_bytes, whole, 1, part.data(), timings, nullptr, r, r_b1.data()));
   double t1 = now_ms();
   B200_CHECK(combine_partials(p->curve, part.data(), 1, r, r_b1.data(), h_out, out_bytes));
   if (timings) {
@@ -1221,6 +1279,9 @@ class ProofWorker {
 
 int run_proof_job(b200_proof_job *j) {
   if (!j->key || !j->h_input || !j->h_out) return set_error(-1, "proof job: null key, input or output");
+  if (j->world > 1 && j->query_spans)
+    return b200_prove_partial_queries(j->key, j->h_input, j->input_bytes, j->query_spans, j->world, j->b1_scaled,
+                                      j->d_h_coefficients, j->h_out, &j->out_bytes, &j->timings);
   if (j->world > 1 && j->b1_scaled)
     return b200_prove_partial_scaled(j->key, j->h_input, j->input_bytes, j->rank, j->rank_end > j->rank ? j->rank_end : j->rank + 1,
                                      j->world, j->d_h_coefficients, j->h_out, &j->out_bytes, &j->timings);

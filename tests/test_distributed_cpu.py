@@ -126,10 +126,13 @@ def _worker_plan(rank, world, port, mode, ret):
     proof_len = [b200.proof_bytes(c) for c, _ in cases]
     slot = [max(a, b) for a, b in zip(pbytes, proof_len)]
     jobs = bench.rank_jobs(rank, world, mode)
+    spans = bench.rank_spans(rank, world, mode)
     outs, r_fr = [], [util.golden(c, k)[1][-96:] for c, k in cases]
     for i, first, units, end in jobs:
         curve, k = cases[i]
-        if i == 0:
+        if i == 0 and i in spans:
+            outs.append(_oracle_partials_queries(b200, O, curve, k, spans[i], units))
+        elif i == 0:
             outs.append(_oracle_partials_span(b200, O, curve, k, first, end, units))
         else:
             params, inp, _ = util.golden(curve, k)
@@ -167,7 +170,54 @@ def _oracle_partials_span(b200, O, curve, k, first, end, units):
     return part
 
 
-@pytest.mark.parametrize("mode", ["dedicated", "balanced"])
+def _oracle_partials_queries(b200, O, curve, k, spans, units):
+    """oracle partial sums with one run of slices PER QUERY (b200_prove_partial_queries): spans in the order A, B1, B2, L,
+    H; an empty run gives O; slots in the order of the partial-sum blob (A, B1, B2, H, L)"""
+    params, inp, _ = util.golden(curve, k)
+    d, m, q = util.split_params(curve, params)
+    x = util.split_input(inp, d, m)
+    H = util.orc_compute_h(O, curve, d, x["ca"], x["cb"], x["cc"])
+    cut = lambda n, r: n if r >= units else r * (n // units)
+
+    def w_range(span):
+        return cut(m + 1, span[0]), cut(m + 1, span[1])
+    lo3, hi3 = w_range(spans[3])
+    lo3, hi3 = max(lo3 - 2, 0), min(max(hi3 - 2, 0), m - 1)
+    jobs = [(1, x["w"], q["A"], *w_range(spans[0]), 0), (1, x["w"], q["B1"], *w_range(spans[1]), 0),
+            (2, x["w"], q["B2"], *w_range(spans[2]), 0), (1, H, q["H"], cut(d, spans[4][0]), cut(d, spans[4][1]), 0),
+            (1, x["w"], q["L"], lo3, max(hi3, lo3), 2)]
+    part = b""
+    for group, sc, pts, lo, hi, shift in jobs:
+        ab = b200.affine_bytes(curve, group)
+        if hi <= lo:
+            part += b200.g_from_affine(curve, group, bytes(ab))   # O
+            continue
+        out = ctypes.create_string_buffer(b200.proj_bytes(curve, group))
+        sb, pb = util.buf(sc[(lo + shift) * 96:(hi + shift) * 96]), util.buf(pts[lo * ab:hi * ab])
+        O.orc_msm(curve, group, ctypes.addressof(sb), ctypes.addressof(pb), hi - lo, ctypes.addressof(out), 1)
+        part += out.raw
+    return part
+
+
+def test_per_query_plans_tile_every_msm():
+    import bench
+    U = bench.PLAN_UNITS
+    for world in range(2, 9):
+        spans, load = bench.query_plan(world)
+        assert len(spans) == world and len(load) == world
+        for qi in range(5):
+            runs = sorted(sp[qi] for sp in spans if sp and sp[qi][1] > sp[qi][0])
+            assert runs[0][0] == 0 and runs[-1][1] == U and all(a[1] == b[0] for a, b in zip(runs, runs[1:])), (world, qi, runs)
+        mode, runs, small = bench.step_plan(world, "queries")
+        assert mode == "queries" and small == world - 1
+        assert [r for r in range(world) if runs[r][1] > runs[r][0]] == [r for r in range(world) if spans[r]]
+        # the per-query plan must not be worse than cutting every MSM evenly under its own model
+        even = max(sum(bench.slice_cost_ms(q, U // world) for q in bench.QUERY_ORDER) + bench.QUERY_MODEL["rank_fixed"]
+                   for _ in range(1))
+        assert max(load) <= even + bench.QUERY_MODEL["mnt6_whole"]
+
+
+@pytest.mark.parametrize("mode", ["dedicated", "balanced", "queries"])
 def test_two_rank_step_plans(mode):
     import bench
     U = bench.PLAN_UNITS
@@ -184,6 +234,6 @@ def test_two_rank_step_plans(mode):
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29950 + (os.getpid() % 40) + (0 if mode == "dedicated" else 41)
+    port = 29950 + (os.getpid() % 40) + {"dedicated": 0, "balanced": 41, "queries": 82}[mode]
     mp.spawn(_worker_plan, args=(world, port, mode, ret), nprocs=world, join=True)
     assert ret.get("ok") is True

@@ -389,6 +389,23 @@ def test_sharded_prover_matches_reference_golden(b200, dev, precompute, curve, a
     runs = [(0, 36), (36, 36), (36, 61), (61, 64)]
     parts = b"".join(P.prove_partial(inp, lo, 64, hi)[0] for lo, hi in runs)
     assert b200.prove_combine(curve, parts, len(runs), inp[-FE:]) == expected
+    # per-query sharding (b200_prove_partial_queries): every MSM cut on its own, some GPUs without a part in some MSMs
+    # (A, B1, B2, L, H): whole MSMs, B2 in three pieces, L cut off the slice grid of the others, H whole on one rank,
+    # a rank with nothing at all
+    plans = [[(0, 64), (0, 0), (0, 20), (50, 64), (0, 0)],
+             [(0, 0), (0, 64), (20, 41), (0, 0), (0, 64)],
+             [(0, 0), (0, 0), (41, 64), (0, 50), (0, 0)],
+             [(0, 0), (0, 0), (0, 0), (0, 0), (0, 0)]]
+    parts = b"".join(P.prove_partial_queries(inp, sp, 64)[0] for sp in plans)
+    assert b200.prove_combine(curve, parts, len(plans), inp[-FE:]) == expected
+    parts = b"".join(P.prove_partial_queries(inp, sp, 64, b1_scaled=True)[0] for sp in plans)
+    assert b200.prove_combine(curve, parts, len(plans), None) == expected
+    # the same slicing through b200_prove_batch jobs, and a second time on the cached tables
+    for _ in range(2):
+        parts = b"".join(b200.prove_batch([(P, inp, 0, 64, 0, None, sp)], b1_scaled=True)[0] for sp in plans[:3])
+        assert b200.prove_combine(curve, parts, 3, None) == expected
+    with pytest.raises(b200.B200Error, match="bad slice run"):
+        P.prove_partial_queries(inp, [(0, 65)] + [(0, 0)] * 4, 64)
     # the witness map computed outside the call (what bench.py does when it splits compute_H over three ranks)
     import torch
     d, m = P.d, P.m
