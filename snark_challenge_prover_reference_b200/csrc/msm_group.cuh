@@ -1082,8 +1082,11 @@ int msm_run_deferred(const void *d_scalars, const void *d_points, size_t n, void
 // built when the key is loaded, like the reference parses and stores the key before its timer starts (main.cpp:200-203).
 // (launch bounds: left alone ptxas takes 216-236 registers - 2 warps per scheduler, the multiplier ~60 % busy; every
 // multiplication / squaring body is out of line and fits 128 registers without spills, the kernel itself spills < 1 KB)
+#ifndef B200_PRE_BLOCKS_G2
+#define B200_PRE_BLOCKS_G2 3
+#endif
 template <class G, int MAXW>
-__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : 3) msm_precompute_kernel(const Affine<typename G::F> *__restrict__ points, uint32_t n,
+__global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : B200_PRE_BLOCKS_G2) msm_precompute_kernel(const Affine<typename G::F> *__restrict__ points, uint32_t n,
                                                              int W, const uint32_t *__restrict__ plan,
                                                              Affine<typename G::F> *__restrict__ table) {
   typedef typename G::F F;
