@@ -556,7 +556,9 @@ __global__ void __launch_bounds__(128) msm_sum_kernel(const Proj<typename G::F> 
 // 3 additions per chunk in total, log2(per) steps of one addition each. The host finishes
 //   S + K * (O_0 + 2 (O_1 + 2 (...)))   (log2(nb) doublings, msm_host_phase).
 #ifndef B200_RED_BLOCKS_G2
-#define B200_RED_BLOCKS_G2 1  // resident blocks per SM asked of the G2 instantiations (1: ptxas' choice, ~255 registers)
+// resident blocks per SM asked of the G2 instantiations; measured at 2^20 buckets: ptxas' own choice (255 registers)
+// 20.5 ms, 3 blocks 18.9 ms, 4 blocks 20.5 ms
+#define B200_RED_BLOCKS_G2 3
 #endif
 template <class G>
 __global__ void __launch_bounds__(128, G::F::kDegree == 1 ? 4 : B200_RED_BLOCKS_G2) msm_reduce_rows_kernel(const Proj<typename G::F> *__restrict__ buckets, uint32_t per,
