@@ -829,7 +829,7 @@ def b200_arm(args):
                        "files": "tools/synth_key output in the reference's formats; the reference arm proves the same files",
                        "l2": "inputs larger than L2: each step streams >1.6 GB of bases and 416 MB of scalars",
                        "key": "synthetic multiples of the generators with the duplicate / infinity structure of real keys",
-                       "multi_gpu": {"mode": mode, "mnt4753_runs_of_%d" % PLAN_UNITS: runs, "mnt6753_rank": small_rank,
+                       "multi_gpu": {"mode": mode, "mnt4753_runs_of_%d" % PLAN_UNITS: None if mode == "queries" else runs, "mnt6753_rank": small_rank,
                                      "rank_busy_ms_per_step": rank_busy_ms,
                                      "per_query_runs_A_B1_B2_L_H": query_plan(world)[0] if mode == "queries" else None,
                                      "witness_map": ("on the ranks with a part of H" if mode == "queries" else
