@@ -316,7 +316,9 @@ def step_plan(world, mode=None):
 QUERY_ORDER = ("A", "B1", "B2", "L", "H")          # the order of b200_params_query / of the spans
 QUERY_MODEL = {"acc": {"A": 24.3, "B1": 49.3, "B2": 146.0, "L": 49.3, "H": 49.3},
                "red": {"A": 5.9, "B1": 5.9, "B2": 20.5, "L": 5.9, "H": 5.9},
-               "sliced_extra": {"B2": 6.0},   # measured on single-GPU emulations of the plans (tools/profile_plan.py)
+               # a slice of B2 costs more than its parts: +7.9 ms at 20/64, +3.3 ms at 40/64, 0 whole (single-GPU
+               # emulations of the plans, tools/profile_plan.py): 11 ms x (1 - f)
+               "sliced_extra": {"B2": 11.0},
                "compute_h": 13.0, "prep": 1.3, "rank_fixed": 3.0, "mnt6_whole": 38.0}
 
 
@@ -332,8 +334,7 @@ def slice_cost_ms(q, units, model=None):
     c = max(8, round(21 + math.log2(f)))
     windows = -(-754 // c)
     t = M["acc"][q] * f * windows / 36.0 + M["red"][q] * max(0.3, 2.0 ** (c - 21)) + M["prep"]
-    if units < PLAN_UNITS:
-        t += M.get("sliced_extra", {}).get(q, 0.0)
+    t += M.get("sliced_extra", {}).get(q, 0.0) * (1.0 - f)
     return t + (M["compute_h"] if q == "H" else 0.0)
 
 
