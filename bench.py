@@ -316,9 +316,9 @@ def step_plan(world, mode=None):
 QUERY_ORDER = ("A", "B1", "B2", "L", "H")          # the order of b200_params_query / of the spans
 QUERY_MODEL = {"acc": {"A": 24.3, "B1": 49.3, "B2": 146.0, "L": 49.3, "H": 49.3},
                "red": {"A": 5.9, "B1": 5.9, "B2": 20.5, "L": 5.9, "H": 5.9},
-               # a slice of B2 costs more than its parts: +7.9 ms at 20/64, +3.3 ms at 40/64, 0 whole (single-GPU
-               # emulations of the plans, tools/profile_plan.py): 11 ms x (1 - f)
-               "sliced_extra": {"B2": 11.0},
+               # a slice of B2 costs more than its parts (single-GPU emulations of the plans, tools/profile_plan.py and
+               # profile_spans.py): ~+3 ms at 19/64 and at 40/64, 0 whole: 5 ms x (1 - f)
+               "sliced_extra": {"B2": 5.0},
                "compute_h": 13.0, "prep": 1.3, "rank_fixed": 3.0, "mnt6_whole": 38.0}
 
 
@@ -718,7 +718,7 @@ def b200_arm(args):
         """which accumulation kernel the library picks (msm_affine_wins in msm.cu)"""
         if lib_mode != "auto":
             return lib_mode
-        return "affine" if kind == "g2_fq2" and entries >= (8 << 20) else "xyzz"
+        return "affine" if kind == "g2_fq2" and entries >= (20 << 20) else "xyzz"
     iso = {"g1": [], "g2": [], "a_merged": []}
     plans = {}
     if world == 1:

@@ -45,7 +45,9 @@ void msm_set_batch_affine(int on) { g_batch_affine = on < 0 || on > 2 ? 2 : on; 
 // Measured on B200 (profiles/r02_summary.md): the batch-affine rounds beat the XYZZ kernel for G2 over Fq2 once a bucket
 // set holds millions of entries (2^20 points: 145 vs 157 ms); for G1 the two are within 1 %, and for small MSMs the
 // ~7 dependent rounds (one inversion latency each) lose to the single XYZZ launch (2^15 points: 9.3 vs 2.8 ms).
-bool msm_affine_wins(int degree, size_t entries) { return degree == 2 && entries >= ((size_t)8 << 20); }
+// A 19/64 slice of the MNT4753 B2 query (12.4 M entries, what a GPU of the 8-GPU plan gets): 56.3 ms against 53.7 ms for
+// XYZZ - the threshold sits between that and the 24.9 M entries of a 40/64 slice.
+bool msm_affine_wins(int degree, size_t entries) { return degree == 2 && entries >= ((size_t)20 << 20); }
 // Lane-cooperative bucket reduction (coop.cuh): B200_COOP=0 never, 1 always, default: bucket sets of at most 2^18 buckets,
 // where the reduction is a latency problem (sharded proofs, the MNT6753 proof); at 2^20 buckets it is a throughput
 // problem and the thread-per-chunk kernel does the same work with all 32 lanes.
@@ -56,11 +58,13 @@ bool msm_affine_wins(int degree, size_t entries) { return degree == 2 && entries
 // So: only when this is the only proof in flight (b200_prove_batch notes how many it runs).
 static std::atomic<int> g_concurrent_proofs{1};
 void msm_note_concurrent_proofs(int n) { g_concurrent_proofs = n; }
-bool msm_use_coop(size_t total_buckets) {
+// G2 over Fq2 at 2^18 buckets (the 19/64 slice of B2): 9.5 ms cooperative against 7.6 ms with a thread per chunk, so its
+// limit is one bit lower.
+bool msm_use_coop(size_t total_buckets, int degree) {
   static const int mode = getenv("B200_COOP") ? atoi(getenv("B200_COOP")) : 2;
   if (mode == 0) return false;
   if (mode == 1) return true;
-  return total_buckets <= ((size_t)1 << 18) && g_concurrent_proofs <= 1;
+  return total_buckets <= ((size_t)1 << (degree == 2 ? 17 : 18)) && g_concurrent_proofs <= 1;
 }
 // B200_AFF_SPLIT=1: cut large batch-affine rounds into an 80 % and a 20 % region (see AffRegions) to fill the tail of the
 // single wave. Measured on B200 and left off: the second region's shorter batches pay more per addition for the shared

@@ -823,7 +823,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
   static const bool planes_env = getenv("B200_REDUCE_PLANES") ? atoi(getenv("B200_REDUCE_PLANES")) != 0 : true;
   if (W == 1 && planes_env) {
     // one bucket set: chunk sums + bit-plane tree (msm_reduce_rows_kernel), thread per chunk or lane group per chunk
-    const bool coop = msm_use_coop(nb);
+    const bool coop = msm_use_coop(nb, F::kDegree);
     typedef CoopTables<G> CT;
     constexpr int LG = CT::kLanes, groups_per_block = 128 / LG;
     const size_t smem_red = groups_per_block * coop_group_bytes<G>(3), smem_step = groups_per_block * coop_group_bytes<G>(2);
@@ -885,7 +885,7 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
     plan.red_K = K;
     nout = (size_t)rows - 1;  // S, O_0 .. O_{planes-1}
     cur += 1;                 // (skip X: the sum of all buckets carries weight 0)
-  } else if (msm_use_coop((size_t)W * nb)) {
+  } else if (msm_use_coop((size_t)W * nb, F::kDegree)) {
     // lane-cooperative reduction (coop.cuh): a group of 8 / 16 / 32 lanes per chunk. The chunk length makes the chunks
     // about one wave of resident groups: short dependent chains, no second wave.
     typedef CoopTables<G> CT;

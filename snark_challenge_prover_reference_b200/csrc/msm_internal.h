@@ -138,7 +138,7 @@ bool msm_use_batch_affine();
 int msm_accum_mode();
 bool msm_affine_wins(int degree, size_t entries);
 bool msm_affine_split_tail();
-bool msm_use_coop(size_t total_buckets);
+bool msm_use_coop(size_t total_buckets, int degree);
 void msm_note_concurrent_proofs(int n);
 constexpr uint32_t kFoldWidth = 32;  // a bucket with more task sums than this is folded in parallel first
 int msm_fold_level(const uint32_t *cnt_in, uint32_t nbuckets, uint32_t width, uint32_t *cnt_out, uint32_t *off_out,
