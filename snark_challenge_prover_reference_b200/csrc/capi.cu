@@ -909,6 +909,10 @@ int b200_msm_wait(b200_msm_pending *pending) {
 
 // Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
 // multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
+// Called once by prove_partials on the issuing thread when all of a proof's MSMs have been issued (b200_prove_batch uses
+// it to start the next proof of a batch at that moment instead of at time zero).
+static thread_local std::function<void()> *tl_all_issued_hook = nullptr;
+
 // h_r_fr / r_b1_out (optional, both or neither): r * (this call's B1 sum) is computed in B1's host tail, i.e. while the
 // GPU is still busy with the L and H MSMs, instead of serially after the join (753 doublings on one core).
 // spans: per query (0 A, 1 B1, 2 B2, 3 L, 4 H) the run [first, end) of `world` slices this call sums; an empty run
@@ -1054,6 +1058,11 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
     *J.ms = now_ms() - a;
   }
   msm_select_slot(0);
+  if (tl_all_issued_hook) {
+    std::function<void()> *hook = tl_all_issued_hook;
+    tl_all_issued_hook = nullptr;
+    (*hook)();
+  }
   double t_join = now_ms();
   std::string issue_err = rc_all ? last_error() : std::string();
   for (auto &f : tails) {
@@ -1294,11 +1303,15 @@ int run_proof_job(b200_proof_job *j) {
 
 int b200_prove_batch(b200_proof_job *jobs, int count) {
   B200_CHECK(require_device());
-  struct ConcurrencyNote {  // several proofs in flight: the GPU is throughput-bound, see msm_use_coop
-    int n;
-    explicit ConcurrencyNote(int k) : n(k) { msm_note_concurrent_proofs(n); }
+  // Staggered start (default; B200_BATCH_STAGGER=0: all jobs start together): job i+1 starts when job i has ISSUED all
+  // its MSMs, i.e. when the GPU is working through the last accumulations and the latency-bound end of job i. Started
+  // together, a small proof's short kernels get no free multiplier cycles next to the large proof's accumulations and
+  // take register-file space from them: MNT4753 2^20 alone 370 ms + MNT6753 2^15 alone 34 ms, both started together 409 ms.
+  static const bool stagger = !(getenv("B200_BATCH_STAGGER") && getenv("B200_BATCH_STAGGER")[0] == '0');
+  struct ConcurrencyNote {  // several proofs in flight at once: the GPU is throughput-bound, see msm_use_coop
+    explicit ConcurrencyNote(int k) { msm_note_concurrent_proofs(k); }
     ~ConcurrencyNote() { msm_note_concurrent_proofs(1); }
-  } note(count);
+  } note(stagger ? 1 : count);
   constexpr int kMaxJobs = 8;
   if (!jobs || count < 1 || count > kMaxJobs) return set_error(-1, "prove_batch: count %d not in [1, %d]", count, kMaxJobs);
   for (int i = 0; i < count; i++)
@@ -1311,17 +1324,41 @@ int b200_prove_batch(b200_proof_job *jobs, int count) {
   int dev = 0;
   B200_CUDA_CHECK(cudaGetDevice(&dev));
   std::string errs[kMaxJobs];
+  // issued[i]: job i has issued all its MSMs (or ended before getting there)
+  std::promise<void> issued[kMaxJobs];
+  std::shared_future<void> issued_f[kMaxJobs];
+  std::atomic<bool> issued_set[kMaxJobs];
+  std::function<void()> hooks[kMaxJobs];
+  for (int i = 0; i < count; i++) {
+    issued_f[i] = issued[i].get_future().share();
+    issued_set[i] = false;
+    std::promise<void> *pr = &issued[i];
+    std::atomic<bool> *flag = &issued_set[i];
+    hooks[i] = [pr, flag] {
+      if (!flag->exchange(true)) pr->set_value();
+    };
+  }
   for (int i = 1; i < count; i++) {
     if (!pool[i]) pool[i] = new ProofWorker();
     b200_proof_job *j = &jobs[i];
     std::string *err = &errs[i];
-    pool[i]->submit([j, err, dev] {
+    std::function<void()> *hook = &hooks[i];
+    std::shared_future<void> before = issued_f[i - 1];
+    const bool wait_first = stagger;
+    pool[i]->submit([j, err, dev, hook, before, wait_first] {
+      if (wait_first) before.wait();
       cudaError_t e = cudaSetDevice(dev);
+      tl_all_issued_hook = hook;
       j->status = e == cudaSuccess ? run_proof_job(j) : set_error(-2, "cudaSetDevice: %s", cudaGetErrorString(e));
+      tl_all_issued_hook = nullptr;
+      (*hook)();  // (a job that failed before issuing must not block its successor)
       if (j->status) *err = last_error();
     });
   }
+  tl_all_issued_hook = &hooks[0];
   jobs[0].status = run_proof_job(&jobs[0]);
+  tl_all_issued_hook = nullptr;
+  hooks[0]();
   if (jobs[0].status) errs[0] = last_error();
   for (int i = 1; i < count; i++) pool[i]->wait();
   for (int i = 0; i < count; i++)
