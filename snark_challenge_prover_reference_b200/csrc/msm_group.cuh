@@ -841,20 +841,16 @@ int msm_gpu_phase(const void *d_scalars, const void *d_points, size_t n, MsmPlan
       }
       resident[coop] = (uint32_t)((per_sm > 0 ? per_sm : 1) * sms * (coop ? groups_per_block : 128));
     }
-    // chunk length K. In units of one point addition of latency: the dependent chain is 2K + log2(nb / K) additions; the
-    // work is (2 + 3 / K) additions per bucket, and a GPU full of resident chunks retires `resident` additions in about
-    // phi latencies (the multiplier is shared: measured 2^20 G1 buckets at K = 2, 3.5 additions per bucket, 5.9 ms at 92 %
-    // multiplier utilisation = 1.7 ns per addition against 55 us alone; a cooperative addition is ~5x shorter and uses
-    // ~1.75x the multiplier time). The slower of the two bounds decides; ties go to the longer chunk.
-    const double phi = coop ? 4.0 : 2.5;
-    uint32_t K = coop ? 4 : 2;
-    double best = 1e30;
+    // chunk length: the dependent chain is waves * 2K additions + log2(per) tree levels; ties go to the longer chunk
+    // ((2K + 3) / K additions per bucket). (A second estimate that also charges the multiplier time of the extra
+    // additions of short chunks picked K = 16 instead of 2 for 2^20 G1 buckets - 5.70 against 5.94 ms - but longer chunks
+    // for the small bucket sets too: MNT6753 proof 34.1 -> 37.1 ms, a 1/7 share of MNT4753 81.7 -> 82.6 ms. Not kept.)
+    uint32_t K = coop ? 4 : 2, best = 0xffffffffu;
     for (uint32_t k = K; k <= 64 && k <= nb; k <<= 1) {
-      const uint32_t chunks = nb / k;
+      const uint32_t chunks = nb / k, waves = (chunks + resident[coop] - 1) / resident[coop];
       uint32_t lg = 0;
       while ((1u << lg) < chunks) lg++;
-      const double chain = 2.0 * k + lg, work = (2.0 + 3.0 / k) * (double)nb / (double)resident[coop] * phi;
-      const double est = chain > work ? chain : work;
+      const uint32_t est = waves * 2 * k + lg;
       if (est <= best) {
         best = est;
         K = k;
