@@ -204,7 +204,8 @@ int b200_prove_combine(int curve, const void *h_partials_all, int world, const v
 /* Several proofs in flight on the current device: job 0 runs on the calling thread, every further job on a
  * persistent worker thread with its own streams and workspaces, so a small proof (MNT6753, 2^15 constraints) runs
  * underneath a large one (MNT4753, 2^20). world <= 1: a finished proof in h_out (as b200_prove); world > 1: this
- * rank's partial sums (as b200_prove_partial). At most 8 jobs; the keys must be distinct objects. Replaces running
+ * rank's partial sums (as b200_prove_partial; query_spans / b1_scaled select the _queries / _scaled variants). At most
+ * 8 jobs; the keys must be distinct objects. Replaces running
  * the reference driver once per curve (cuda_prover_piecewise.cu:100-121). */
 typedef struct {
   b200_params *key;
