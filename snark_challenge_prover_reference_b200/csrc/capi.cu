@@ -970,7 +970,8 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
   static const int h_first_env = getenv("B200_H_FIRST") ? atoi(getenv("B200_H_FIRST")) : -1;
   const bool h_first = h_first_env >= 0 ? h_first_env != 0 : false;
   const int order_default[5] = {2, 0, 1, 4, 3}, order_h_first[5] = {3, 2, 0, 1, 4};
-  const int *order = h_first ? order_h_first : order_default;
+  int order[5];
+  memcpy(order, h_first ? order_h_first : order_default, sizeof(order));
   int slot_of_job[5] = {1, 2, 0, 4, 3};  // workspace of A, B1, B2, H, L (slot 0 is the one the others share)
   const int jobq[5] = {0, 1, 2, 4, 3};   // job -> query index
   auto job_slice = [&](int j, size_t &lo, size_t &hi) {
@@ -986,6 +987,8 @@ static int prove_partials(b200_params *p, const void *h_input, size_t input_byte
       producer = 1;
       slot_of_job[1] = 0;
       slot_of_job[2] = 2;
+      for (int k = 0; k < 5; k++)  // the producer is issued before the MSMs that consume its preparation: B1 before A
+        if (order[k] == 0 || order[k] == 1) order[k] ^= 1;
     }
   }
   // every tail reports its own status and message (it runs on another thread, whose thread-local error slot this thread

@@ -406,6 +406,19 @@ def test_sharded_prover_matches_reference_golden(b200, dev, precompute, curve, a
         assert b200.prove_combine(curve, parts, 3, None) == expected
     with pytest.raises(b200.B200Error, match="bad slice run"):
         P.prove_partial_queries(inp, [(0, 65)] + [(0, 0)] * 4, 64)
+    # a key whose A query has no equal bases (here: a copy of B1), so that A takes part in the shared preparation, and a
+    # rank without a part in B2: B1 then makes the preparation that A and L reuse. Expected proof from the oracle.
+    d0, m0, q = util.split_params(curve, params)
+    g1 = 2 * FE
+    plain = params[:16] + q["B1"] + params[16 + (m0 + 1) * g1:]
+    assert len(plain) == len(params)
+    want = util.orc_prove(util.load_oracle(), curve, plain, inp)
+    Q = b200.Params.from_bytes(curve, plain)
+    assert Q.prove(inp) == want
+    plans = [[(0, 64), (0, 64), (0, 0), (0, 64), (0, 0)], [(0, 0), (0, 0), (0, 64), (0, 0), (0, 64)]]
+    parts = b"".join(Q.prove_partial_queries(inp, sp, 64, b1_scaled=True)[0] for sp in plans)
+    assert b200.prove_combine(curve, parts, 2, None) == want
+    Q.close()
     # the witness map computed outside the call (what bench.py does when it splits compute_H over three ranks)
     import torch
     d, m = P.d, P.m
