@@ -907,12 +907,12 @@ int b200_msm_wait(b200_msm_pending *pending) {
   return 0;
 }
 
-// Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
-// multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
-// Called once by prove_partials on the issuing thread when all of a proof's MSMs have been issued (b200_prove_batch uses
-// it to start the next proof of a batch at that moment instead of at time zero).
+// Called once by prove_partials on the issuing thread when all of a proof's MSMs have been issued (b200_prove_batch can
+// start the next proof of a batch at that moment instead of at time zero: B200_BATCH_STAGGER).
 static thread_local std::function<void()> *tl_all_issued_hook = nullptr;
 
+// Partial sums of the five MSMs over this rank's slice of every point range (contiguous split like
+// multi_exp's chunks, multiexp.tcc:417-431; the last rank takes the remainder).
 // h_r_fr / r_b1_out (optional, both or neither): r * (this call's B1 sum) is computed in B1's host tail, i.e. while the
 // GPU is still busy with the L and H MSMs, instead of serially after the join (753 doublings on one core).
 // spans: per query (0 A, 1 B1, 2 B2, 3 L, 4 H) the run [first, end) of `world` slices this call sums; an empty run
