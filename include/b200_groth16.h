@@ -103,9 +103,6 @@ int b200_host_jacobian_doublings(int curve, int group, const void *h_xy, int k, 
  * 6 inv by the bitwise binary gcd (the device's routine, run on the host) 7 inv by the batched binary gcd (what op 3
  * uses on the host) 8 inv by Fermat's little theorem */
 int b200_host_fp_op(int tag, int op, const void *h_a, const void *h_b, void *h_r);
-/* host only (test hook): `bytes` bytes at `file_offset` of a file into host memory through the loaders' multi-threaded
- * reader (b200_params_from_file / b200_file_to_device read their 64 MB chunks with it) */
-int b200_host_read_file(const char *path, size_t file_offset, void *h_dst, size_t bytes);
 
 /* ---- proving key resident on the device + whole-proof entry point ------------------------------------------ */
 typedef struct b200_params b200_params;

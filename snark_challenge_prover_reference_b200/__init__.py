@@ -139,7 +139,6 @@ _SIGNATURES = {
     "b200_prove_partial_queries": (_i, [_vp, _vp, _sz, ctypes.POINTER(_i), _i, _i, _vp, _vp, ctypes.POINTER(_sz),
                                         ctypes.POINTER(ProveTimings)]),
     "b200_params_precompute_queries": (_i, [_vp, ctypes.POINTER(_i), _i]),
-    "b200_host_read_file": (_i, [ctypes.c_char_p, _sz, _vp, _sz]),
     "b200_prove_combine": (_i, [_i, _vp, _i, _vp, _vp, ctypes.POINTER(_sz)]),
     "b200_dev_fp_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),
     "b200_dev_fqe_op": (_i, [_i, _i, _vp, _vp, _vp, _sz]),

@@ -8,12 +8,8 @@
 #include <memory>
 #include <mutex>
 #include <thread>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <vector>
-#include <fcntl.h>
-#include <unistd.h>
 #include "../../include/b200_groth16.h"
 #include "common.cuh"
 #include "curve.cuh"
@@ -631,64 +627,18 @@ StagePool &stage_pool() {
   return *pool;
 }
 }  // namespace
-// n bytes at file offset `off` into dst, read by several threads at once: one thread copies out of the page cache at
-// ~4 GB/s, eight at ~20 GB/s (measured on the build host), and the reads are what the loaders wait for (the copies to the
-// device run underneath them). Returns the number of bytes read.
-static size_t parallel_pread(int fd, char *dst, size_t n, off_t off) {
-  static const unsigned threads = [] {
-    const unsigned hw = std::thread::hardware_concurrency();
-    const unsigned t = hw / 2;
-    return t < 1 ? 1u : (t > 8 ? 8u : t);
-  }();
-  auto read_range = [fd](char *to, size_t len, off_t at) -> size_t {
-    size_t got = 0;
-    while (got < len) {
-      const ssize_t r = pread(fd, to + got, len - got, at + (off_t)got);
-      if (r <= 0) break;
-      got += (size_t)r;
-    }
-    return got;
-  };
-  if (threads <= 1 || n < ((size_t)4 << 20)) return read_range(dst, n, off);
-  size_t part = (n + threads - 1) / threads;
-  part = (part + 4095) & ~(size_t)4095;
-  std::vector<std::thread> pool;
-  std::vector<size_t> got(threads, 0);
-  for (unsigned i = 0; i < threads; i++) {
-    const size_t lo = (size_t)i * part;
-    if (lo >= n) break;
-    const size_t len = n - lo < part ? n - lo : part;
-    pool.emplace_back([&, i, lo, len] { got[i] = read_range(dst + lo, len, off + (off_t)lo); });
-  }
-  for (auto &t : pool) t.join();
-  size_t total = 0;
-  for (size_t g : got) total += g;
-  return total;
-}
-int b200_host_read_file(const char *path, size_t file_offset, void *h_dst, size_t bytes) {
-  const int fd = open(path, O_RDONLY);
-  if (fd < 0) return set_error(-4, "cannot open %s", path);
-  const size_t got = parallel_pread(fd, (char *)h_dst, bytes, (off_t)file_offset);
-  close(fd);
-  if (got != bytes) return set_error(-4, "short read on %s: %zu of %zu bytes", path, got, bytes);
-  return 0;
-}
-
 static int stream_file_to_device(FILE *f, const char *path, void *d_dst, size_t bytes, double &read_ms, double &wait_ms) {
   StagePool &sp = stage_pool();
   std::lock_guard<std::mutex> g(sp.mu);
   B200_CHECK(sp.ensure());
   const size_t chunk = StagePool::kChunk;
-  const int fd = fileno(f);
-  const long base = ftell(f);
-  if (fd < 0 || base < 0) return set_error(-4, "cannot locate the read position in %s", path);
   int k = 0;
   for (size_t off = 0; off < bytes; off += chunk, k ^= 1) {
     const size_t n = bytes - off < chunk ? bytes - off : chunk;
     double a = now_ms();
     B200_CUDA_CHECK(cudaEventSynchronize(sp.done[k]));  // the copy that last used this buffer (no-op the first time)
     double b = now_ms();
-    if (parallel_pread(fd, (char *)sp.h[k], n, (off_t)base + (off_t)off) != n) return set_error(-4, "short read on %s", path);
+    if (fread(sp.h[k], 1, n, f) != n) return set_error(-4, "short read on %s", path);
     double c = now_ms();
     wait_ms += b - a;
     read_ms += c - b;

@@ -164,19 +164,3 @@ def test_jacobian_doubling_of_the_table_builder_matches_oracle(b200, oracle):
                 for _ in range(nd):
                     Q = util.orc_group(oracle, curve, group, 1, Q)
                 assert out.raw == util.orc_to_affine(oracle, curve, group, Q), (curve, group, nd)
-
-
-def test_loader_reader_returns_the_file_bytes(b200, tmp_path):
-    """the multi-threaded reader behind b200_params_from_file / b200_file_to_device: every byte, at odd offsets and
-    lengths, and a short file is an error"""
-    import os
-    data = os.urandom((9 << 20) + 12345)
-    path = tmp_path / "blob"
-    path.write_bytes(data)
-    for off, n in ((0, len(data)), (16, len(data) - 16), (4097, (8 << 20) + 3), (len(data) - 5, 5), (123, 0)):
-        buf = ctypes.create_string_buffer(max(n, 1))
-        b200.check(b200.lib().b200_host_read_file(str(path).encode(), off, ctypes.addressof(buf), n))
-        assert buf.raw[:n] == data[off:off + n]
-    buf = ctypes.create_string_buffer(6 << 20)
-    assert b200.lib().b200_host_read_file(str(path).encode(), len(data) - (5 << 20), ctypes.addressof(buf), 6 << 20) != 0
-    assert b200.lib().b200_host_read_file(b"/nonexistent/file", 0, ctypes.addressof(buf), 16) != 0
